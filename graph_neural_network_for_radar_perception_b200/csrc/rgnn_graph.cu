@@ -1,0 +1,563 @@
+// Graph construction on the GPU: batched exact kNN + radius degree, symmetrised row-major adjacency,
+// CSR utilities and the raw node / edge features.
+// Replaces reference modules/compute_features/graph_features.py (compute_adjacency_information :58-84,
+// _v2 :87-114, compute_knn :25-44, compute_ball_query :11-22, compute_node_features :117-144,
+// compute_edge_features :147-164) without ever forming the N x N matrices.
+#include <float.h>
+#include <limits.h>
+
+#include "rgnn_common.cuh"
+
+namespace rgnn {
+
+// ---------------------------------------------------------------------------------------------
+// device-wide exclusive scan of int32 (three small kernels; n up to 2^31)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 1024;   // elements per block (256 threads x 4)
+
+__global__ void scan_reduce_kernel(const int* __restrict__ in, int n, int* __restrict__ block_sums) {
+    __shared__ int sh[8];
+    const int base = blockIdx.x * SCAN_BLOCK;
+    int s = 0;
+    for (int i = threadIdx.x; i < SCAN_BLOCK; i += 256) {
+        const int g = base + i;
+        if (g < n) s += in[g];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void scan_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total_out) {
+    // single block: sequential over chunks of 1024 with an in-block scan
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? block_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const int incl = sh[threadIdx.x];
+        if (i < nb) block_sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out != nullptr) *total_out = carry;
+}
+
+__global__ void scan_apply_kernel(const int* __restrict__ in, int n, const int* __restrict__ block_sums,
+                                  int* __restrict__ out /* n+1 entries; out[n] = total */) {
+    __shared__ int sh[256];
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    int v[4];
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[q] = (base + q < n) ? in[base + q] : 0;
+        s += v[q];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = block_sums[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (base + q < n) out[base + q] = run;
+        run += v[q];
+        if (base + q == n - 1) out[n] = run;
+    }
+}
+
+static size_t scan_ws_ints(int n) { return (size_t)(n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1; }
+
+// out has n+1 entries.  in and out may alias only if identical pointers are NOT used (they must differ).
+static int exclusive_scan(const int* in, int n, int* out, int* ws, cudaStream_t stream) {
+    if (n <= 0) {
+        RGNN_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(int), stream));
+        return RGNN_OK;
+    }
+    const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    scan_reduce_kernel<<<nb, 256, 0, stream>>>(in, n, ws);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(ws, nb, nullptr);
+    scan_apply_kernel<<<nb, 256, 0, stream>>>(in, n, ws, out);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase A: exact k nearest (by (d2, index)) + radius count, brute force per frame with smem tiles
+// ---------------------------------------------------------------------------------------------
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 512;
+
+__device__ __forceinline__ float dist2(float xi, float yi, float xj, float yj) {
+    // fl(fl(dx*dx) + fl(dy*dy)): what NumPy's batched (1x2)@(2x1) float32 matmul yields (graph_features.py:70-75)
+    const float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+template <int KCAP>
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                          const int* __restrict__ frame_ptr, float eps2, int knn,
+                                                          int ks /* row stride of knn_idx */,
+                                                          int* __restrict__ knn_idx, int* __restrict__ degree) {
+    __shared__ float sx[KNN_TILE], sy[KNN_TILE];
+    const int f = blockIdx.y;
+    const int f0 = frame_ptr[f], f1 = frame_ptr[f + 1];
+    const int nf = f1 - f0;
+    if ((int)blockIdx.x * KNN_THREADS >= nf) return;
+    const int li = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const bool active = li < nf;
+    const int gi = f0 + li;
+    const float xi = active ? px[gi] : 0.f, yi = active ? py[gi] : 0.f;
+    float bd[KCAP];
+    int bj[KCAP];
+#pragma unroll
+    for (int q = 0; q < KCAP; ++q) { bd[q] = FLT_MAX; bj[q] = -1; }
+    int deg = 0;
+    for (int t0 = 0; t0 < nf; t0 += KNN_TILE) {
+        const int tn = min(KNN_TILE, nf - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += KNN_THREADS) { sx[i] = px[f0 + t0 + i]; sy[i] = py[f0 + t0 + i]; }
+        __syncthreads();
+        if (active) {
+            for (int jj = 0; jj < tn; ++jj) {
+                const float d = dist2(xi, yi, sx[jj], sy[jj]);
+                const int j = t0 + jj;
+                deg += (d <= eps2 && j != li) ? 1 : 0;
+                if (d < bd[KCAP - 1]) {
+#pragma unroll
+                    for (int q = KCAP - 1; q > 0; --q) {
+                        if (d < bd[q - 1]) { bd[q] = bd[q - 1]; bj[q] = bj[q - 1]; }
+                        else if (d < bd[q]) { bd[q] = d; bj[q] = j; }
+                    }
+                    if (d < bd[0]) { bd[0] = d; bj[0] = j; }
+                }
+            }
+        }
+    }
+    if (active) {
+        degree[gi] = deg;
+        const int kp1 = knn >= nf ? nf : knn + 1;   // graph_features.py:35
+#pragma unroll
+        for (int q = 0; q < KCAP; ++q)
+            if (q < ks) knn_idx[(size_t)gi * ks + q] = (q < kp1) ? f0 + bj[q] : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase B: symmetrise.  row(i) = (kNN(i) \ {i})  U  {j : i in kNN(j)}   [U radius(i) for _v2]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool in_list(const int* __restrict__ lst, int n, int v) {
+    for (int q = 0; q < n; ++q)
+        if (lst[q] == v) return true;
+    return false;
+}
+
+// own[i] = entries row i writes itself; extra[j] += entries pushed into row j by non-mutual neighbours
+__global__ void sym_count_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                 const int* __restrict__ knn_idx, int ks, const int* __restrict__ degree, int n,
+                                 float eps2, int union_radius, int* __restrict__ own, int* __restrict__ extra) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int* mine = knn_idx + (size_t)i * ks;
+    int cnt = union_radius ? degree[i] : 0;
+    const float xi = px[i], yi = py[i];
+    for (int q = 0; q < ks; ++q) {
+        const int j = mine[q];
+        if (j < 0) break;
+        if (j == i) continue;
+        const bool in_ball = union_radius && dist2(xi, yi, px[j], py[j]) <= eps2;
+        if (!in_ball) {
+            ++cnt;
+            if (!in_list(knn_idx + (size_t)j * ks, ks, i)) atomicAdd(extra + j, 1);
+        }
+    }
+    own[i] = cnt;
+}
+
+__global__ void add_kernel(const int* __restrict__ a, const int* __restrict__ b, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
+// _v2 only: list the radius neighbours of i (ascending j) at the head of its row
+__global__ void __launch_bounds__(KNN_THREADS) radius_fill_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                                  const int* __restrict__ frame_ptr, float eps2,
+                                                                  const int* __restrict__ row_ptr, int n_total, int capacity,
+                                                                  int* __restrict__ col) {
+    __shared__ float sx[KNN_TILE], sy[KNN_TILE];
+    if (row_ptr[n_total] > capacity) return;
+    const int f = blockIdx.y;
+    const int f0 = frame_ptr[f], f1 = frame_ptr[f + 1];
+    const int nf = f1 - f0;
+    if ((int)blockIdx.x * KNN_THREADS >= nf) return;
+    const int li = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const bool active = li < nf;
+    const int gi = f0 + li;
+    const float xi = active ? px[gi] : 0.f, yi = active ? py[gi] : 0.f;
+    int w = active ? row_ptr[gi] : 0;
+    for (int t0 = 0; t0 < nf; t0 += KNN_TILE) {
+        const int tn = min(KNN_TILE, nf - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += KNN_THREADS) { sx[i] = px[f0 + t0 + i]; sy[i] = py[f0 + t0 + i]; }
+        __syncthreads();
+        if (active)
+            for (int jj = 0; jj < tn; ++jj)
+                if (t0 + jj != li && dist2(xi, yi, sx[jj], sy[jj]) <= eps2) col[w++] = f0 + t0 + jj;
+    }
+}
+
+__global__ void sym_fill_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                const int* __restrict__ knn_idx, int ks, const int* __restrict__ degree,
+                                const int* __restrict__ own, const int* __restrict__ row_ptr, int n, float eps2,
+                                int union_radius, int capacity, int* __restrict__ cursor, int* __restrict__ col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || row_ptr[n] > capacity) return;
+    const int* mine = knn_idx + (size_t)i * ks;
+    int w = row_ptr[i] + (union_radius ? degree[i] : 0);
+    const float xi = px[i], yi = py[i];
+    for (int q = 0; q < ks; ++q) {
+        const int j = mine[q];
+        if (j < 0) break;
+        if (j == i) continue;
+        const bool in_ball = union_radius && dist2(xi, yi, px[j], py[j]) <= eps2;
+        if (!in_ball) {
+            col[w++] = j;
+            if (!in_list(knn_idx + (size_t)j * ks, ks, i)) {
+                const int slot = atomicAdd(cursor + j, 1);
+                col[row_ptr[j] + own[j] + slot] = i;
+            }
+        }
+    }
+}
+
+// ascending insertion sort of every CSR row (rows are short: ~k..2k entries, radius rows a few dozen)
+__global__ void sort_rows_kernel(const int* __restrict__ row_ptr, int n, int capacity, int* __restrict__ col,
+                                 int* __restrict__ aux /* optional second array permuted alongside, or nullptr */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || row_ptr[n] > capacity) return;
+    const int a = row_ptr[i], b = row_ptr[i + 1];
+    for (int p = a + 1; p < b; ++p) {
+        const int v = col[p];
+        const int x = aux ? aux[p] : 0;
+        int q = p - 1;
+        while (q >= a && col[q] > v) {
+            col[q + 1] = col[q];
+            if (aux) aux[q + 1] = aux[q];
+            --q;
+        }
+        col[q + 1] = v;
+        if (aux) aux[q + 1] = x;
+    }
+}
+
+__global__ void copy_last_kernel(const int* __restrict__ row_ptr, int n, int* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = row_ptr[n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: row ids, reverse-edge permutation, undirected list
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int n,
+                                     int* __restrict__ row_of_edge, int* __restrict__ perm, int* __restrict__ und_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = row_ptr[i], b = row_ptr[i + 1];
+    int cnt = 0;
+    for (int k = a; k < b; ++k) {
+        const int c = col[k];
+        row_of_edge[k] = i;
+        cnt += (c > i) ? 1 : 0;
+        // position of the reverse edge (c -> i) inside row c (binary search, row sorted ascending)
+        int lo = row_ptr[c], hi = row_ptr[c + 1] - 1, pos = -1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int v = col[mid];
+            if (v == i) { pos = mid; break; }
+            if (v < i) lo = mid + 1; else hi = mid - 1;
+        }
+        perm[k] = pos;   // -1 would mean the adjacency is not symmetric
+    }
+    und_cnt[i] = cnt;
+}
+
+__global__ void finalize_und_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int n,
+                                    const int* __restrict__ und_ptr, int* __restrict__ und_a, int* __restrict__ und_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int w = und_ptr[i];
+    for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) {
+        const int c = col[k];
+        if (c > i) { und_a[w] = i; und_b[w] = c; ++w; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// general path: target-major CSR from an arbitrary int64 edge_index
+// ---------------------------------------------------------------------------------------------
+__global__ void ei_count_kernel(const int64_t* __restrict__ es, const int64_t* __restrict__ ed, int n_edges,
+                                int* __restrict__ cnt, int* __restrict__ und_flag) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    atomicAdd(cnt + (int)ed[e], 1);
+    und_flag[e] = es[e] < ed[e] ? 1 : 0;
+}
+
+__global__ void ei_fill_kernel(const int64_t* __restrict__ ed, int n_edges, const int* __restrict__ row_ptr,
+                               int* __restrict__ cursor, int* __restrict__ perm) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int t = (int)ed[e];
+    perm[row_ptr[t] + atomicAdd(cursor + t, 1)] = e;
+}
+
+__global__ void ei_expand_kernel(const int64_t* __restrict__ es, const int64_t* __restrict__ ed, int n_edges,
+                                 const int* __restrict__ perm, const int* __restrict__ und_flag,
+                                 const int* __restrict__ und_pos, int* __restrict__ src, int* __restrict__ tgt,
+                                 int* __restrict__ und_a, int* __restrict__ und_b) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_edges) return;
+    const int e = perm[k];
+    src[k] = (int)es[e];
+    tgt[k] = (int)ed[e];
+    if (und_flag[k]) {   // k used as an edge id here (same index range)
+        und_a[und_pos[k]] = (int)es[k];
+        und_b[und_pos[k]] = (int)ed[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw node / edge features
+// ---------------------------------------------------------------------------------------------
+__global__ void node_features_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                     const float* __restrict__ vr, const float* __restrict__ rcs,
+                                     const int64_t* __restrict__ ts, const int* __restrict__ degree,
+                                     const int* __restrict__ frame_ptr, double min_range, double max_range,
+                                     double min_az, double max_az, int range_f64, int az_f64,
+                                     float* __restrict__ out /* (n,6) */) {
+    __shared__ long long s_min[8], s_max[8];
+    const int f = blockIdx.x;
+    const int f0 = frame_ptr[f], f1 = frame_ptr[f + 1];
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    for (int i = f0 + threadIdx.x; i < f1; i += blockDim.x) {
+        const long long t = ts[i];
+        lo = t < lo ? t : lo;
+        hi = t > hi ? t : hi;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    lo = s_min[0]; hi = s_max[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        lo = s_min[w] < lo ? s_min[w] : lo;
+        hi = s_max[w] > hi ? s_max[w] : hi;
+    }
+    for (int i = f0 + threadIdx.x; i < f1; i += blockDim.x) {
+        float* o = out + (size_t)i * 6;
+        o[0] = vr[i];
+        o[1] = rcs[i];
+        // normalize_time (graph_features.py:47-55): int64 / int64 true division in float64
+        o[2] = hi == lo ? 0.f : (float)((double)(ts[i] - lo) / (double)(hi - lo));
+        o[3] = (float)((double)degree[i] / 10.0);                       // :130
+        const float x = px[i], y = py[i];
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));   // :133
+        const float th = fabsf((float)atan2((double)y, (double)x));     // :134 (float32 arctan2, correctly rounded here)
+        o[4] = range_f64 ? (float)(((double)r - max_range) / (min_range - max_range))
+                         : __fdiv_rn(__fsub_rn(r, (float)max_range), (float)(min_range - max_range));
+        o[5] = az_f64 ? (float)(((double)th - max_az) / (min_az - max_az))
+                      : __fdiv_rn(__fsub_rn(th, (float)max_az), (float)(min_az - max_az));
+    }
+}
+
+__global__ void edge_features_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                     const float* __restrict__ vx, const float* __restrict__ vy,
+                                     const int64_t* __restrict__ ts, const int* __restrict__ er,
+                                     const int* __restrict__ ec, int n_edges, float* __restrict__ out /* (E,7) */) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int s = er[e], t = ec[e];   // feature(source) - feature(target), source = edge_index[0] (graph_features.py:153)
+    const float ex = __fdiv_rn(__fsub_rn(px[s], px[t]), 10.f);
+    const float ey = __fdiv_rn(__fsub_rn(py[s], py[t]), 10.f);
+    const float el = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey))), 10.f);
+    const float evx = __fsub_rn(vx[s], vx[t]), evy = __fsub_rn(vy[s], vy[t]);
+    const float ev = __fsqrt_rn(__fadd_rn(__fmul_rn(evx, evx), __fmul_rn(evy, evy)));
+    const float et = (float)((double)(ts[s] - ts[t]) * 1e-6);
+    float* o = out + (size_t)e * 7;
+    o[0] = ex; o[1] = ey; o[2] = el; o[3] = evx; o[4] = evy; o[5] = ev; o[6] = et;
+}
+
+static int knn_stride(int knn) { return knn + 1; }
+
+}  // namespace rgnn
+
+using namespace rgnn;
+
+// workspace: knn_idx (n*ks) | own (n) | extra (n) | total (n) | cursor (n) | scan ws
+extern "C" size_t rgnn_graph_build_workspace_bytes(int n_points, int n_frames, int knn) {
+    (void)n_frames;
+    const size_t n = (size_t)n_points;
+    return align256(n * knn_stride(knn) * 4) + 4 * align256(n * 4) + align256(scan_ws_ints(n_points) * 4) + 256;
+}
+
+extern "C" int rgnn_graph_build(const float* px, const float* py, const int32_t* frame_ptr_dev,
+                                const int32_t* frame_ptr_host, int n_frames, int n_points, float eps2, int knn,
+                                int union_radius, int32_t* degree, int32_t* row_ptr, int32_t* col,
+                                int32_t edge_capacity, int32_t* n_edges_out, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RGNN_REQUIRE(n_frames >= 1 && n_points >= 1 && knn >= 1, "graph_build: empty input");
+    RGNN_REQUIRE(knn <= 67, "graph_build: knn=%d above the supported maximum of 67", knn);
+    RGNN_REQUIRE(workspace_bytes >= rgnn_graph_build_workspace_bytes(n_points, n_frames, knn), "graph_build: workspace too small");
+    int max_nf = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const int nf = frame_ptr_host[f + 1] - frame_ptr_host[f];
+        RGNN_REQUIRE(nf >= 1, "graph_build: frame %d is empty", f);
+        max_nf = nf > max_nf ? nf : max_nf;
+    }
+    RGNN_REQUIRE(frame_ptr_host[n_frames] - frame_ptr_host[0] == n_points && n_frames <= 65535, "graph_build: bad frame_ptr");
+    const int ks = knn_stride(knn);
+    char* w = static_cast<char*>(workspace);
+    int* knn_idx = reinterpret_cast<int*>(w); w += align256((size_t)n_points * ks * 4);
+    int* own = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
+    int* extra = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
+    int* total = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
+    int* cursor = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
+    int* scan_ws = reinterpret_cast<int*>(w);
+
+    const dim3 grid_a((max_nf + KNN_THREADS - 1) / KNN_THREADS, n_frames);
+    if (ks <= 12) knn_kernel<12><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
+    else if (ks <= 20) knn_kernel<20><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
+    else if (ks <= 36) knn_kernel<36><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
+    else knn_kernel<68><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+
+    RGNN_CHECK_CUDA(cudaMemsetAsync(extra, 0, (size_t)n_points * 4, stream));
+    RGNN_CHECK_CUDA(cudaMemsetAsync(cursor, 0, (size_t)n_points * 4, stream));
+    const int nb = (n_points + 255) / 256;
+    sym_count_kernel<<<nb, 256, 0, stream>>>(px, py, knn_idx, ks, degree, n_points, eps2, union_radius, own, extra);
+    add_kernel<<<nb, 256, 0, stream>>>(own, extra, n_points, total);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    int rc = exclusive_scan(total, n_points, row_ptr, scan_ws, stream);
+    if (rc) return rc;
+    copy_last_kernel<<<1, 32, 0, stream>>>(row_ptr, n_points, n_edges_out);
+    if (union_radius)
+        radius_fill_kernel<<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, row_ptr, n_points, edge_capacity, col);
+    sym_fill_kernel<<<nb, 256, 0, stream>>>(px, py, knn_idx, ks, degree, own, row_ptr, n_points, eps2, union_radius,
+                                            edge_capacity, cursor, col);
+    sort_rows_kernel<<<nb, 256, 0, stream>>>(row_ptr, n_points, edge_capacity, col, nullptr);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+extern "C" size_t rgnn_graph_finalize_workspace_bytes(int n_points, int n_edges) {
+    (void)n_edges;
+    return 2 * align256((size_t)(n_points + 1) * 4) + align256(scan_ws_ints(n_points) * 4) + 256;
+}
+
+extern "C" int rgnn_graph_finalize(const int32_t* row_ptr, const int32_t* col, int n_points, int n_edges,
+                                   int32_t* row_of_edge, int32_t* perm, int32_t* und_a, int32_t* und_b,
+                                   int32_t* n_und_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    (void)n_edges;
+    RGNN_REQUIRE(workspace_bytes >= rgnn_graph_finalize_workspace_bytes(n_points, n_edges), "graph_finalize: workspace too small");
+    char* w = static_cast<char*>(workspace);
+    int* und_cnt = reinterpret_cast<int*>(w); w += align256((size_t)(n_points + 1) * 4);
+    int* und_ptr = reinterpret_cast<int*>(w); w += align256((size_t)(n_points + 1) * 4);
+    int* scan_ws = reinterpret_cast<int*>(w);
+    const int nb = (n_points + 255) / 256;
+    finalize_rows_kernel<<<nb, 256, 0, stream>>>(row_ptr, col, n_points, row_of_edge, perm, und_cnt);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    int rc = exclusive_scan(und_cnt, n_points, und_ptr, scan_ws, stream);
+    if (rc) return rc;
+    finalize_und_kernel<<<nb, 256, 0, stream>>>(row_ptr, col, n_points, und_ptr, und_a, und_b);
+    copy_last_kernel<<<1, 32, 0, stream>>>(und_ptr, n_points, n_und_out);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+// workspace: cnt (n+1) | cursor (n) | und_flag (E) | und_pos (E+1) | scan ws
+extern "C" size_t rgnn_csr_from_edge_index_workspace_bytes(int n_nodes, int n_edges) {
+    const int m = n_nodes > n_edges ? n_nodes : n_edges;
+    return 2 * align256((size_t)(n_nodes + 1) * 4) + 2 * align256((size_t)(n_edges + 1) * 4) + align256(scan_ws_ints(m) * 4) + 256;
+}
+
+extern "C" int rgnn_csr_from_edge_index(const int64_t* edge_src, const int64_t* edge_dst, int n_nodes, int n_edges,
+                                        int32_t* row_ptr, int32_t* src, int32_t* tgt, int32_t* perm, int32_t* und_a,
+                                        int32_t* und_b, int32_t* n_und_out, void* workspace, size_t workspace_bytes,
+                                        void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RGNN_REQUIRE(n_nodes >= 1 && n_edges >= 0, "csr_from_edge_index: empty graph");
+    RGNN_REQUIRE(workspace_bytes >= rgnn_csr_from_edge_index_workspace_bytes(n_nodes, n_edges), "csr_from_edge_index: workspace too small");
+    char* w = static_cast<char*>(workspace);
+    int* cnt = reinterpret_cast<int*>(w); w += align256((size_t)(n_nodes + 1) * 4);
+    int* cursor = reinterpret_cast<int*>(w); w += align256((size_t)(n_nodes + 1) * 4);
+    int* und_flag = reinterpret_cast<int*>(w); w += align256((size_t)(n_edges + 1) * 4);
+    int* und_pos = reinterpret_cast<int*>(w); w += align256((size_t)(n_edges + 1) * 4);
+    int* scan_ws = reinterpret_cast<int*>(w);
+    RGNN_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n_nodes + 1) * 4, stream));
+    RGNN_CHECK_CUDA(cudaMemsetAsync(cursor, 0, (size_t)(n_nodes + 1) * 4, stream));
+    if (n_edges == 0) {
+        RGNN_CHECK_CUDA(cudaMemsetAsync(row_ptr, 0, (size_t)(n_nodes + 1) * 4, stream));
+        RGNN_CHECK_CUDA(cudaMemsetAsync(n_und_out, 0, 4, stream));
+        return RGNN_OK;
+    }
+    const int nbe = (n_edges + 255) / 256, nbn = (n_nodes + 255) / 256;
+    ei_count_kernel<<<nbe, 256, 0, stream>>>(edge_src, edge_dst, n_edges, cnt, und_flag);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    int rc = exclusive_scan(cnt, n_nodes, row_ptr, scan_ws, stream);
+    if (rc) return rc;
+    rc = exclusive_scan(und_flag, n_edges, und_pos, scan_ws, stream);
+    if (rc) return rc;
+    ei_fill_kernel<<<nbe, 256, 0, stream>>>(edge_dst, n_edges, row_ptr, cursor, perm);
+    // order each row by caller edge id: deterministic, and source-ascending for reference-ordered input
+    sort_rows_kernel<<<nbn, 256, 0, stream>>>(row_ptr, n_nodes, n_edges, perm, nullptr);
+    ei_expand_kernel<<<nbe, 256, 0, stream>>>(edge_src, edge_dst, n_edges, perm, und_flag, und_pos, src, tgt, und_a, und_b);
+    copy_last_kernel<<<1, 32, 0, stream>>>(und_pos, n_edges, n_und_out);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+extern "C" int rgnn_graph_features(const float* px, const float* py, const float* vx, const float* vy, const float* vr,
+                                   const float* rcs, const int64_t* timestamp_us, const int32_t* degree,
+                                   const int32_t* frame_ptr_dev, int n_frames, int n_points, const int32_t* edge_row,
+                                   const int32_t* edge_col, int n_edges, double min_range, double max_range,
+                                   double min_azimuth, double max_azimuth, int range_in_f64, int azimuth_in_f64,
+                                   float* node_features, float* edge_features, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    (void)n_points;
+    if (node_features != nullptr) {
+        node_features_kernel<<<n_frames, 256, 0, stream>>>(px, py, vr, rcs, timestamp_us, degree, frame_ptr_dev, min_range,
+                                                           max_range, min_azimuth, max_azimuth, range_in_f64,
+                                                           azimuth_in_f64, node_features);
+    }
+    if (edge_features != nullptr && n_edges > 0) {
+        edge_features_kernel<<<(n_edges + 255) / 256, 256, 0, stream>>>(px, py, vx, vy, timestamp_us, edge_row, edge_col,
+                                                                        n_edges, edge_features);
+    }
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}

@@ -1,0 +1,38 @@
+// Internal declarations shared by the forward and backward host code of the detector.
+#pragma once
+#include <functional>
+
+#include "rgnn_programs.h"
+
+namespace rgnn {
+
+// Where everything lives inside the caller-provided detector workspace.
+struct DetPlan {
+    ConvDims d;
+    int link_w, cls_w;
+    float* x[RGNN_MAX_CONV + 1];   // node embeddings entering conv l (x[L] feeds the heads)
+    float* P[RGNN_MAX_CONV];       // per-node projections of msg.0: [x W1_target^T | x W1_source^T]
+    float* agg[RGNN_MAX_CONV];     // aggregated messages
+    float* emb;                    // edge embedding, target-major order
+    float* hlink;                  // predict_link.compute_edge.stem output per node
+    float* gcls;                   // predict_class.stem output per node
+    // ---- backward only ----
+    float* dx;       // (N, cn) running gradient w.r.t. the node embedding
+    float* dx2;      // (N, cn) second buffer (ping-pong between layers)
+    float* dP;       // (N, 2h)
+    float* dagg;     // (N, cn)
+    float* demb;     // (E, ce) accumulated over all conv layers
+    float* dh;       // (N, link_w)
+    float* dg;       // (N, cls_w)
+    float* scratch;  // per-CTA parameter-gradient partial sums
+    size_t scratch_floats;
+    size_t bytes;
+};
+
+typedef std::function<float*(size_t)> TakeFn;
+int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, void* base, DetPlan* pl);
+void plan_detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const TakeFn& take, DetPlan* pl);
+
+int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream);
+
+}  // namespace rgnn

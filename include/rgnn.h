@@ -1,0 +1,228 @@
+/*
+ * rgnn.h -- C-ABI of librgnn.so, the B200 (sm_100a) implementation of the radar GNN hot path of
+ * UditBhaskar19/GRAPH_NEURAL_NETWORK_FOR_RADAR_PERCEPTION.
+ *
+ * The reference is pure Python/PyTorch (no FFI of its own), so the "binding" a maintainer adds is a ctypes
+ * stub; INTEGRATION.md shows it.  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller allocates every output
+ *     and every workspace (sizes from the *_workspace_bytes functions); the library owns no memory.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous w.r.t. the host and performs
+ *     no hidden synchronisation or allocation.
+ *   - return value 0 = ok; otherwise an RGNN_ERR_* code, with text from rgnn_last_error() (thread local).
+ *   - floating point is fp32; node / edge indices are int32 inside the library (the PyTorch-facing layer
+ *     converts the reference's int64 tensors).
+ *   - there is no CPU fallback: a missing CUDA device is an error.
+ */
+#ifndef RGNN_H_
+#define RGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGNN_OK 0
+#define RGNN_ERR_INVALID 1
+#define RGNN_ERR_CUDA 2
+#define RGNN_ERR_WORKSPACE 3
+
+#define RGNN_MAX_STACK 8   /* ffn_blocks in one nn.Sequential of the reference */
+#define RGNN_MAX_CONV 16   /* residual_graph_conv_block count */
+
+int rgnn_version(void);
+const char* rgnn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * One reference `ffn_block` (modules/neural_net/common.py:185-205): nn.Linear, optional
+ * channel_normalization (:208-220; scalar affine `std`,`mu`), optional LeakyReLU(0.01) (:256-267).
+ * A bare nn.Linear (FFN_TaskSpecificHead's last layer, gnn_blocks.py:185-188) has norm_* NULL, activation 0.
+ * grad_* are written (accumulated, +=) by the *_bwd entry points and may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rgnn_linear {
+    const float* weight;      /* (out_features, in_features) row-major: the PyTorch state_dict layout   */
+    const float* weight_t;    /* packed copy from rgnn_pack_linear: (round_up(in,8), round_up(out,64))   */
+    const float* bias;        /* (out_features) or NULL                                                 */
+    const float* norm_scale;  /* channel_normalization.std, shape (1,), or NULL when there is no norm   */
+    const float* norm_shift;  /* channel_normalization.mu,  shape (1,)                                  */
+    float* grad_weight;       /* same layouts as the parameters; NULL = not wanted                      */
+    float* grad_bias;
+    float* grad_norm_scale;
+    float* grad_norm_shift;
+    int in_features;
+    int out_features;
+    int activation;           /* 1 = LeakyReLU(0.01), 0 = none */
+    int reserved;
+} rgnn_linear;
+
+typedef struct rgnn_stack {   /* an nn.Sequential of ffn_blocks (graph_feature_encoding.encoder, *.stem ...) */
+    int n;
+    int reserved;
+    rgnn_linear layer[RGNN_MAX_STACK];
+} rgnn_stack;
+
+/* residual_graph_conv_block (gnn_blocks.py:45-113): msg = [ffn(2*Cn+Ce -> H), ffn(H -> Cn)], upd = [ffn(2*Cn -> Cn)] */
+typedef struct rgnn_conv {
+    rgnn_stack msg;
+    rgnn_stack upd;
+} rgnn_conv;
+
+/* Model_Inference (modules/neural_net/gnn/gnn_detector.py:31-201), parameters only */
+typedef struct rgnn_detector {
+    rgnn_stack node_enc;       /* encode_node_feat.encoder                      gnn_blocks.py:19-42   */
+    rgnn_stack edge_enc;       /* encode_edge_feat.encoder                                            */
+    int n_conv;
+    int reserved;
+    rgnn_conv conv[RGNN_MAX_CONV]; /* pass_messages.conv_blk                    gnn_blocks.py:116-164 */
+    rgnn_stack head_node;      /* predict_node: stem + pred_cls.head (last = bare Linear)  :200-234   */
+    rgnn_stack head_offset;    /* predict_offset: stem + pred_offsets.head                 :237-271   */
+    rgnn_stack link_node;      /* predict_link.compute_edge.stem (node-wise part)          :274-298   */
+    rgnn_stack head_link;      /* predict_link.stem + pred_cls.head (per undirected edge)  :301-344   */
+    rgnn_stack class_node;     /* predict_class.stem (node-wise part)                      :347-389   */
+    rgnn_stack head_class;     /* predict_class.pred_cls.head (per cluster, after max-pool)           */
+} rgnn_detector;
+
+/* A batch of per-frame graphs packed block-diagonally (node ids are global within the batch).
+ * The edges are held target-major (CSR over edge_index[1]) so that the sum-aggregation of
+ * MessagePassing.propagate (gnn_blocks.py:106; PyG scatter-add onto edge_index[1]) is a segmented sum. */
+typedef struct rgnn_graph {
+    int n_nodes, n_edges, n_und, n_clusters;
+    const int32_t* row_ptr;    /* (n_nodes+1) CSR over targets                                         */
+    const int32_t* src;        /* (n_edges)   source node (edge_index[0]) of the k-th target-major edge */
+    const int32_t* tgt;        /* (n_edges)   target node (edge_index[1])                              */
+    const int32_t* perm;       /* (n_edges)   row of the caller's edge_features / edge_index for edge k */
+    const int32_t* und_a;      /* (n_und) undirected links r<c in row-major order = nonzero(triu(adj,1)) */
+    const int32_t* und_b;      /*          (gnn_blocks.py:295-296)                                      */
+    const int32_t* cl_ptr;     /* (n_clusters+1) cluster_node_idx lists flattened (gnn_blocks.py:384-386) */
+    const int32_t* cl_members; /* (cl_ptr[n_clusters]) */
+} rgnn_graph;
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) graph construction -- replaces modules/compute_features/graph_features.py
+ * ---------------------------------------------------------------------------------------------- */
+
+/* compute_adjacency_information (graph_features.py:58-84) and _v2 (:87-114) for a batch of frames.
+ * px,py: (n_points) f32, frames concatenated; frame_ptr_host: (n_frames+1) host array of point offsets.
+ * Outputs (all caller-allocated):
+ *   degree      (n_points) int32   radius-gate neighbour count, D <= eps2, diagonal excluded (:11-22,:78)
+ *   row_ptr     (n_points+1) int32 CSR over edge_index[0] in reference order (== CSR over targets, the
+ *                                  adjacency is symmetric)
+ *   col         (edge_capacity) int32  edge_index[1], GLOBAL node ids, ascending within a row  (:79)
+ *   n_edges_out (1) int32          number of directed edges written (device scalar)
+ * kNN ties are ordered by (d2, index) (the reference's argsort is unstable there).
+ * Returns RGNN_ERR_WORKSPACE if edge_capacity is too small (checked on device; n_edges_out holds the need). */
+size_t rgnn_graph_build_workspace_bytes(int n_points, int n_frames, int knn);
+int rgnn_graph_build(const float* px, const float* py, const int32_t* frame_ptr_dev, const int32_t* frame_ptr_host,
+                     int n_frames, int n_points, float eps2, int knn, int union_radius,
+                     int32_t* degree, int32_t* row_ptr, int32_t* col, int32_t edge_capacity, int32_t* n_edges_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Expand a symmetric row-major CSR (from rgnn_graph_build) into everything rgnn_graph needs plus the
+ * reference-facing edge_index: src_of_row (n_edges) = edge_index[0] (global ids), perm = reverse-edge
+ * permutation, und_a/und_b = pairs with row<col in order, n_und_out device scalar. */
+size_t rgnn_graph_finalize_workspace_bytes(int n_points, int n_edges);
+int rgnn_graph_finalize(const int32_t* row_ptr, const int32_t* col, int n_points, int n_edges,
+                        int32_t* row_of_edge, int32_t* perm, int32_t* und_a, int32_t* und_b, int32_t* n_und_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* General path: build the target-major CSR from a caller-supplied edge_index (any order, int64 like the
+ * reference API, node ids already global).  und_* are the edges with edge_index[0] < edge_index[1] in the
+ * caller's order (identical to nonzero(triu(adj,1)) when edge_index is in reference order). */
+size_t rgnn_csr_from_edge_index_workspace_bytes(int n_nodes, int n_edges);
+int rgnn_csr_from_edge_index(const int64_t* edge_src, const int64_t* edge_dst, int n_nodes, int n_edges,
+                             int32_t* row_ptr, int32_t* src, int32_t* tgt, int32_t* perm,
+                             int32_t* und_a, int32_t* und_b, int32_t* n_und_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* compute_node_features (graph_features.py:117-144, include_region_confidence=True) and
+ * compute_edge_features (:147-164) for a batch; outputs are the float32 tensors of datagen_gnn.py:121-122.
+ * t_min/t_max per frame come from frame_ptr (device). edge rows follow (edge_row, edge_col) = edge_index in
+ * reference order.  node_features (n_points,6), edge_features (n_edges,7); either may be NULL to skip it.
+ * range_in_f64 / azimuth_in_f64 say whether NumPy evaluates (r - max)/(min - max) in float64 (max given as an
+ * np.float64 scalar, as datagen_gnn.py:77 does for the range) or in float32 (Python float, NEP 50 weak scalar,
+ * as for the azimuth np.pi*0.5 of datagen_gnn.py:75). */
+int rgnn_graph_features(const float* px, const float* py, const float* vx, const float* vy, const float* vr,
+                        const float* rcs, const int64_t* timestamp_us, const int32_t* degree,
+                        const int32_t* frame_ptr_dev, int n_frames, int n_points,
+                        const int32_t* edge_row, const int32_t* edge_col, int n_edges,
+                        double min_range, double max_range, double min_azimuth, double max_azimuth,
+                        int range_in_f64, int azimuth_in_f64,
+                        float* node_features, float* edge_features, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2)-(4) model forward -- replaces gnn_blocks.py / gnn_detector.py forward passes
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Packed k-major copy of one Linear weight for the tile GEMM: dst (round_up(in,8), round_up(out,64)), zero padded. */
+size_t rgnn_packed_weight_floats(int in_features, int out_features);
+int rgnn_pack_linear(const float* weight, int in_features, int out_features, float* weight_t, void* stream);
+/* Pack every Linear of a stack / conv block / detector (weight -> weight_t) in one launch.
+ * The first Linear of a conv block's msg stack (in = 2*Cn+Ce) is packed as two operands back to back:
+ * the node projection [W_target^T | W_source^T] (round_up(Cn,8) x round_up(2H,64)) followed by the edge part
+ * W_edge^T (round_up(Ce,8) x round_up(H,64)); its weight_t buffer needs rgnn_packed_conv_msg0_floats floats. */
+size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden);
+int rgnn_pack_stack(const rgnn_stack* stack, void* stream);
+int rgnn_pack_conv(const rgnn_conv* blk, void* stream);
+int rgnn_pack_detector(const rgnn_detector* net, void* stream);
+
+/* nn.Sequential of ffn_blocks applied row-wise (graph_feature_encoding.forward gnn_blocks.py:41-42,
+ * the *.stem stacks and FFN_TaskSpecificHead.forward :196-197).  x (n_rows, in), y (n_rows, out). */
+int rgnn_ffn_stack_fwd(const rgnn_stack* stack, const float* x, int n_rows, float* y, void* stream);
+int rgnn_ffn_stack_bwd(const rgnn_stack* stack, const float* x, const float* grad_y, int n_rows,
+                       float* grad_x /* NULL = not wanted */, void* workspace, size_t workspace_bytes, void* stream);
+size_t rgnn_ffn_stack_bwd_workspace_bytes(const rgnn_stack* stack);
+
+/* residual_graph_conv_block.forward (gnn_blocks.py:96-113): x (N,Cn), edge embedding e (E,Ce) in TARGET-MAJOR
+ * order (row k belongs to edge k of g), out (N,Cn).  scratch: agg (N,Cn) and proj (N,2H) caller-allocated. */
+int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* x, const float* e,
+                        float* out, float* agg, float* proj, void* stream);
+
+/* Model_Inference.forward with cluster_node_idx given (gnn_detector.py:141-162).
+ * edge_features rows are in the caller's order (g->perm maps them).  Outputs: node_cls (N,7), node_off (N,2),
+ * link_cls (n_und,2), obj_cls (n_clusters,7).  With training != 0 the node-level activations needed by
+ * rgnn_detector_bwd stay in the workspace (edge activations are never stored; they are recomputed). */
+size_t rgnn_detector_workspace_bytes(const rgnn_detector* net, const rgnn_graph* g, int training);
+int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, const float* node_features,
+                      const float* edge_features, float* node_cls, float* node_off, float* link_cls, float* obj_cls,
+                      void* workspace, size_t workspace_bytes, int training, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) backward and training -- replaces torch autograd over the above (gnn/training.py:81) and
+ *     Loss_Graph (gnn/loss.py:37-76)
+ * ---------------------------------------------------------------------------------------------- */
+int rgnn_detector_bwd(const rgnn_detector* net, const rgnn_graph* g, const float* node_features,
+                      const float* edge_features, const float* grad_node_cls, const float* grad_node_off,
+                      const float* grad_link_cls, const float* grad_obj_cls,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Loss_Graph.forward + its gradient w.r.t. the logits, and compute_accuracy (gnn_detector.py:23-28).
+ * counts_* are the GLOBAL batch sizes each sum is divided by (loss.py:58,62,66,70) -- under data parallelism
+ * they are the all-reduced counts, which is what makes per-rank sums add up to the reference's loss.
+ * losses_out (4) f64: node_cls, node_reg, edge_cls, obj_cls (already weighted, this rank's share);
+ * correct_out (3) int32: argmax hits for node / edge / object.  node_off_gt is already normalised. */
+typedef struct rgnn_loss_cfg {
+    float class_weights[16];
+    int n_classes, n_edge_classes;
+    float w_node_cls, w_node_reg, w_edge_cls, w_obj_cls;
+    float focal_alpha, focal_gamma;
+} rgnn_loss_cfg;
+int rgnn_losses_fwdbwd(const rgnn_loss_cfg* cfg, const float* node_cls, const float* node_off, const float* link_cls,
+                       const float* obj_cls, const int64_t* node_cls_gt, const float* node_off_gt,
+                       const int64_t* link_gt, const int64_t* obj_gt, int n_nodes, int n_und, int n_clusters,
+                       double count_nodes, double count_und, double count_clusters,
+                       float* grad_node_cls, float* grad_node_off, float* grad_link_cls, float* grad_obj_cls,
+                       double* losses_out, int32_t* correct_out, void* stream);
+
+/* torch.optim.SGD(momentum, weight_decay) step on a flat parameter buffer
+ * (modules/set_configurations/set_param_for_training_gnn.py:46): g += wd*p; buf = mu*buf + g; p -= lr*buf.
+ * grad_scale multiplies the (all-reduced) gradient first. */
+int rgnn_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
+                  float weight_decay, float grad_scale, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGNN_H_ */
