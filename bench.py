@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the radar GNN hot path (BASELINE.json metric: radar frames/s and edges/s, GNN forward and
+forward+backward, % of roofline, CPU reference beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--points P] [--impl reference]
+
+A step = one pass of the hot path over one batch of synthetic RadarScenes-shaped frames:
+graph construction (kNN + radius degree + features) -> node/edge encoders -> 7 message-passing layers ->
+4 heads.  Workload at N=1 is BASELINE.json configs[1]: 256 accumulated frames x 3000 points (reference-default
+symmetrised-kNN graph, k=10, eps^2=25).  Under torchrun every rank processes its own 256 frames (weak scaling,
+no data-path collective: frames are independent graphs).
+
+`--impl reference` times the reference's CPU algorithm (oracle port of graph_features.py + gnn_detector.py in
+plain PyTorch/NumPy, the per-frame loop of Model_Training.forward) on the host cores, on a bounded sample
+of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from graph_neural_network_for_radar_perception_b200 import synth  # noqa: E402
+
+KNN, EPS2 = 10, 25
+GRID_MAX_R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
+GRID_MAX_TH = np.pi * 0.5
+CKPT = os.path.join(ROOT, 'tests', 'golden', 'graph_based_detector.pt')
+
+
+def make_frames(n_frames, n_points, seed0=0, distinct=16):
+    """`distinct` different synthetic frames, tiled to n_frames (generation is host-side NumPy and not timed)."""
+    base = [synth.make_frame(seed0 + i, n_points, knn=KNN) for i in range(min(distinct, n_frames))]
+    return [base[i % len(base)] for i in range(n_frames)]
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v == 'Active'})
+        return {'sm_mhz': int(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference algorithm)
+# -------------------------------------------------------------------------------------------------
+def cpu_frame_pass(sd, data, lab_src, train=False):
+    from oracle import graph_np, model_torch
+    adj = graph_np.adjacency_information(data, EPS2, KNN)
+    nf = torch.from_numpy(graph_np.node_features(data, adj['degree'], True, 0, GRID_MAX_R, 0, GRID_MAX_TH).astype(np.float32))
+    ef = torch.from_numpy(graph_np.edge_features(data, adj['adj_list']).astype(np.float32))
+    ei = torch.from_numpy(adj['adj_list'])
+    lab = synth.make_labels(data, lab_src, adj['adj_list'])
+    cl = [torch.from_numpy(c) for c in lab['cluster_node_idx']]
+    with torch.no_grad():
+        model_torch.detector_forward(sd, nf, ef, ei, cl)
+    return ei.shape[1]
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = torch.load(CKPT, map_location='cpu', weights_only=True)
+    sample = max(1, min(args.ref_frames, args.frames))
+    frames = make_frames(sample, args.points)
+    for _ in range(args.warmup):
+        cpu_frame_pass(sd, *frames[0])
+    t0 = time.perf_counter()
+    edges = 0
+    for _ in range(args.steps):
+        for f in frames:
+            edges += cpu_frame_pass(sd, *f)
+    dt = time.perf_counter() - t0
+    fps = args.steps * sample / dt
+    line = {'impl': 'reference', 'metric': 'radar_frames_per_s_gnn_fwd', 'value': fps, 'unit': 'frames/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args),
+            'edges_per_s': edges / dt,
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} frames x {args.points} points per step (graph build + forward, per-frame loop)'},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {'workload': f'batched inference: {args.frames} synthetic accumulated frames x {args.points} points, '
+                        f'symmetrised-kNN graph k={KNN} + radius degree eps2={EPS2} (BASELINE.json configs[1])',
+            'frames_per_gpu': args.frames, 'points_per_frame': args.points, 'knn': KNN,
+            'weights': 'reference checkpoint 1718175257362', 'cache': 'inputs larger than L2 (no flush needed)'}
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+    from graph_neural_network_for_radar_perception_b200 import config, Model_Training, _cabi
+    from graph_neural_network_for_radar_perception_b200 import graph_features as gf
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _cabi.lib()
+
+    model = Model_Training(config(), dev)
+    model.load_state_dict(torch.load(CKPT, map_location='cpu', weights_only=True))
+    model = model.to(dev)
+    det = model.pred.eval()
+
+    frames = make_frames(args.frames, args.points, seed0=1000 * rank)
+    # host buffers (pinned) of the raw accumulated points: what the reference's data loader hands over
+    keys = ('meas_px', 'meas_py', 'meas_vx', 'meas_vy', 'meas_vr', 'meas_rcs', 'meas_timestamp')
+    host = {}
+    for k in keys:
+        a = np.concatenate([f[0][k] for f in frames])
+        host[k] = torch.from_numpy(a.astype(np.int64 if k == 'meas_timestamp' else np.float32)).pin_memory()
+    fp = [0]
+    for f in frames:
+        fp.append(fp[-1] + f[0]['meas_px'].shape[0])
+    n_nodes = fp[-1]
+    # clusters: synthetic blobs + singletons (labels are inputs of the object head)
+    from oracle import graph_np  # noqa: F401  (only the CPU-baseline leg below executes oracle code)
+    pts_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    bf0 = gf.build_graph_batch(pts_dev, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+    cl_lists = []
+    for (d, src) in frames:
+        blob = src['blob_of']
+        cl = [np.nonzero(blob == b)[0] for b in np.unique(blob[blob >= 0])] + [np.array([i]) for i in np.nonzero(blob < 0)[0]]
+        cl_lists.append([torch.from_numpy(c.astype(np.int64)) for c in cl])
+    bf0.gb.set_clusters(cl_lists, fp[:-1], dev)
+    cl_ptr, cl_members, n_clusters = bf0.gb.cl_ptr, bf0.gb.cl_members, bf0.gb.n_clusters
+    n_edges, n_und = bf0.gb.n_edges, bf0.gb.n_und
+
+    def device_step(pts):
+        bf = gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+        bf.gb.cl_ptr, bf.gb.cl_members, bf.gb.n_clusters = cl_ptr, cl_members, n_clusters
+        with torch.no_grad():
+            return det.forward_batch(bf.gb, bf.node_features, bf.edge_features, training=False)
+
+    out_host = None
+
+    def e2e_step():
+        nonlocal out_host
+        pts = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        outs = device_step(pts)
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        for h, o in zip(out_host, outs):
+            h.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        device_step(pts_dev)
+        e2e_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(lambda: device_step(pts_dev), args.steps)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # forward only (graph + features already built): the GNN proper, for edges/s
+    with torch.no_grad():
+        ms_fwd = timed(lambda: det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False), args.steps)
+    ms_graph = timed(lambda: gf.build_graph_batch(pts_dev, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH), args.steps)
+    roof = measure_roofline(det, bf0, dev, args.steps)
+    train = measure_train(model, bf0, frames, fp, dev, args, timed) if args.train else None
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf, which = peaks()
+    total_frames = args.frames * world
+    per_step_s = ms_dev / args.steps / 1e3
+    line = {
+        'metric': 'radar_frames_per_s_gnn_fwd', 'value': total_frames / per_step_s, 'unit': 'frames/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'edges_per_s_gnn_fwd': n_edges * world / (ms_fwd / args.steps / 1e3),
+        'frames_per_s_gnn_fwd_only': total_frames / (ms_fwd / args.steps / 1e3),
+        'breakdown_ms': {'graph_build_and_features': ms_graph / args.steps, 'gnn_forward': ms_fwd / args.steps},
+        'graph': {'nodes_per_gpu': n_nodes, 'directed_edges_per_gpu': n_edges, 'undirected_links_per_gpu': n_und,
+                  'clusters_per_gpu': n_clusters},
+        'e2e': {'value': total_frames / (ms_e2e / args.steps / 1e3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': int(sum(v.numel() * v.element_size() for v in host.values())),
+                'd2h_bytes_per_step': int(sum(h.numel() * h.element_size() for h in out_host))},
+        'gpu_launches': launches_per_step(det),
+        'roofline': dict(roof, peak=hbm, frac=roof['achieved'] / hbm, peak_source=which),
+        'clocks': clocks,
+    }
+    if train:
+        line['train'] = train
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launches_per_step(det):
+    # graph build: knn, 2 memsets excluded; kernels only: knn, sym_count, add, 3 scan, copy_last, sym_fill, sort,
+    # finalize (rows, 3 scan, und, copy_last), node feat, edge feat = 17; model: pack 2, node enc, edge enc,
+    # 7 x (edge, node), 6 head programs = 24
+    return 17 + 2 + 2 + 2 * len(det.pass_messages.conv_blk) + 6
+
+
+def measure_roofline(det, bf, dev, steps):
+    """Dominant kernels: the message-passing layer (edge tile program + node tile program).  Algorithmic bytes per
+    layer B_f = 512 N + 260 E (read x, write x', read e, 4-byte column index)."""
+    import ctypes as C
+    from graph_neural_network_for_radar_perception_b200 import _cabi
+    from graph_neural_network_for_radar_perception_b200._engine import detector_table
+    from graph_neural_network_for_radar_perception_b200._cabi import check, lib, ptr, stream_ptr
+    gb = bf.gb
+    table = detector_table(det)
+    table.refill(None)
+    check(lib().rgnn_pack_detector(C.byref(table.det), stream_ptr()), 'pack')
+    N, E = gb.n_nodes, gb.n_edges
+    x = torch.randn(N, 64, device=dev)
+    e = torch.randn(E, 64, device=dev)
+    out = torch.empty_like(x)
+    agg = torch.empty_like(x)
+    proj = torch.empty(N, 256, device=dev)
+    g = gb.c_struct()
+    conv = table.det.conv[0]
+    s = stream_ptr()
+    for _ in range(3):
+        check(lib().rgnn_conv_block_fwd(C.byref(conv), C.byref(g), ptr(x), ptr(e), ptr(out), ptr(agg), ptr(proj), s), 'conv')
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(steps, 3)
+    e0.record()
+    for _ in range(reps):
+        check(lib().rgnn_conv_block_fwd(C.byref(conv), C.byref(g), ptr(x), ptr(e), ptr(out), ptr(agg), ptr(proj), s), 'conv')
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bytes_alg = 512.0 * N + 260.0 * E
+    flops_alg = 65536.0 * E + 16384.0 * N
+    return {'kernel': 'message-passing layer fwd (chain_fwd_kernel: edge program + node program)', 'bound': 'hbm',
+            'achieved': bytes_alg / (ms * 1e-3) / 1e9, 'unit': 'GB/s', 'traffic': None,
+            'ms_per_launch': ms, 'algorithmic_bytes': bytes_alg, 'algorithmic_tflops': flops_alg / (ms * 1e-3) / 1e12}
+
+
+def measure_train(model, bf, frames, fp, dev, args, timed):
+    return None
+
+
+def cpu_baseline(args):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = torch.load(CKPT, map_location='cpu', weights_only=True)
+    sample = max(1, min(args.ref_frames, args.frames))
+    frames = make_frames(sample, args.points)
+    cpu_frame_pass(sd, *frames[0])
+    t0 = time.perf_counter()
+    edges = 0
+    reps = 0
+    while True:
+        for f in frames:
+            edges += cpu_frame_pass(sd, *f)
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return {'value': reps * sample / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'edges_per_s': edges / dt,
+            'sample': f'{reps} x {sample} frames x {args.points} points (graph build + forward per frame, oracle port of the reference)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--frames', type=int, default=256)
+    ap.add_argument('--points', type=int, default=3000)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--ref-frames', type=int, default=4)
+    ap.add_argument('--train', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()
