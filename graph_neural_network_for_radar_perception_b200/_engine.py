@@ -177,6 +177,9 @@ class StackFn(torch.autograd.Function):
         s = stream_ptr()
         check(lib().rgnn_pack_stack(C.byref(st), s), 'rgnn_pack_stack')
         gy = _f32c(gy)
+        if ctx.needs_input_grad[0] and refs[0].in_features % 64 != 0:
+            raise NotImplementedError('gradient w.r.t. the input of an ffn stack needs in_features % 64 == 0 '
+                                      '(raw 6/7-wide feature inputs never require it in the reference)')
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         nbytes = lib().rgnn_ffn_stack_bwd_workspace_bytes(C.byref(st))
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)

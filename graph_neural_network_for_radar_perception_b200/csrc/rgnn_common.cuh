@@ -39,46 +39,49 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 // ---------------------------------------------------------------------------------------------
-// tile-program steps (see rgnn_chain.cu)
+// tile programs (interpreted by rgnn_chain.cu): a CTA owns a tile of TR rows; its activations live in
+// numbered shared-memory regions; a step reads/writes explicit regions (ra, rb).
 // ---------------------------------------------------------------------------------------------
 enum Op : int {
     OP_END = 0,
-    OP_LOAD_ROWS,      // cur[r][i2 + j] = src[row(r)*i0 + j], j < i1; zero up to i3; p1 = optional int32 row index
-    OP_LOAD_PAIRSUM,   // cur[r][j] = h[a[row]][j] + h[b[row]][j]
-    OP_LOAD_SEGMAX,    // cur[r][j] = max_{m in members[ptr[row]..ptr[row+1])} g[m][j]
-    OP_LINEAR,         // nxt = cur * Wt (+ bias); swap
-    OP_ADD_GATHER2,    // cur[r][j] += P[t[row]][j] + P[s[row]][i2 + j]
-    OP_NORM_ACT,       // per-row channel norm (optional) + LeakyReLU (optional), in place
-    OP_ADD_ROWS,       // cur[r][j] += src[row*i0 + j]
-    OP_STORE_ROWS,     // dst[row*i0 + i2 + j] = cur[r][j], j < i1
-    OP_SEGSUM,         // agg[t[row]][j] += cur[r][j]  (segmented by equal consecutive t)
-    // ---- backward-only steps (rgnn_chain_bwd.cu) ----
-    OPB_SAVE_INPUT,    // remember the current buffer as the input of linear #i0
-    OPB_LOAD_GRAD,     // work[r][j] = g[row(r)*i0 + j] (p1 optional row index), j < i1
-    OPB_ACTNORM_BWD,   // work (dY) -> dZ in place through LeakyReLU + channel norm of layer i0
-    OPB_WGRAD,         // dW[c][k] += sum_r dZ[r][c] X[r][k];  db[c] += sum_r dZ[r][c]
-    OPB_DGRAD,         // nxt_work = dZ * W ; swap
-    OPB_STORE_GRAD,    // dst[row*i0 + i2 + j] (=|+=) work[r][j]
-    OPB_SCATTER_GRAD,  // atomicAdd(dst[idx[row]*i0 + i2 + j], work[r][j])
-    OPB_SEGSUM_GRAD,   // like OP_SEGSUM but from the work buffer
-    OPB_SEGMAX_BWD,    // route d(pooled) to the arg-max member rows
-    OPB_PAIR_SCATTER,  // atomicAdd dst[a[row]] and dst[b[row]]
+    OP_LOAD_ROWS,      // ra[r][i2 + j] = src[row(r)*i0 + i4 + j], j < i1; zero-fill up to i3; p1 = optional int32 row index
+    OP_LOAD_PAIRSUM,   // ra[r][j] = h[a[row]][j] + h[b[row]][j]
+    OP_LOAD_SEGMAX,    // ra[r][j] = max_{m in members[ptr[row]..ptr[row+1])} g[m][j]
+    OP_LINEAR,         // rb = ra * Wt (+ bias): i0 = K (mult of 8), i1 = C, i2 = Cpad (mult of 64), i3 = valid rows of Wt, i4 = ldw
+    OP_ADD_GATHER2,    // ra[r][j] += P[t[row]][j] + P[s[row]][i2 + j], j < i1
+    OP_NORM_ACT,       // ra: per-row channel norm (p0/p1 scale/shift, nullable) + LeakyReLU (i1); i2 = sigma slot or -1
+    OP_ADD_ROWS,       // ra[r][j] += src[row*i0 + j], j < i1
+    OP_STORE_ROWS,     // dst[row*i0 + i2 + j] (= or +=, i3) ra[r][i4 + j], j < i1
+    OP_SEGSUM,         // dst[t[row]*i0 + i2 + j] += ra[r][i4 + j], j < i1, segmented over equal consecutive t
+    OP_ADD_REGION,     // ra[r][i2 + j] += rb[r][i3 + j], j < i1
+    OP_ACTNORM_BWD,    // ra (dY -> dZ in place) through LeakyReLU (i1) + channel norm of the layer whose output is rb
+    OP_WGRAD,          // dW[c*i2 + i3 + k] += sum_r ra[r][i4 + c] * rb[r][k], c < i0, k < i1; db[c] += sum_r ra[r][i4 + c]
+    OP_SCATTER_ADD,    // atomicAdd(dst[idx[row]*i0 + i2 + j], ra[r][i4 + j]), j < i1
+    OP_PAIR_SCATTER,   // atomicAdd into dst[a[row]] and dst[b[row]]
+    OP_SEGMAX_BWD,     // route d(pooled) rows in ra to the arg-max member rows of dst
 };
 
 struct Step {
     int op;
-    int i0, i1, i2, i3;
+    short ra, rb;
+    int i0, i1, i2, i3, i4, i5;
     const void* p0;
     const void* p1;
     const void* p2;
     const void* p3;
 };
 
-constexpr int MAX_STEPS = 40;
+constexpr int MAX_STEPS = 44;
+constexpr int MAX_REGIONS = 16;
+constexpr int MAX_SIGMA = 8;
 
 struct Program {
     int n_steps;
     int n_rows;
+    int tr;                 // rows per tile (64 forward, 32 backward)
+    int region_floats;      // total shared-memory floats of all regions
+    int reg_off[MAX_REGIONS];
+    int reg_ld[MAX_REGIONS];
     Step steps[MAX_STEPS];
 };
 

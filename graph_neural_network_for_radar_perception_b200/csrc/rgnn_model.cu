@@ -9,7 +9,7 @@ namespace rgnn {
 struct PackEntry {
     const float* W;   // (C, ldW) row-major
     float* dst;       // (Kpad, ldd)
-    int ldW, koff, K, C, Kpad, ldd, c0, cw;
+    int ldW, koff, K, C, Kpad, ldd, c0, cw, transpose;
 };
 constexpr int PACK_BATCH = 48;
 struct PackTable {
@@ -23,7 +23,7 @@ __global__ void pack_kernel(const __grid_constant__ PackTable tab) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
         const int k = i / e.cw, c = i - k * e.cw;
         float v = 0.f;
-        if (k < e.K && c < e.C) v = e.W[(size_t)c * e.ldW + e.koff + k];
+        if (k < e.K && c < e.C) v = e.transpose ? e.W[(size_t)c * e.ldW + e.koff + k] : e.W[(size_t)k * e.ldW + e.koff + c];
         e.dst[(size_t)k * e.ldd + e.c0 + c] = v;
     }
 }
@@ -40,8 +40,15 @@ struct Packer {
         tab.n = 0;
     }
     void push(const PackEntry& e) {
-        tab.e[tab.n++] = e;
-        if (tab.n == PACK_BATCH) flush();
+        tab.e[tab.n] = e;
+        tab.e[tab.n].transpose = 1;
+        if (++tab.n == PACK_BATCH) flush();
+    }
+    // plain (non transposed) copy: dst[r][c] = W[r][koff + c], r < K (rows), c < C (cols), zero padded to (Kpad, cw)
+    void push_nat(const PackEntry& e) {
+        tab.e[tab.n] = e;
+        tab.e[tab.n].transpose = 0;
+        if (++tab.n == PACK_BATCH) flush();
     }
     void linear(const rgnn_linear& L) {
         if (L.weight == nullptr || L.weight_t == nullptr) { set_error("pack: null weight pointer"); rc = RGNN_ERR_INVALID; return; }
@@ -62,6 +69,11 @@ struct Packer {
         push({L.weight, wp, ldW, 0, d.cn, d.h, cnp, ldp, 0, d.h});
         push({L.weight, wp, ldW, d.cn, d.cn, d.h, cnp, ldp, d.h, ldp - d.h});
         push({L.weight, wc, ldW, 2 * d.cn, d.ce, d.h, cep, ldc, 0, ldc});
+        // WP_nat[c][k] (2h x round_up(cn,64)) for the backward: rows [0,h) = W[:, 0:cn], rows [h,2h) = W[:, cn:2cn]
+        float* wn = wc + conv_msg0_edge_floats(d);
+        const int ldn = round_up(d.cn, 64);
+        push_nat({L.weight, wn, ldW, 0, d.h, d.cn, d.h, ldn, 0, ldn});
+        push_nat({L.weight, wn + (size_t)d.h * ldn, ldW, d.cn, d.h, d.cn, d.h, ldn, 0, ldn});
         for (int i = 1; i < c.msg.n; ++i) linear(c.msg.layer[i]);
         stack(c.upd);
     }
@@ -89,34 +101,61 @@ bool conv_dims(const rgnn_conv& c, ConvDims* d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward programs
+// forward programs (two ping-pong regions of the maximum width)
 // ---------------------------------------------------------------------------------------------
-static int stack_in(const rgnn_stack& s) { return s.layer[0].in_features; }
-static int stack_out(const rgnn_stack& s) { return s.layer[s.n - 1].out_features; }
+int stack_in(const rgnn_stack& s) { return s.layer[0].in_features; }
+int stack_out(const rgnn_stack& s) { return s.layer[s.n - 1].out_features; }
+
+struct FwdBuilder : ProgBuilder {
+    int cur, nxt;
+    explicit FwdBuilder(int n_rows) : ProgBuilder(n_rows, TR_FWD) {
+        cur = region(256);
+        nxt = region(256);
+    }
+    void swap() { int t = cur; cur = nxt; nxt = t; }
+    void lin(const rgnn_linear& L) { linear(cur, nxt, L); swap(); }
+    void stack(const rgnn_stack& s, int first = 0) { for (int i = first; i < s.n; ++i) lin(s.layer[i]); }
+    void proj(const rgnn_conv& c, const ConvDims& d, float* P) {
+        const int Cp = round_up(2 * d.h, 64), Kp = round_up(d.cn, 8);
+        gemm(cur, nxt, c.msg.layer[0].weight_t, Cp, Kp, Kp, 2 * d.h, Cp, nullptr);
+        swap();
+        store_rows(cur, P, 2 * d.h, 2 * d.h);
+    }
+};
 
 int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream) {
     RGNN_REQUIRE(s.n >= 1 && s.n <= RGNN_MAX_STACK, "stack with %d layers", s.n);
-    ProgBuilder b(n_rows);
-    b.load_rows(x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
+    FwdBuilder b(n_rows);
+    b.load_rows(b.cur, x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
     b.stack(s);
-    b.store_rows(y, stack_out(s), stack_out(s));
+    b.store_rows(b.cur, y, stack_out(s), stack_out(s));
     if (!b.ok) return RGNN_ERR_INVALID;
-    return launch_fwd(b.p, stream);
-}
-
-static void add_proj(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, float* P) {
-    b.add(OP_LINEAR, round_up(d.cn, 8), 2 * d.h, round_up(2 * d.h, 64), 0, c.msg.layer[0].weight_t, nullptr);
-    b.store_rows(P, 2 * d.h, 2 * d.h);
+    return launch_program(b.p, stream);
 }
 
 int run_proj(const rgnn_conv& c, const float* x, int n_nodes, float* P, cudaStream_t stream) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
-    ProgBuilder b(n_nodes);
-    b.load_rows(x, d.cn, d.cn);
-    add_proj(b, c, d, P);
+    RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
+    FwdBuilder b(n_nodes);
+    b.load_rows(b.cur, x, d.cn, d.cn, 0, round_up(d.cn, 8));
+    b.proj(c, d, P);
     if (!b.ok) return RGNN_ERR_INVALID;
-    return launch_fwd(b.p, stream);
+    return launch_program(b.p, stream);
+}
+
+// Recomputable part of the message function, shared by forward and backward builders:
+// z1 = e W_edge^T + b + P_t[tgt] + P_s[src]; y1 = act(norm(z1)); y2 = msg[1..](y1)
+void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* P,
+                        int r_in, int r_mid, int r_out, int slot0, int slot1) {
+    const rgnn_linear& m0 = c.msg.layer[0];
+    const int Kp = round_up(d.ce, 8), Cp = round_up(d.h, 64);
+    b.gemm(r_in, r_mid, m0.weight_t + conv_msg0_proj_floats(d), Cp, Kp, Kp, d.h, Cp, m0.bias);
+    Step* s = b.add(OP_ADD_GATHER2, r_mid);
+    s->p0 = P; s->p1 = g.tgt; s->p2 = g.src;
+    s->i0 = 2 * d.h; s->i1 = d.h; s->i2 = d.h;
+    b.norm_act(r_mid, m0, slot0);
+    b.linear(r_mid, r_out, c.msg.layer[1], slot1);
 }
 
 // message + aggregation: agg[t] = sum_{e: s->t} msg(x_t, x_s, e)
@@ -124,19 +163,17 @@ int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, co
                    cudaStream_t stream) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(c.msg.n == 2, "conv block: msg stack must have 2 ffn_blocks (has %d)", c.msg.n);
     RGNN_CHECK_CUDA(cudaMemsetAsync(agg, 0, (size_t)g.n_nodes * d.cn * sizeof(float), stream));
-    const rgnn_linear& m0 = c.msg.layer[0];
-    RGNN_REQUIRE(m0.weight_t != nullptr, "conv msg.0 not packed");
-    ProgBuilder b(g.n_edges);
-    b.load_rows(emb, d.ce, d.ce);
-    b.add(OP_LINEAR, round_up(d.ce, 8), d.h, round_up(d.h, 64), 0, m0.weight_t + conv_msg0_proj_floats(d), m0.bias);
-    b.add(OP_ADD_GATHER2, 2 * d.h, d.h, d.h, 0, P, g.tgt, g.src);
-    if (m0.norm_scale != nullptr || m0.activation)
-        b.add(OP_NORM_ACT, d.h, m0.activation, 0, 0, m0.norm_scale, m0.norm_shift);
-    b.stack(c.msg, 1);
-    b.add(OP_SEGSUM, d.cn, d.cn, 0, 0, agg, g.tgt, g.row_ptr);
+    RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
+    FwdBuilder b(g.n_edges);
+    b.load_rows(b.cur, emb, d.ce, d.ce, 0, round_up(d.ce, 8));
+    add_message_layers(b, c, d, g, P, b.cur, b.nxt, b.cur, -1, -1);
+    Step* s = b.add(OP_SEGSUM, b.cur);
+    s->p0 = agg; s->p1 = g.tgt; s->p2 = g.row_ptr;
+    s->i0 = d.cn; s->i1 = d.cn;
     if (!b.ok) return RGNN_ERR_INVALID;
-    return launch_fwd(b.p, stream);
+    return launch_program(b.p, stream);
 }
 
 // node update: out = x + upd(cat(x, agg)); optionally the next layer's projections
@@ -144,20 +181,21 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
                    const rgnn_conv* next, float* P_next, cudaStream_t stream) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
-    ProgBuilder b(n_nodes);
-    b.load_rows(x, d.cn, d.cn, 0);
-    b.load_rows(agg, d.cn, d.cn, d.cn);
+    FwdBuilder b(n_nodes);
+    b.load_rows(b.cur, x, d.cn, d.cn, 0);
+    b.load_rows(b.cur, agg, d.cn, d.cn, d.cn);
     b.stack(c.upd);
-    b.add(OP_ADD_ROWS, d.cn, d.cn, 0, 0, x);
-    b.store_rows(out, d.cn, d.cn);
+    Step* s = b.add(OP_ADD_ROWS, b.cur);
+    s->p0 = x; s->i0 = d.cn; s->i1 = d.cn;
+    b.store_rows(b.cur, out, d.cn, d.cn);
     if (next != nullptr) {
         ConvDims dn;
         if (!conv_dims(*next, &dn)) return RGNN_ERR_INVALID;
         RGNN_REQUIRE(dn.cn == d.cn, "conv blocks with different node widths");
-        add_proj(b, *next, dn, P_next);
+        b.proj(*next, dn, P_next);
     }
     if (!b.ok) return RGNN_ERR_INVALID;
-    return launch_fwd(b.p, stream);
+    return launch_program(b.p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -214,23 +252,23 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
     int rc;
     {   // node encoder (+ first layer's projections)
-        ProgBuilder b(N);
+        FwdBuilder b(N);
         const int in = stack_in(net.node_enc);
-        b.load_rows(node_features, in, in, 0, round_up(in, 8));
+        b.load_rows(b.cur, node_features, in, in, 0, round_up(in, 8));
         b.stack(net.node_enc);
-        b.store_rows(pl.x[0], d.cn, d.cn);
-        add_proj(b, net.conv[0], d, pl.P[0]);
+        b.store_rows(b.cur, pl.x[0], d.cn, d.cn);
+        b.proj(net.conv[0], d, pl.P[0]);
         if (!b.ok) return RGNN_ERR_INVALID;
-        if ((rc = launch_fwd(b.p, stream))) return rc;
+        if ((rc = launch_program(b.p, stream))) return rc;
     }
-    {   // edge encoder, rows gathered into target-major order
-        ProgBuilder b(E);
+    if (E > 0) {   // edge encoder, rows gathered into target-major order
+        FwdBuilder b(E);
         const int in = stack_in(net.edge_enc);
-        b.load_rows(edge_features, in, in, 0, round_up(in, 8), g.perm);
+        b.load_rows(b.cur, edge_features, in, in, 0, round_up(in, 8), g.perm);
         b.stack(net.edge_enc);
-        b.store_rows(pl.emb, d.ce, d.ce);
+        b.store_rows(b.cur, pl.emb, d.ce, d.ce);
         if (!b.ok) return RGNN_ERR_INVALID;
-        if ((rc = launch_fwd(b.p, stream))) return rc;
+        if ((rc = launch_program(b.p, stream))) return rc;
     }
     for (int l = 0; l < L; ++l) {
         if ((rc = run_conv_edges(net.conv[l], g, pl.emb, pl.P[l], pl.agg[l], stream))) return rc;
@@ -243,21 +281,23 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream))) return rc;
     if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream))) return rc;
     if (g.n_und > 0) {
-        ProgBuilder b(g.n_und);
-        b.add(OP_LOAD_PAIRSUM, pl.link_w, pl.link_w, 0, 0, pl.hlink, g.und_a, g.und_b);
+        FwdBuilder b(g.n_und);
+        Step* s = b.add(OP_LOAD_PAIRSUM, b.cur);
+        s->p0 = pl.hlink; s->p1 = g.und_a; s->p2 = g.und_b; s->i0 = pl.link_w; s->i1 = pl.link_w;
         b.stack(net.head_link);
-        b.store_rows(link_cls, stack_out(net.head_link), stack_out(net.head_link));
+        b.store_rows(b.cur, link_cls, stack_out(net.head_link), stack_out(net.head_link));
         if (!b.ok) return RGNN_ERR_INVALID;
-        if ((rc = launch_fwd(b.p, stream))) return rc;
+        if ((rc = launch_program(b.p, stream))) return rc;
     }
     if ((rc = run_stack_fwd(net.class_node, xL, N, pl.gcls, stream))) return rc;
     if (g.n_clusters > 0) {
-        ProgBuilder b(g.n_clusters);
-        b.add(OP_LOAD_SEGMAX, pl.cls_w, pl.cls_w, 0, 0, pl.gcls, g.cl_ptr, g.cl_members);
+        FwdBuilder b(g.n_clusters);
+        Step* s = b.add(OP_LOAD_SEGMAX, b.cur);
+        s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
         b.stack(net.head_class);
-        b.store_rows(obj_cls, stack_out(net.head_class), stack_out(net.head_class));
+        b.store_rows(b.cur, obj_cls, stack_out(net.head_class), stack_out(net.head_class));
         if (!b.ok) return RGNN_ERR_INVALID;
-        if ((rc = launch_fwd(b.p, stream))) return rc;
+        if ((rc = launch_program(b.p, stream))) return rc;
     }
     return RGNN_OK;
 }
@@ -347,5 +387,5 @@ extern "C" int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, 
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d);
+    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
 }

@@ -18,14 +18,11 @@ struct DetPlan {
     float* gcls;                   // predict_class.stem output per node
     // ---- backward only ----
     float* dx;       // (N, cn) running gradient w.r.t. the node embedding
-    float* dx2;      // (N, cn) second buffer (ping-pong between layers)
     float* dP;       // (N, 2h)
     float* dagg;     // (N, cn)
     float* demb;     // (E, ce) accumulated over all conv layers
     float* dh;       // (N, link_w)
     float* dg;       // (N, cls_w)
-    float* scratch;  // per-CTA parameter-gradient partial sums
-    size_t scratch_floats;
     size_t bytes;
 };
 
@@ -33,6 +30,10 @@ typedef std::function<float*(size_t)> TakeFn;
 int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, void* base, DetPlan* pl);
 void plan_detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const TakeFn& take, DetPlan* pl);
 
+int stack_in(const rgnn_stack& s);
+int stack_out(const rgnn_stack& s);
 int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream);
+void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* P,
+                        int r_in, int r_mid, int r_out, int slot0, int slot1);
 
 }  // namespace rgnn

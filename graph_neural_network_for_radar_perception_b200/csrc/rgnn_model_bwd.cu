@@ -1,21 +1,291 @@
-// Backward of the detector (placeholder until the backward tile programs land).
+// Backward of the detector as tile programs.  Every program first recomputes the forward activations of its
+// tile into shared memory (nothing per-edge is ever read back from HBM), then walks the layers in reverse:
+//   OP_ACTNORM_BWD (LeakyReLU + channel norm)  ->  OP_WGRAD (dW, db by RED into the gradient buffers)
+//   ->  OP_LINEAR with the natural-layout weight as operand (dX = dZ W).
+// Replaces torch autograd over gnn_blocks.py / gnn_detector.py (reference gnn/training.py:81).
+#include <vector>
+
 #include "rgnn_model.h"
 
 namespace rgnn {
-void plan_detector_bwd(const rgnn_detector&, const rgnn_graph&, const TakeFn&, DetPlan* pl) {
-    pl->dx = pl->dx2 = pl->dP = pl->dagg = pl->demb = pl->dh = pl->dg = pl->scratch = nullptr;
-    pl->scratch_floats = 0;
+
+struct BwdBuilder : ProgBuilder {
+    int wcur, wnxt;
+    explicit BwdBuilder(int n_rows) : ProgBuilder(n_rows, TR_BWD), wcur(-1), wnxt(-1) {}
+    void work_regions() {
+        wcur = region(256);
+        wnxt = region(256);
+    }
+    void swap() { int t = wcur; wcur = wnxt; wnxt = t; }
+
+    // forward recompute of layers [first, n): outputs go to fresh regions, one sigma slot per normalised layer
+    void chain_fwd(const rgnn_stack& s, int first, int r_in, std::vector<int>& regs, std::vector<int>& slots) {
+        regs.assign(s.n, -1);
+        slots.assign(s.n, -1);
+        int prev = r_in;
+        for (int i = first; i < s.n; ++i) {
+            const rgnn_linear& L = s.layer[i];
+            regs[i] = region(round_up(L.out_features, 64));
+            if (L.norm_scale != nullptr) slots[i] = sigma_slot();
+            linear(prev, regs[i], L, slots[i]);
+            prev = regs[i];
+        }
+    }
+
+    void actnorm_bwd(const rgnn_linear& L, int r_y, int slot) {
+        if (L.norm_scale == nullptr && !L.activation) return;
+        Step* st = add(OP_ACTNORM_BWD, wcur, r_y);
+        st->i0 = L.out_features; st->i1 = L.activation; st->i2 = slot < 0 ? 0 : slot;
+        st->p0 = L.norm_scale; st->p1 = L.norm_shift; st->p2 = L.grad_norm_scale; st->p3 = L.grad_norm_shift;
+    }
+
+    void wgrad(int r_dz, int r_x, int C, int K, float* dW, int ldW, int wcol, int zcol, float* db) {
+        if (dW == nullptr && db == nullptr) return;
+        Step* st = add(OP_WGRAD, r_dz, r_x);
+        st->i0 = C; st->i1 = K; st->i2 = ldW; st->i3 = wcol; st->i4 = zcol;
+        st->p0 = dW; st->p1 = db;
+    }
+
+    // dX = dZ * W with W in its natural (out, in) layout: rows = reduction index
+    bool dgrad(const float* W, int ldw, int n_out_rows, int n_in_cols) {
+        if (n_in_cols % 64 != 0) {
+            set_error("backward: input width %d of a differentiated Linear must be a multiple of 64", n_in_cols);
+            ok = false;
+            return false;
+        }
+        gemm(wcur, wnxt, W, ldw, round_up(n_out_rows, 8), n_out_rows, n_in_cols, n_in_cols, nullptr);
+        swap();
+        return true;
+    }
+
+    // reverse pass over layers [first, n); dY is in wcur on entry, dX (if wanted) in wcur on exit
+    void chain_bwd(const rgnn_stack& s, int first, int r_in, const std::vector<int>& regs, const std::vector<int>& slots,
+                   bool need_dx_first) {
+        for (int i = s.n - 1; i >= first; --i) {
+            const rgnn_linear& L = s.layer[i];
+            actnorm_bwd(L, regs[i], slots[i]);
+            const int r_x = (i == first) ? r_in : regs[i - 1];
+            wgrad(wcur, r_x, L.out_features, L.in_features, L.grad_weight, L.in_features, 0, 0, L.grad_bias);
+            if (i > first || need_dx_first) dgrad(L.weight, L.in_features, L.out_features, L.in_features);
+        }
+    }
+
+    void zero_region(int r, int w) { load_rows(r, nullptr, 4, 0, 0, w); }
+    void add_region(int ra, int rb, int w, int ca = 0, int cb = 0) {
+        Step* st = add(OP_ADD_REGION, ra, rb);
+        st->i1 = w; st->i2 = ca; st->i3 = cb;
+    }
+};
+
+// generic ffn-stack backward; x rows optionally gathered through ridx
+static int stack_bwd(const rgnn_stack& s, const float* x, const int* ridx, const float* grad_y, int n_rows,
+                     float* grad_x, bool accumulate_gx, cudaStream_t stream) {
+    RGNN_REQUIRE(s.n >= 1 && s.n <= RGNN_MAX_STACK, "stack with %d layers", s.n);
+    BwdBuilder b(n_rows);
+    const int in = stack_in(s), out = stack_out(s);
+    const int r_in = b.region(round_up(in, 8));
+    b.load_rows(r_in, x, in, in, 0, round_up(in, 8), ridx);
+    std::vector<int> regs, slots;
+    b.chain_fwd(s, 0, r_in, regs, slots);
+    b.work_regions();
+    b.load_rows(b.wcur, grad_y, out, out, 0, round_up(out, 8));
+    b.chain_bwd(s, 0, r_in, regs, slots, grad_x != nullptr);
+    if (grad_x != nullptr) b.store_rows(b.wcur, grad_x, in, in, 0, accumulate_gx);
+    if (!b.ok) return RGNN_ERR_INVALID;
+    return launch_program(b.p, stream);
 }
-int launch_bwd(const Program&, cudaStream_t) { set_error("backward not built"); return RGNN_ERR_INVALID; }
+
+// dL/dP (N, 2h) -> weight gradient of the projection part of msg.0 and the contribution to dL/dx, added into wcur
+static void proj_bwd(BwdBuilder& b, const rgnn_conv& c, const ConvDims& d, const float* dP, int r_x, int r_tmp) {
+    const rgnn_linear& m0 = c.msg.layer[0];
+    b.load_rows(b.wnxt, dP, 2 * d.h, 2 * d.h);
+    // msg.0.weight (h, 2cn+ce): columns [0,cn) act on x_target, [cn,2cn) on x_source (gnn_blocks.py:113)
+    b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, 0, 0, nullptr);
+    b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, d.cn, d.h, nullptr);
+    const float* wp_nat = m0.weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d);
+    b.gemm(b.wnxt, r_tmp, wp_nat, round_up(d.cn, 64), 2 * d.h, 2 * d.h, d.cn, round_up(d.cn, 64), nullptr);
+    b.add_region(b.wcur, r_tmp, d.cn);
+}
+
+static int conv_nodes_bwd(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg,
+                          const rgnn_conv* next, const float* x_next, const float* dP_next, float* dx, float* dagg,
+                          cudaStream_t stream) {
+    BwdBuilder b(n_nodes);
+    const int r_cat = b.region(2 * d.cn);
+    b.load_rows(r_cat, x, d.cn, d.cn, 0);
+    b.load_rows(r_cat, agg, d.cn, d.cn, d.cn);
+    std::vector<int> regs, slots;
+    b.chain_fwd(c.upd, 0, r_cat, regs, slots);
+    const int r_keep = b.region(d.cn);
+    int r_xn = -1, r_tmp = -1;
+    if (next != nullptr) {
+        r_xn = b.region(d.cn);
+        r_tmp = b.region(round_up(d.cn, 64));
+    }
+    b.work_regions();
+    b.load_rows(b.wcur, dx, d.cn, d.cn, 0, round_up(d.cn, 8));
+    if (next != nullptr) {
+        b.load_rows(r_xn, x_next, d.cn, d.cn, 0, round_up(d.cn, 8));
+        proj_bwd(b, *next, d, dP_next, r_xn, r_tmp);
+    }
+    b.zero_region(r_keep, d.cn);
+    b.add_region(r_keep, b.wcur, d.cn);           // dL/dx_{l+1}: needed again for the identity residual
+    b.chain_bwd(c.upd, 0, r_cat, regs, slots, true);
+    b.add_region(b.wcur, r_keep, d.cn);
+    b.store_rows(b.wcur, dx, d.cn, d.cn, 0, false, 0);
+    b.store_rows(b.wcur, dagg, d.cn, d.cn, 0, false, d.cn);
+    if (!b.ok) return RGNN_ERR_INVALID;
+    return launch_program(b.p, stream);
+}
+
+static int conv_edges_bwd(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
+                          const float* dagg, float* dP, float* demb, bool first_demb, cudaStream_t stream) {
+    RGNN_REQUIRE(c.msg.n == 2, "conv block: msg stack must have 2 ffn_blocks");
+    RGNN_CHECK_CUDA(cudaMemsetAsync(dP, 0, (size_t)g.n_nodes * 2 * d.h * sizeof(float), stream));
+    if (g.n_edges == 0) return RGNN_OK;
+    const rgnn_linear& m0 = c.msg.layer[0];
+    const rgnn_linear& m1 = c.msg.layer[1];
+    BwdBuilder b(g.n_edges);
+    const int r_e = b.region(round_up(d.ce, 8));
+    const int r_1 = b.region(round_up(d.h, 64));
+    const int r_2 = b.region(round_up(d.cn, 64));
+    const int s0 = m0.norm_scale ? b.sigma_slot() : -1;
+    const int s1 = m1.norm_scale ? b.sigma_slot() : -1;
+    b.load_rows(r_e, emb, d.ce, d.ce, 0, round_up(d.ce, 8));
+    add_message_layers(b, c, d, g, P, r_e, r_1, r_2, s0, s1);
+    b.work_regions();
+    b.load_rows(b.wcur, dagg, d.cn, d.cn, 0, round_up(d.cn, 8), g.tgt);      // d(message) = d(agg)[target]
+    b.actnorm_bwd(m1, r_2, s1);
+    b.wgrad(b.wcur, r_1, m1.out_features, m1.in_features, m1.grad_weight, m1.in_features, 0, 0, m1.grad_bias);
+    b.dgrad(m1.weight, m1.in_features, m1.out_features, m1.in_features);
+    b.actnorm_bwd(m0, r_1, s0);                                               // wcur = dz1 (E_tile, h)
+    b.wgrad(b.wcur, r_e, d.h, d.ce, m0.grad_weight, m0.in_features, 2 * d.cn, 0, m0.grad_bias);
+    const int r_dz1 = b.wcur;
+    if (d.ce % 64 != 0) { set_error("backward: edge width must be a multiple of 64"); return RGNN_ERR_INVALID; }
+    b.gemm(b.wcur, b.wnxt, m0.weight + 2 * d.cn, m0.in_features, round_up(d.h, 8), d.h, d.ce, d.ce, nullptr);
+    b.store_rows(b.wnxt, demb, d.ce, d.ce, 0, !first_demb);
+    Step* s = b.add(OP_SEGSUM, r_dz1);
+    s->p0 = dP; s->p1 = g.tgt; s->p2 = g.row_ptr;
+    s->i0 = 2 * d.h; s->i1 = d.h; s->i2 = 0; s->i4 = 0;
+    s = b.add(OP_SCATTER_ADD, r_dz1);
+    s->p0 = dP; s->p1 = g.src;
+    s->i0 = 2 * d.h; s->i1 = d.h; s->i2 = d.h; s->i4 = 0;
+    if (!b.ok) return RGNN_ERR_INVALID;
+    return launch_program(b.p, stream);
+}
+
+void plan_detector_bwd(const rgnn_detector&, const rgnn_graph& g, const TakeFn& take, DetPlan* pl) {
+    const size_t N = (size_t)g.n_nodes, E = (size_t)g.n_edges;
+    pl->dx = take(N * pl->d.cn);
+    pl->dP = take(N * 2 * pl->d.h);
+    pl->dagg = take(N * pl->d.cn);
+    pl->demb = take((E > 0 ? E : 1) * pl->d.ce);
+    pl->dh = take(N * pl->link_w);
+    pl->dg = take(N * pl->cls_w);
+}
+
+static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const float* node_features,
+                        const float* edge_features, const float* g_node_cls, const float* g_node_off,
+                        const float* g_link, const float* g_obj, const DetPlan& pl, cudaStream_t stream) {
+    const ConvDims& d = pl.d;
+    const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
+    const float* xL = pl.x[L];
+    int rc;
+    // ---- heads: accumulate dL/dx_L in pl.dx ----
+    if ((rc = stack_bwd(net.head_node, xL, nullptr, g_node_cls, N, pl.dx, false, stream))) return rc;
+    if ((rc = stack_bwd(net.head_offset, xL, nullptr, g_node_off, N, pl.dx, true, stream))) return rc;
+    RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dh, 0, (size_t)N * pl.link_w * sizeof(float), stream));
+    if (g.n_und > 0) {
+        BwdBuilder b(g.n_und);
+        const int r_in = b.region(pl.link_w);
+        Step* s = b.add(OP_LOAD_PAIRSUM, r_in);
+        s->p0 = pl.hlink; s->p1 = g.und_a; s->p2 = g.und_b; s->i0 = pl.link_w; s->i1 = pl.link_w;
+        std::vector<int> regs, slots;
+        b.chain_fwd(net.head_link, 0, r_in, regs, slots);
+        b.work_regions();
+        const int out = stack_out(net.head_link);
+        b.load_rows(b.wcur, g_link, out, out, 0, round_up(out, 8));
+        b.chain_bwd(net.head_link, 0, r_in, regs, slots, true);
+        s = b.add(OP_PAIR_SCATTER, b.wcur);
+        s->p0 = pl.dh; s->p1 = g.und_a; s->p2 = g.und_b; s->i0 = pl.link_w; s->i1 = pl.link_w;
+        if (!b.ok) return RGNN_ERR_INVALID;
+        if ((rc = launch_program(b.p, stream))) return rc;
+    }
+    if ((rc = stack_bwd(net.link_node, xL, nullptr, pl.dh, N, pl.dx, true, stream))) return rc;
+    RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dg, 0, (size_t)N * pl.cls_w * sizeof(float), stream));
+    if (g.n_clusters > 0) {
+        BwdBuilder b(g.n_clusters);
+        const int r_in = b.region(pl.cls_w);
+        Step* s = b.add(OP_LOAD_SEGMAX, r_in);
+        s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
+        std::vector<int> regs, slots;
+        b.chain_fwd(net.head_class, 0, r_in, regs, slots);
+        b.work_regions();
+        const int out = stack_out(net.head_class);
+        b.load_rows(b.wcur, g_obj, out, out, 0, round_up(out, 8));
+        b.chain_bwd(net.head_class, 0, r_in, regs, slots, true);
+        s = b.add(OP_SEGMAX_BWD, b.wcur);
+        s->p0 = pl.dg; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->p3 = pl.gcls; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
+        if (!b.ok) return RGNN_ERR_INVALID;
+        if ((rc = launch_program(b.p, stream))) return rc;
+    }
+    if ((rc = stack_bwd(net.class_node, xL, nullptr, pl.dg, N, pl.dx, true, stream))) return rc;
+
+    // ---- message-passing layers, last to first ----
+    for (int l = L - 1; l >= 0; --l) {
+        const bool has_next = l + 1 < L;
+        if ((rc = conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], has_next ? &net.conv[l + 1] : nullptr,
+                                 has_next ? pl.x[l + 1] : nullptr, has_next ? pl.dP : nullptr, pl.dx, pl.dagg, stream)))
+            return rc;
+        if ((rc = conv_edges_bwd(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, stream)))
+            return rc;
+    }
+    // ---- node encoder (receives dL/dx_0 and the projection gradient of layer 0) ----
+    {
+        BwdBuilder b(N);
+        const rgnn_stack& s = net.node_enc;
+        const int in = stack_in(s);
+        const int r_in = b.region(round_up(in, 8));
+        b.load_rows(r_in, node_features, in, in, 0, round_up(in, 8));
+        std::vector<int> regs, slots;
+        b.chain_fwd(s, 0, r_in, regs, slots);
+        const int r_tmp = b.region(round_up(d.cn, 64));
+        b.work_regions();
+        b.load_rows(b.wcur, pl.dx, d.cn, d.cn, 0, round_up(d.cn, 8));
+        proj_bwd(b, net.conv[0], d, pl.dP, regs[s.n - 1], r_tmp);
+        b.chain_bwd(s, 0, r_in, regs, slots, false);
+        if (!b.ok) return RGNN_ERR_INVALID;
+        if ((rc = launch_program(b.p, stream))) return rc;
+    }
+    // ---- edge encoder ----
+    if (E > 0) {
+        if ((rc = stack_bwd(net.edge_enc, edge_features, g.perm, pl.demb, E, nullptr, false, stream))) return rc;
+    }
+    return RGNN_OK;
+}
+
 }  // namespace rgnn
 
+using namespace rgnn;
+
 extern "C" size_t rgnn_ffn_stack_bwd_workspace_bytes(const rgnn_stack*) { return 0; }
-extern "C" int rgnn_ffn_stack_bwd(const rgnn_stack*, const float*, const float*, int, float*, void*, size_t, void*) {
-    rgnn::set_error("backward not built");
-    return RGNN_ERR_INVALID;
+
+extern "C" int rgnn_ffn_stack_bwd(const rgnn_stack* stack, const float* x, const float* grad_y, int n_rows, float* grad_x,
+                                  void*, size_t, void* stream) {
+    return stack_bwd(*stack, x, nullptr, grad_y, n_rows, grad_x, false, static_cast<cudaStream_t>(stream));
 }
-extern "C" int rgnn_detector_bwd(const rgnn_detector*, const rgnn_graph*, const float*, const float*, const float*,
-                                 const float*, const float*, const float*, void*, size_t, void*) {
-    rgnn::set_error("backward not built");
-    return RGNN_ERR_INVALID;
+
+extern "C" int rgnn_detector_bwd(const rgnn_detector* net, const rgnn_graph* g, const float* node_features,
+                                 const float* edge_features, const float* grad_node_cls, const float* grad_node_off,
+                                 const float* grad_link_cls, const float* grad_obj_cls, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    DetPlan pl;
+    int rc = plan_detector(*net, *g, 1, workspace, &pl);
+    if (rc) return rc;
+    if (pl.bytes > workspace_bytes) {
+        set_error("detector workspace too small for backward: need %zu bytes, got %zu", pl.bytes, workspace_bytes);
+        return RGNN_ERR_WORKSPACE;
+    }
+    return detector_bwd(*net, *g, node_features, edge_features, grad_node_cls, grad_node_off, grad_link_cls,
+                        grad_obj_cls, pl, static_cast<cudaStream_t>(stream));
 }

@@ -10,8 +10,6 @@
 
 namespace rgnn {
 
-constexpr int LD = 260;   // smem row stride in floats: 256 + 4 (keeps float4 alignment, spreads rows over banks)
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
@@ -22,25 +20,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : LEAKY * v; }
 
-// Copy rows [k0, k0+kn) x cols [cb, cb+bw) of the k-major weight Wt (row stride ldw) into a stage buffer
-// laid out [KC][CBMAX].
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Copy rows [k0, k0+kn) x cols [cb, cb+bw) of the k-major operand Wt (row stride ldw) into a stage buffer laid
+// out [KC][CBMAX].  Rows at or beyond k_valid do not exist in memory and are zero-filled.
 __device__ __forceinline__ void stage_weights(float* ws, const float* __restrict__ Wt, int ldw, int k0, int kn,
-                                              int cb, int bw) {
+                                              int k_valid, int cb, int bw) {
     const int per_row = bw >> 2;
     const int tot = kn * per_row;
     for (int i = threadIdx.x; i < tot; i += NT) {
         const int r = i / per_row, c4 = i - r * per_row;
-        cp_async16(ws + r * CBMAX + 4 * c4, Wt + (size_t)(k0 + r) * ldw + cb + 4 * c4);
+        float* d = ws + r * CBMAX + 4 * c4;
+        if (k0 + r < k_valid)
+            cp_async16(d, Wt + (size_t)(k0 + r) * ldw + cb + 4 * c4);
+        else
+            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// Y[TR][LD] = X[TR][LD] * Wt[K][ldw] (+ bias[c], c < C).  K multiple of 8, Cpad multiple of 64.
-// X columns [K_true, K) must be zero-filled by the producer.  Thread (ty,tx) = (tid/16, tid%16) owns rows
-// ty*RPT.. and columns cb + 4*tx.. (+64).  Ends with a __syncthreads().
+// One output-column block of Y[TR][ldy] = X[TR][ldx] * Wt[K][ldw] (+ bias[c], c < C).
+// K multiple of 8 (X columns [K_true, K) are zero-filled by the producer), bw = 64 or 128.
+// Thread (ty,tx) = (tid/16, tid%16) owns rows ty*RPT.. and columns cb + 4*tx.. (+64 when TWO).
 template <int TR, bool TWO>
-__device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, int K, const float* __restrict__ Wt,
-                                                int ldw, int cb, int bw, const float* __restrict__ bias, int C,
-                                                float* __restrict__ Ys, float* __restrict__ wstage) {
+__device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, int ldx, int K, int k_valid,
+                                                const float* __restrict__ Wt, int ldw, int cb, int bw,
+                                                const float* __restrict__ bias, int C, float* __restrict__ Ys, int ldy,
+                                                float* __restrict__ wstage) {
     constexpr int RPT = TR / 16;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     float acc[RPT][TWO ? 8 : 4];
@@ -50,11 +59,12 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
         for (int j = 0; j < (TWO ? 8 : 4); ++j) acc[i][j] = 0.f;
 
     const int nch = (K + KC - 1) / KC;
-    stage_weights(wstage, Wt, ldw, 0, min(KC, K), cb, bw);
+    stage_weights(wstage, Wt, ldw, 0, min(KC, K), k_valid, cb, bw);
     cp_async_commit();
     for (int ch = 0; ch < nch; ++ch) {
         if (ch + 1 < nch) {
-            stage_weights(wstage + ((ch + 1) & 1) * KC * CBMAX, Wt, ldw, (ch + 1) * KC, min(KC, K - (ch + 1) * KC), cb, bw);
+            stage_weights(wstage + ((ch + 1) & 1) * KC * CBMAX, Wt, ldw, (ch + 1) * KC, min(KC, K - (ch + 1) * KC),
+                          k_valid, cb, bw);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -63,12 +73,12 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
         __syncthreads();
         const float* ws = wstage + (ch & 1) * KC * CBMAX;
         const int kn = min(KC, K - ch * KC);
-        const float* xrow = Xs + (ty * RPT) * LD + ch * KC;
+        const float* xrow = Xs + (ty * RPT) * ldx + ch * KC;
 #pragma unroll 2
         for (int kk = 0; kk < kn; kk += 4) {
             float4 xv[RPT];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + i * LD + kk);
+            for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + i * ldx + kk);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 w0 = *reinterpret_cast<const float4*>(ws + (kk + q) * CBMAX + 4 * tx);
@@ -92,7 +102,6 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
         }
         __syncthreads();
     }
-    // epilogue: bias, write to the output tile
     const int c0 = cb + 4 * tx;
     float b[TWO ? 8 : 4];
 #pragma unroll
@@ -103,7 +112,7 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
     }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-        float* y = Ys + (ty * RPT + i) * LD + c0;
+        float* y = Ys + (ty * RPT + i) * ldy + c0;
         *reinterpret_cast<float4*>(y) = make_float4(acc[i][0] + b[0], acc[i][1] + b[1], acc[i][2] + b[2], acc[i][3] + b[3]);
         if (TWO)
             *reinterpret_cast<float4*>(y + 64) =
@@ -111,44 +120,35 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
     }
 }
 
+// Y = X * Wt (+bias) over all Cpad output columns (Cpad multiple of 64).  Ends with __syncthreads().
 template <int TR>
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ Xs, int K, const float* __restrict__ Wt, int ldw,
-                                          int Cpad, const float* __restrict__ bias, int C, float* __restrict__ Ys,
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ Xs, int ldx, int K, int k_valid,
+                                          const float* __restrict__ Wt, int ldw, int Cpad,
+                                          const float* __restrict__ bias, int C, float* __restrict__ Ys, int ldy,
                                           float* __restrict__ wstage) {
     for (int cb = 0; cb < Cpad; cb += CBMAX) {
         const int bw = min(CBMAX, Cpad - cb);
         if (bw > 64)
-            tile_gemm_block<TR, true>(Xs, K, Wt, ldw, cb, bw, bias, C, Ys, wstage);
+            tile_gemm_block<TR, true>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage);
         else
-            tile_gemm_block<TR, false>(Xs, K, Wt, ldw, cb, bw, bias, C, Ys, wstage);
+            tile_gemm_block<TR, false>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage);
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// In-place per-row channel_normalization (reference common.py:215-220) and LeakyReLU on a [TR][LD] tile.
-// C is a multiple of 32 when has_norm.  If sigma_out != nullptr the row's unbiased std is stored there.
-// One warp per row; lane owns columns lane + 32 q.
+// In-place per-row channel_normalization (reference common.py:215-220: mean, UNBIASED std, eps added to the
+// std, scalar affine) and LeakyReLU on a [TR][ld] tile.  C multiple of 32 (<= 256) when normalising.
+// One warp per row; lane owns columns lane + 32 q.  sigma_out (nullable): the row's std, kept for the backward.
 template <int TR>
-__device__ __forceinline__ void tile_norm_act(float* __restrict__ Ys, int C, const float* __restrict__ scale_p,
+__device__ __forceinline__ void tile_norm_act(float* __restrict__ Ys, int ld, int C, const float* __restrict__ scale_p,
                                               const float* __restrict__ shift_p, bool act,
                                               float* __restrict__ sigma_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool has_norm = scale_p != nullptr;
-    float scale = 1.f, shift = 0.f;
-    if (has_norm) {
-        scale = __ldg(scale_p);
-        shift = __ldg(shift_p);
-    }
-    if (has_norm) {
+    if (scale_p != nullptr) {
+        const float scale = __ldg(scale_p), shift = __ldg(shift_p);
         const int nq = C >> 5;
         for (int r = warp; r < TR; r += NT / 32) {
-            float* y = Ys + r * LD;
+            float* y = Ys + r * ld;
             float v[8];
             float s = 0.f;
 #pragma unroll
@@ -179,7 +179,7 @@ __device__ __forceinline__ void tile_norm_act(float* __restrict__ Ys, int C, con
     } else if (act) {
         for (int i = threadIdx.x; i < TR * C; i += NT) {
             const int r = i / C, j = i - r * C;
-            Ys[r * LD + j] = leaky(Ys[r * LD + j]);
+            Ys[r * ld + j] = leaky(Ys[r * ld + j]);
         }
     }
     __syncthreads();
