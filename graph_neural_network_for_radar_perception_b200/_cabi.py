@@ -65,6 +65,8 @@ _SZ = C.c_size_t
 SIGNATURES = {
     'rgnn_version': (_I, []),
     'rgnn_last_error': (C.c_char_p, []),
+    'rgnn_set_option': (_I, [C.c_char_p, _I]),
+    'rgnn_get_option': (_I, [C.c_char_p]),
     'rgnn_graph_build_workspace_bytes': (_SZ, [_I, _I, _I]),
     'rgnn_graph_build': (_I, [_V, _V, _V, _V, _I, _I, C.c_float, _I, _I, _V, _V, _V, C.c_int32, _V, _V, _SZ, _V]),
     'rgnn_graph_finalize_workspace_bytes': (_SZ, [_I, _I]),

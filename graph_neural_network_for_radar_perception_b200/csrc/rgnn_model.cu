@@ -76,6 +76,11 @@ struct Packer {
         push_nat({L.weight, wn + (size_t)d.h * ldn, ldW, d.cn, d.h, d.cn, d.h, ldn, 0, ldn});
         for (int i = 1; i < c.msg.n; ++i) linear(c.msg.layer[i]);
         stack(c.upd);
+        // hi/lo split operands of the tcgen05 message kernel (after the three FFMA-path blocks)
+        if (c.msg.n == 2 && c.msg.layer[1].weight != nullptr) {
+            const int r = mp_tc_pack(c, d, wn + conv_msg0_projnat_floats(d), stream);
+            if (r != RGNN_OK) rc = r;
+        }
     }
 };
 
@@ -166,6 +171,10 @@ int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, co
     RGNN_REQUIRE(c.msg.n == 2, "conv block: msg stack must have 2 ffn_blocks (has %d)", c.msg.n);
     RGNN_CHECK_CUDA(cudaMemsetAsync(agg, 0, (size_t)g.n_nodes * d.cn * sizeof(float), stream));
     RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
+    if (g.n_edges > 0 && mp_tc_supported(d)) {
+        const float* wpack = c.msg.layer[0].weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
+        return run_conv_edges_tc(c, d, g, emb, P, wpack, agg, stream);
+    }
     FwdBuilder b(g.n_edges);
     b.load_rows(b.cur, emb, d.ce, d.ce, 0, round_up(d.ce, 8));
     add_message_layers(b, c, d, g, P, b.cur, b.nxt, b.cur, -1, -1);
@@ -387,5 +396,5 @@ extern "C" int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, 
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
+    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d) + mp_tc_pack_floats(d);
 }

@@ -36,4 +36,11 @@ int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cud
 void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* P,
                         int r_in, int r_mid, int r_out, int slot0, int slot1);
 
+// tensor-core (tcgen05) message kernel, rgnn_mp_tc.cu
+bool mp_tc_supported(const ConvDims& d);
+size_t mp_tc_pack_floats(const ConvDims& d);      // extra floats at the end of msg.0's packed buffer
+int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
+int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
+                      const float* wpack, float* agg, cudaStream_t stream);
+
 }  // namespace rgnn

@@ -36,6 +36,14 @@ extern "C" {
 int rgnn_version(void);
 const char* rgnn_last_error(void);
 
+/* Process-wide numeric options (the reference has none: it always computes in fp32).
+ *   "tf32_passes"  3 (default) = 3xTF32 split-operand tensor-core products, fp32-equivalent (parity mode);
+ *                  1           = single TF32 pass (faster, ~1e-3 relative error per layer; never the default)
+ *   "tensor_cores" 1 (default) = tcgen05 kernels where the channel plan allows; 0 = FFMA tile programs only.
+ * rgnn_get_option returns -1 for an unknown name. */
+int rgnn_set_option(const char* name, int value);
+int rgnn_get_option(const char* name);
+
 /* ------------------------------------------------------------------------------------------------
  * One reference `ffn_block` (modules/neural_net/common.py:185-205): nn.Linear, optional
  * channel_normalization (:208-220; scalar affine `std`,`mu`), optional LeakyReLU(0.01) (:256-267).
@@ -162,7 +170,9 @@ int rgnn_pack_linear(const float* weight, int in_features, int out_features, flo
 /* Pack every Linear of a stack / conv block / detector (weight -> weight_t) in one launch.
  * The first Linear of a conv block's msg stack (in = 2*Cn+Ce) is packed as two operands back to back:
  * the node projection [W_target^T | W_source^T] (round_up(Cn,8) x round_up(2H,64)) followed by the edge part
- * W_edge^T (round_up(Ce,8) x round_up(H,64)); its weight_t buffer needs rgnn_packed_conv_msg0_floats floats. */
+ * W_edge^T (round_up(Ce,8) x round_up(H,64)), the natural-layout projection for the backward and -- for the channel
+ * plan of the reference configuration (Cn=Ce=64, H=128) -- the hi/lo split tensor-core operands of msg.0's edge
+ * part and of msg.1; its weight_t buffer needs rgnn_packed_conv_msg0_floats floats. */
 size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden);
 int rgnn_pack_stack(const rgnn_stack* stack, void* stream);
 int rgnn_pack_conv(const rgnn_conv* blk, void* stream);
