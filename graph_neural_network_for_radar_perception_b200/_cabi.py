@@ -109,6 +109,11 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)          # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
+        # optional process-wide numeric options (include/rgnn.h: rgnn_set_option), e.g. RGNN_OPT_TENSOR_CORES=0
+        for key, val in os.environ.items():
+            if key.startswith('RGNN_OPT_'):
+                if l.rgnn_set_option(key[len('RGNN_OPT_'):].lower().encode(), int(val)) != 0:
+                    raise RgnnError(f'{key}={val}: ' + l.rgnn_last_error().decode())
         _lib = l
     return _lib
 

@@ -74,11 +74,16 @@ struct Packer {
         const int ldn = round_up(d.cn, 64);
         push_nat({L.weight, wn, ldW, 0, d.h, d.cn, d.h, ldn, 0, ldn});
         push_nat({L.weight, wn + (size_t)d.h * ldn, ldW, d.cn, d.h, d.cn, d.h, ldn, 0, ldn});
+        // bias2h = [bias | 0]
+        float* wb = wn + conv_msg0_projnat_floats(d);
+        const int ldb = (int)conv_msg0_bias_floats(d);
+        if (L.bias != nullptr) push_nat({L.bias, wb, d.h, 0, 1, d.h, 1, ldb, 0, ldb});
+        else if (cudaMemsetAsync(wb, 0, ldb * sizeof(float), stream) != cudaSuccess) rc = RGNN_ERR_CUDA;
         for (int i = 1; i < c.msg.n; ++i) linear(c.msg.layer[i]);
         stack(c.upd);
         // hi/lo split operands of the tcgen05 message kernel (after the three FFMA-path blocks)
         if (c.msg.n == 2 && c.msg.layer[1].weight != nullptr) {
-            const int r = mp_tc_pack(c, d, wn + conv_msg0_projnat_floats(d), stream);
+            const int r = mp_tc_pack(c, d, wp + conv_msg0_tc_offset(d), stream);
             if (r != RGNN_OK) rc = r;
         }
     }
@@ -122,7 +127,8 @@ struct FwdBuilder : ProgBuilder {
     void stack(const rgnn_stack& s, int first = 0) { for (int i = first; i < s.n; ++i) lin(s.layer[i]); }
     void proj(const rgnn_conv& c, const ConvDims& d, float* P) {
         const int Cp = round_up(2 * d.h, 64), Kp = round_up(d.cn, 8);
-        gemm(cur, nxt, c.msg.layer[0].weight_t, Cp, Kp, Kp, 2 * d.h, Cp, nullptr);
+        const float* bias2h = c.msg.layer[0].weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
+        gemm(cur, nxt, c.msg.layer[0].weight_t, Cp, Kp, Kp, 2 * d.h, Cp, bias2h);
         swap();
         store_rows(cur, P, 2 * d.h, 2 * d.h);
     }
@@ -150,12 +156,12 @@ int run_proj(const rgnn_conv& c, const float* x, int n_nodes, float* P, cudaStre
 }
 
 // Recomputable part of the message function, shared by forward and backward builders:
-// z1 = e W_edge^T + b + P_t[tgt] + P_s[src]; y1 = act(norm(z1)); y2 = msg[1..](y1)
+// z1 = e W_edge^T + P_t[tgt] + P_s[src] (P_t carries the bias); y1 = act(norm(z1)); y2 = msg[1..](y1)
 void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* P,
                         int r_in, int r_mid, int r_out, int slot0, int slot1) {
     const rgnn_linear& m0 = c.msg.layer[0];
     const int Kp = round_up(d.ce, 8), Cp = round_up(d.h, 64);
-    b.gemm(r_in, r_mid, m0.weight_t + conv_msg0_proj_floats(d), Cp, Kp, Kp, d.h, Cp, m0.bias);
+    b.gemm(r_in, r_mid, m0.weight_t + conv_msg0_proj_floats(d), Cp, Kp, Kp, d.h, Cp, nullptr);   // bias is inside P_t
     Step* s = b.add(OP_ADD_GATHER2, r_mid);
     s->p0 = P; s->p1 = g.tgt; s->p2 = g.src;
     s->i0 = 2 * d.h; s->i1 = d.h; s->i2 = d.h;
@@ -172,7 +178,7 @@ int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, co
     RGNN_CHECK_CUDA(cudaMemsetAsync(agg, 0, (size_t)g.n_nodes * d.cn * sizeof(float), stream));
     RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
     if (g.n_edges > 0 && mp_tc_supported(d)) {
-        const float* wpack = c.msg.layer[0].weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
+        const float* wpack = c.msg.layer[0].weight_t + conv_msg0_tc_offset(d);
         return run_conv_edges_tc(c, d, g, emb, P, wpack, agg, stream);
     }
     FwdBuilder b(g.n_edges);
@@ -396,5 +402,5 @@ extern "C" int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, 
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d) + mp_tc_pack_floats(d);
+    return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d);
 }

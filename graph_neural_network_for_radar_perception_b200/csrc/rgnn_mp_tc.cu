@@ -5,7 +5,7 @@
 // with ffn1 = Linear(2Cn+Ce -> H) + channel_normalization + LeakyReLU and ffn2 = Linear(H -> Cn) + norm + act.
 // The node part of ffn1's Linear is hoisted out of the edge loop (P = [x W_t^T | x W_s^T], one row per node,
 // produced by the node kernel), so per edge
-//   z1 = emb_e W_e^T + b1 + P_t[tgt] + P_s[src]
+//   z1 = emb_e W_e^T + P_t[tgt] + P_s[src]                  (msg.0's bias rides on P_t)
 // A CTA owns tiles of 128 target-major edges (UMMA M = 128, thread = TMEM lane = edge row):
 //   GEMM1  D1[128 x H]  = A(emb tile, smem) * W_e^T (smem)          tcgen05.mma kind::tf32, SS
 //   epi 1  z1 -> mean / unbiased std / scalar affine / LeakyReLU -> y1, written back to TMEM (hi and lo parts)
@@ -17,6 +17,7 @@
 // hi*hi term (plain TF32, documented tolerance).
 #include "rgnn_model.h"
 #include "rgnn_tc.cuh"
+#include "rgnn_tile.cuh"
 
 namespace rgnn {
 
@@ -37,87 +38,147 @@ struct MpTcArgs {
     int n_edges;
     int act1, act2;
     int passes;             // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
+    int debug;              // experiment switches (0 in production)
+    long long* prof;        // PROFILE builds: [grid][12] cycle counters of thread 0
 };
 
 static int g_tf32_passes = 3;
 static int g_use_tensor_cores = 1;
+static int g_debug = 0;
 
-template <int CE, int H, int CN>
+template <int CE, int H, int CN, int NQ>
 struct MpTcLayout {
-    static constexpr int TM = 128;
+    static constexpr int TM = 128;             // edges per tile = UMMA M
+    static constexpr int NT = 128 * NQ;        // NQ threads share a row, each owns 1/NQ of its columns
     static constexpr int W1 = CE * H;          // floats per (hi or lo) copy
     static constexpr int W2 = H * CN;
     static constexpr int A = TM * CE;
-    static constexpr int LDS = CN + 4;         // staging row stride (floats): 16 B skew per row, conflict-free float4 rows
+    static constexpr int SEG = TM + 4;
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_W2 = OFF_W1 + 2 * W1;
-    static constexpr int OFF_A = OFF_W2 + 2 * W2;
-    static constexpr int A_REGION = (2 * A > TM * LDS) ? 2 * A : TM * LDS;
-    static constexpr int OFF_B1 = OFF_A + A_REGION;
-    static constexpr int OFF_B2 = OFF_B1 + H;
-    static constexpr int OFF_TGT = OFF_B2 + CN;
-    static constexpr int OFF_BAR = OFF_TGT + TM;           // 2 x uint64
+    static constexpr int OFF_A = OFF_W2 + 2 * W2;           // A operand (hi | lo); between GEMM1 and the next fill: P_s row staging
+    static constexpr int OFF_STAGE = OFF_A + 2 * A;         // messages of one tile, XOR-swizzled 16-byte chunks
+    static constexpr int OFF_TGT = OFF_STAGE + TM * CN;     // [2][TM] target ids (double buffered: deferred segsum)
+    static constexpr int OFF_SEG = OFF_TGT + 2 * TM;        // [2][SEG] first row of every target segment
+    static constexpr int OFF_MASK = OFF_SEG + 2 * SEG;      // [2][4] segment-head ballots, [2] segment counts, 3 x [2] boundary flags
+    static constexpr int OFF_BAR = OFF_MASK + 16;           // 2 x uint64
     static constexpr int OFF_SLOT = OFF_BAR + 4;
-    static constexpr int FLOATS = OFF_SLOT + 4;
+    static constexpr int FLOATS = OFF_SLOT + 2;
     static constexpr size_t BYTES = (size_t)FLOATS * 4;
-    static constexpr int TMEM_COLS = 512;                   // D1/y1_hi [0,H) | y1_lo [H,2H) | D2 [2H, 2H+CN)
-    static_assert(CE % 8 == 0 && H % 16 == 0 && CN % 16 == 0, "UMMA shape constraints");
-    static_assert(2 * H + CN <= 512, "TMEM budget");
-    static_assert(128 % CN == 0, "segmented sum thread mapping");
+    static constexpr int TMEM_COLS = 512;                   // D1/y1_hi [0,H) | y1_lo [H,2H) | D2 [2H, 2H+CN) | row statistics (16)
+    static_assert(CE % 16 == 0 && H % 16 == 0 && CN % 16 == 0, "UMMA shape constraints");
+    static_assert(2 * H + CN + 16 <= 512, "TMEM budget");
+    static_assert((H / NQ) % 16 == 0 && (CN / NQ) % 16 == 0, "column split must keep 16-column TMEM accesses");
+    static_assert(NT % CN == 0 && CN % 4 == 0 && CN / 4 >= 8, "segmented sum thread mapping / stage swizzle");
     static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+    static_assert(TM * H * 4 <= 2 * A * 4, "P_s staging must fit in the A region");
+    static_assert(NQ == 2 || NQ == 4, "row statistics exchange through TMEM");
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 
-// channel_normalization + LeakyReLU on a register-resident row (reference common.py:215-220)
-template <int C>
-__device__ __forceinline__ void row_norm_act(float (&z)[C], const float* __restrict__ sp, const float* __restrict__ mp, bool act) {
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// sum of one value per thread over the NQ threads that share an edge row (same lane, different warps): the partials
+// meet in NQ spare TMEM columns of the row's lane.
+template <int NQ>
+__device__ __forceinline__ float row_allreduce(float v, uint32_t t_cols, int q, int bar_id) {
+    tc::tmem_st1(t_cols + q, v);
+    tc::tmem_wait_st();
+    tc::tc_fence_before();
+    group_sync(bar_id, 32 * NQ);
+    tc::tc_fence_after();
+    float p0, p1, p2 = 0.f, p3 = 0.f;
+    if (NQ == 4) tc::tmem_ld4(t_cols, p0, p1, p2, p3); else tc::tmem_ld2(t_cols, p0, p1);
+    tc::tmem_wait_ld();
+    return (p0 + p1) + (p2 + p3);
+}
+
+// channel_normalization + LeakyReLU on a row whose C columns are spread over NQ threads (2*CP each, held as
+// register pairs for the packed f32x2 pipe).  Two-pass mean / unbiased std like the reference (common.py:215-220).
+template <int CP, int NQ>
+__device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, const float* __restrict__ sp, const float* __restrict__ mp,
+                                             bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id) {
     if (sp != nullptr) {
-        float s = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < C; ++c) s += z[c];
-        const float mean = s * (1.f / (float)C);
-        float ss = 0.f;
+        for (int c = 0; c < CP; ++c) s2 = __fadd2_rn(s2, z[c]);
+        const float mean = row_allreduce<NQ>(s2.x + s2.y, t_cols, q, bar_id) / (float)C;
+        const float2 nm = make_float2(-mean, -mean);
+        float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            z[c] -= mean;
-            ss = fmaf(z[c], z[c], ss);
+        for (int c = 0; c < CP; ++c) {
+            z[c] = __fadd2_rn(z[c], nm);
+            ss2 = __ffma2_rn(z[c], z[c], ss2);
         }
-        const float sd = sqrtf(ss * (1.f / (float)(C - 1)));
+        const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
+        const float sd = sqrtf(ss / (float)(C - 1));
         const float k = __ldg(sp) / (sd + NORM_EPS);
         const float sh = __ldg(mp);
+        const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh);
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c] = fmaf(z[c], k, sh);
+        for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
     }
-    if (act) {
+    if (act) {   // LeakyReLU(0.01): max(v, 0.01 v)
+        const float2 sl = make_float2(LEAKY, LEAKY);
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c] = z[c] > 0.f ? z[c] : LEAKY * z[c];
+        for (int c = 0; c < CP; ++c) {
+            const float2 t = __fmul2_rn(z[c], sl);
+            z[c].x = fmaxf(z[c].x, t.x);
+            z[c].y = fmaxf(z[c].y, t.y);
+        }
     }
 }
 
-template <int CE, int H, int CN>
-__global__ void __launch_bounds__(128, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
-    using L = MpTcLayout<CE, H, CN>;
-    constexpr int TM = L::TM;
+// named barriers (0 = __syncthreads, 1..4 = the NQ warps sharing 32 rows)
+constexpr int BAR_WORKERS = 5;   // all worker warps
+constexpr int BAR_A_READY = 6;   // workers arrive, MMA warp waits: A operand (smem) written
+constexpr int BAR_Y_READY = 7;   // workers arrive, MMA warp waits: y1 (TMEM) written
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 32 bytes per lane and request: a full L2 sector (the 16-byte form fetches the sector twice when L1 is tiny)
+__device__ __forceinline__ void ldg256(const float* p, float2& a, float2& b, float2& c, float2& d) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y)
+                 : "l"(p));
+}
+
+// Thread roles: 128*NQ worker threads (thread = edge row x column quarter; loads, both epilogues, segmented sum)
+// + one extra warp whose lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy,
+// so it must not sit on a worker's critical path).
+template <int CE, int H, int CN, int NQ, bool PROFILE>
+__global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
+    using L = MpTcLayout<CE, H, CN, NQ>;
+    constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 32, HQ = H / NQ, CQ = CN / NQ;
     extern __shared__ __align__(1024) float smem[];
     float* w1s = smem + L::OFF_W1;
     float* w2s = smem + L::OFF_W2;
     float* As = smem + L::OFF_A;
-    float* stage = As;                       // aliases the A operand (free once GEMM1 has completed)
-    float* b1s = smem + L::OFF_B1;
-    float* b2s = smem + L::OFF_B2;
+    float* Gs = As;                          // P_s rows of the NEXT tile, staged while no GEMM1 reads A
+    float* stage = smem + L::OFF_STAGE;
     int* tgt_s = reinterpret_cast<int*>(smem + L::OFF_TGT);
+    int* seg_s = reinterpret_cast<int*>(smem + L::OFF_SEG);
+    unsigned* mask_s = reinterpret_cast<unsigned*>(smem + L::OFF_MASK);
+    int* nseg_s = reinterpret_cast<int*>(smem + L::OFF_MASK + 8);
+    int* cut_s = nseg_s + 2;
+    int* cut_first_s = nseg_s + 4;
+    int* cut_last_s = nseg_s + 6;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem + L::OFF_SLOT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid & 127, q = tid >> 7;
+    const int bar_id = 1 + (row >> 5);       // the NQ warps that share rows [32k, 32k+32)
 
     // ---- one-time setup: weights -> smem (already hi/lo split and chunk-major), barriers, TMEM ----
     {
         const float4* g = reinterpret_cast<const float4*>(a.wpack);
         float4* s = reinterpret_cast<float4*>(w1s);
         constexpr int N4 = (2 * L::W1 + 2 * L::W2) / 4;
-        for (int i = tid; i < N4; i += 128) s[i] = __ldg(g + i);
-        for (int i = tid; i < H; i += 128) b1s[i] = a.b1 ? __ldg(a.b1 + i) : 0.f;
-        for (int i = tid; i < CN; i += 128) b2s[i] = a.b2 ? __ldg(a.b2 + i) : 0.f;
+        for (int i = tid; i < N4; i += NALL) s[i] = __ldg(g + i);
     }
     if (tid == 0) {
         tc::mbar_init(&bars[0], 1);
@@ -130,182 +191,307 @@ __global__ void __launch_bounds__(128, 1) mp_edge_tc_kernel(const __grid_constan
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *slot;
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
-    constexpr uint32_t COL_Y1LO = H, COL_D2 = 2 * H;
-
-    constexpr uint32_t IDESC1 = tc::idesc_tf32(TM, H);
-    constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
-    constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
-    const uint32_t sA = tc::smem_u32(As), sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
-
+    constexpr uint32_t COL_Y1LO = H, COL_D2 = 2 * H, COL_XS = 2 * H + CN;
     const int n_tiles = (a.n_edges + TM - 1) / TM;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-        const int row0 = tile * TM;
-        const int nvalid = min(TM, a.n_edges - row0);
+    const int np = a.passes == 1 ? 1 : 3;
 
-        // ---- (a) emb tile -> A operand, hi/lo split.  A quarter-warp reads 8 rows x 16 B and writes one
-        //      128-byte core matrix; a warp request covers 8 rows x 64 B (fully used sectors).
-        {
-            const int r8 = lane & 7, kq = lane >> 3;
-            float4* Ahi = reinterpret_cast<float4*>(As);
-            float4* Alo = reinterpret_cast<float4*>(As + L::A);
+    if (tid >= NW) {
+        // =========================== MMA issue warp ===========================
+        constexpr uint32_t IDESC1 = tc::idesc_tf32(TM, H);
+        constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
+        constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
+        const uint32_t sA = tc::smem_u32(As), sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // GEMM1: D1 = A * W1e^T.  3xTF32: small terms first (lo*hi, hi*lo), then hi*hi
+            group_sync(BAR_A_READY, NALL);
+            tc::tc_fence_after();
+            if (lane == 0) {
+                bool acc = false;
+                for (int p = 0; p < np; ++p) {
+                    const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                    const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                    const uint64_t ad0 = tc::smem_desc(sA + pa * (L::A * 4), LBO_A, SBO);
+                    const uint64_t bd0 = tc::smem_desc(sW1 + pb * (L::W1 * 4), LBO_W1, SBO);
 #pragma unroll
-            for (int rg = 0; rg < 4; ++rg) {
-                const int r = warp * 32 + rg * 8 + r8;
-                const bool ok = r < nvalid;
-                const float4* grow = reinterpret_cast<const float4*>(a.emb + (size_t)(row0 + r) * CE);
+                    for (int ks = 0; ks < CE / 8; ++ks) {
+                        tc::mma_tf32_ss(tmem, ad0 + (uint64_t)((ks * 2 * LBO_A) >> 4), bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
+                        acc = true;
+                    }
+                }
+                tc::mma_commit(&bars[0]);
+            }
+            __syncwarp();
+            // GEMM2: D2 = y1 * W2^T, A operand from TMEM
+            group_sync(BAR_Y_READY, NALL);
+            tc::tc_fence_after();
+            if (lane == 0) {
+                bool acc = false;
+                for (int p = 0; p < np; ++p) {
+                    const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                    const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                    const uint32_t acol = tmem + (pa ? COL_Y1LO : 0);
+                    const uint64_t bd0 = tc::smem_desc(sW2 + pb * (L::W2 * 4), LBO_W2, SBO);
 #pragma unroll
-                for (int kb = 0; kb < CE / 16; ++kb) {
-                    const int kc = kb * 4 + kq;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) v = __ldg(grow + kc);
+                    for (int ks = 0; ks < H / 8; ++ks) {
+                        tc::mma_tf32_ts(tmem + COL_D2, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W2) >> 4), IDESC2, acc);
+                        acc = true;
+                    }
+                }
+                tc::mma_commit(&bars[1]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================== worker warps ===========================
+        const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
+
+        // emb tile -> A operand mapping: a warp instruction reads 8 rows x 64 B (4 chunks per row) and each
+        // quarter-warp writes one contiguous 128-byte core matrix (rgnn_tc.cuh).  UNITS such instructions per warp.
+        constexpr int UNITS = (TM / 8) * (CE / 16) / (NW / 32);
+        static_assert(UNITS >= 1 && (TM / 8) * (CE / 16) % (NW / 32) == 0, "emb tile load mapping");
+        const int r8 = lane & 7, kq = lane >> 3;
+        float4 pre[UNITS];
+        auto prefetch = [&](int tile) {
+            const int row0 = tile * TM;
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                const int unit = warp * UNITS + u;
+                const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
+                pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < a.n_edges) pre[u] = __ldg(reinterpret_cast<const float4*>(a.emb + (size_t)(row0 + r) * CE) + kc);
+            }
+        };
+
+        // per-row inputs of one tile, fetched ONE TILE AHEAD so that their latency hides behind the GEMMs:
+        //   t_my / s_my : target / source node of this thread's edge row;  e_first (lane 0 of the first four warps):
+        //   target of the edge just before this warp's rows;  e_last (thread TM-1): target of the edge after the tile
+        constexpr int RPW = TM / (NW / 32);     // P_s rows staged per warp
+        auto load_idx = [&](int tile, int& t_my, int& s_my, int& e_first, int& e_last) {
+            const int e = tile * TM + row;
+            const bool v = e < a.n_edges;
+            t_my = v ? __ldg(a.tgt + e) : -1;
+            const int es = tile * TM + warp * RPW + (lane % RPW);   // source of the (lane % RPW)-th row this warp stages
+            s_my = es < a.n_edges ? __ldg(a.src + es) : -1;
+            e_first = (tid < TM && lane == 0 && v && e > 0) ? __ldg(a.tgt + e - 1) : -2;
+            e_last = (tid == TM - 1 && e + 1 < a.n_edges) ? __ldg(a.tgt + e + 1) : -3;
+        };
+        // P_s[source] rows of a tile -> shared memory, whole 512-byte rows per warp instruction (cp.async, 16 B per
+        // lane; sector-granular per-thread gathers run ~2.5x slower, tools/micro/bench_gather.cu).  Row r is stored
+        // with its 16-byte chunks XOR-swizzled by (r & 7) so that the row-owning threads read it conflict-free.
+        auto stage_ps = [&](int s_my) {
+            static_assert(H == 128, "one warp instruction copies one H-float row");
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp * RPW + i;
+                const int sn = __shfl_sync(0xffffffffu, s_my, i);
+                if (sn >= 0 && !(a.debug & 1))
+                    cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+            }
+            cp_async_commit();
+        };
+        // z = P_t[target] + P_s[source] for this thread's quarter of the row (the hoisted node part of msg.0; the
+        // Linear bias is already inside P_t).  P_t rows repeat over consecutive edges: few distinct sectors per warp.
+        auto gather = [&](float2 (&z)[HQ / 2], int t_my) {
+            const bool v = t_my >= 0;
+            const float* Pt = a.P + (size_t)(v ? t_my : 0) * (2 * H) + q * HQ;
+#pragma unroll
+            for (int c8 = 0; c8 < HQ / 8; ++c8) {
+                float2 t0, t1, t2, t3;
+                t0 = t1 = t2 = t3 = make_float2(0.f, 0.f);
+                if (v && !(a.debug & 2)) ldg256(Pt + 8 * c8, t0, t1, t2, t3);
+                const float4 s0 = *reinterpret_cast<const float4*>(Gs + row * H + (((q * (HQ / 4) + 2 * c8) ^ (row & 7)) << 2));
+                const float4 s1 = *reinterpret_cast<const float4*>(Gs + row * H + (((q * (HQ / 4) + 2 * c8 + 1) ^ (row & 7)) << 2));
+                z[4 * c8] = __fadd2_rn(t0, make_float2(s0.x, s0.y));
+                z[4 * c8 + 1] = __fadd2_rn(t1, make_float2(s0.z, s0.w));
+                z[4 * c8 + 2] = __fadd2_rn(t2, make_float2(s1.x, s1.y));
+                z[4 * c8 + 3] = __fadd2_rn(t3, make_float2(s1.z, s1.w));
+            }
+        };
+
+        // deferred segmented sum of the tile whose messages sit in `stage` (runs while the next GEMM1 executes).
+        // 16 threads (one float4 of columns each) per target segment; interior segments are whole CSR rows by
+        // construction (edges are target-major), only the first / last segment of a tile can be cut by its boundary.
+        auto segsum = [&](int buf) {
+            static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
+            const int* tg = tgt_s + buf * TM;
+            const int* sg = seg_s + buf * L::SEG;
+            const int nseg = nseg_s[buf];
+            const int cut = cut_s[buf];            // bit 0: first segment continues from the previous tile; bit 1: last one continues
+            const int c4 = tid & 15;
+            for (int s = tid >> 4; s < nseg; s += NW / 16) {
+                const int rs = sg[s], re = sg[s + 1];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int r = rs; r < re; ++r) {
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
+                // boundary is completed with atomicAdd onto the zero-initialised output
+                const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
+                float* o = a.agg + (size_t)tg[rs] * CN + 4 * c4;
+                if (whole) {
+                    *reinterpret_cast<float4*>(o) = acc;
+                } else {
+                    atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+                }
+            }
+        };
+
+        long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+        auto tick = [&](int i) {
+            if (PROFILE && tid == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
+        };
+        if (PROFILE) tlast = clock64();
+        uint32_t phase = 0;
+        int buf = 0;
+        bool have_prev = false;
+        int t_my = -1, s_my = 0, e_first = -2, e_last = -3;
+        float2 z[HQ / 2];
+        if ((int)blockIdx.x < n_tiles) {
+            prefetch(blockIdx.x);
+            load_idx(blockIdx.x, t_my, s_my, e_first, e_last);
+            stage_ps(s_my);
+            cp_async_wait<0>();
+            group_sync(BAR_WORKERS, NW);
+            gather(z, t_my);
+            group_sync(BAR_WORKERS, NW);     // the A region is about to be overwritten by the first tile's operand
+        }
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1, buf ^= 1) {
+            const int row0 = tile * TM;
+            const int nvalid = min(TM, a.n_edges - row0);
+
+            tick(0);
+            // ---- (a) A operand (hi/lo split) from the prefetched registers; target ids and segment heads ----
+            {
+                float4* Ahi = reinterpret_cast<float4*>(As);
+                float4* Alo = reinterpret_cast<float4*>(As + L::A);
+#pragma unroll
+                for (int u = 0; u < UNITS; ++u) {
+                    const int unit = warp * UNITS + u;
+                    const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
                     float4 hi, lo;
-                    tc::split_tf32(v.x, hi.x, lo.x);
-                    tc::split_tf32(v.y, hi.y, lo.y);
-                    tc::split_tf32(v.z, hi.z, lo.z);
-                    tc::split_tf32(v.w, hi.w, lo.w);
+                    tc::split_tf32(pre[u].x, hi.x, lo.x);
+                    tc::split_tf32(pre[u].y, hi.y, lo.y);
+                    tc::split_tf32(pre[u].z, hi.z, lo.z);
+                    tc::split_tf32(pre[u].w, hi.w, lo.w);
                     Ahi[kc * TM + r] = hi;
                     Alo[kc * TM + r] = lo;
                 }
+                if (tid < TM) {
+                    const bool v = tid < nvalid;
+                    int prev = __shfl_up_sync(0xffffffffu, t_my, 1);
+                    if (lane == 0) prev = e_first;
+                    const unsigned m = __ballot_sync(0xffffffffu, v && (tid == 0 || t_my != prev));
+                    tgt_s[buf * TM + tid] = t_my;
+                    if (lane == 0) mask_s[buf * 4 + warp] = m;
+                    if (tid == 0) cut_first_s[buf] = (e_first == t_my) ? 1 : 0;
+                    if (tid == nvalid - 1) cut_last_s[buf] = (tid == TM - 1 && e_last == t_my) ? 2 : 0;
+                }
             }
-            tgt_s[tid] = tid < nvalid ? __ldg(a.tgt + row0 + tid) : -1;
-        }
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            bar_arrive(BAR_A_READY, NALL);          // -> MMA warp issues GEMM1
+            group_sync(BAR_WORKERS, NW);
+            tick(1);
 
-        // ---- (b) GEMM1: D1 = A * W1e^T ----
-        if (tid == 0) {
+            // ---- while GEMM1 runs: issue the next tile's emb / index loads, finish the previous tile's segsum ----
+            const int next = tile + (int)gridDim.x;
+            const bool has_next = next < n_tiles;
+            int n_t = -1, n_s = 0, n_first = -2, n_last = -3;
+            if (has_next) {
+                prefetch(next);
+                load_idx(next, n_t, n_s, n_first, n_last);
+            }
+            if (tid < TM) {   // segment start rows of this tile (consumed by the deferred segsum)
+                const unsigned* mk = mask_s + buf * 4;
+                const unsigned m = mk[warp];
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
+                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = tid;
+                if (tid == TM - 1) {
+                    const int n = base + __popc(m);
+                    seg_s[buf * L::SEG + n] = nvalid;
+                    nseg_s[buf] = n;
+                    cut_s[buf] = cut_first_s[buf] | cut_last_s[buf];
+                }
+            }
+            tick(2);
+            if (have_prev && !(a.debug & 4)) segsum(buf ^ 1);
+            tick(3);
+
+            // ---- (c) epilogue 1: z1 = D1 + (P_t + P_s) -> norm -> act -> y1 (hi | lo) back into TMEM ----
+            tc::mbar_wait(&bars[0], phase);
             tc::tc_fence_after();
-            bool acc = false;
-            const int np = a.passes == 1 ? 1 : 3;
-            for (int p = 0; p < np; ++p) {
-                // small terms first: lo*hi, hi*lo, then hi*hi
-                const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                const uint32_t abase = sA + pa * (L::A * 4), bbase = sW1 + pb * (L::W1 * 4);
+            tick(4);
+            if (has_next) stage_ps(n_s);            // GEMM1 is done with the A region: next tile's P_s rows land there
+            {
+                float2 d[HQ / 2];
 #pragma unroll
-                for (int ks = 0; ks < CE / 8; ++ks) {
-                    const uint64_t ad = tc::smem_desc(abase + ks * 2 * LBO_A, LBO_A, SBO);
-                    const uint64_t bd = tc::smem_desc(bbase + ks * 2 * LBO_W1, LBO_W1, SBO);
-                    tc::mma_tf32_ss(tmem, ad, bd, IDESC1, acc);
-                    acc = true;
-                }
+                for (int c = 0; c < HQ; c += 16) tc::tmem_ld16(t_row + q * HQ + c, d + c / 2);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < HQ / 2; ++c) z[c] = __fadd2_rn(z[c], d[c]);
             }
-            tc::mma_commit(&bars[0]);
-        }
-        __syncwarp();
-
-        // ---- (c) epilogue 1 ----
-        const bool valid = tid < nvalid;
-        const int e = row0 + tid;
-        const int tg = valid ? tgt_s[tid] : 0;
-        const int sr = valid ? __ldg(a.src + e) : 0;
-        const float4* Pt = reinterpret_cast<const float4*>(a.P + (size_t)tg * (2 * H));
-        const float4* Ps = reinterpret_cast<const float4*>(a.P + (size_t)sr * (2 * H) + H);
-        tc::mbar_wait(&bars[0], phase);
-        tc::tc_fence_after();
-        {
-            float z[H];
+            row_norm_act<HQ / 2, NQ>(z, H, a.s1, a.m1, a.act1 != 0, t_row + COL_XS, q, bar_id);
+            if (np == 1) {
 #pragma unroll
-            for (int c = 0; c < H; c += 16) tc::tmem_ld16(t_row + c, z + c);
-            tc::tmem_wait_ld();
-            if (valid) {
-#pragma unroll
-                for (int c4 = 0; c4 < H / 4; ++c4) {
-                    const float4 pt = __ldg(Pt + c4), ps = __ldg(Ps + c4);
-                    const float4 b = *reinterpret_cast<const float4*>(b1s + 4 * c4);
-                    z[4 * c4 + 0] += b.x + (pt.x + ps.x);
-                    z[4 * c4 + 1] += b.y + (pt.y + ps.y);
-                    z[4 * c4 + 2] += b.z + (pt.z + ps.z);
-                    z[4 * c4 + 3] += b.w + (pt.w + ps.w);
-                }
-            }
-            row_norm_act<H>(z, a.s1, a.m1, a.act1 != 0);
-            // y1 -> TMEM as the A operand of GEMM2: hi part in place over D1, lo part next to it
-            if (a.passes == 1) {
-#pragma unroll
-                for (int c = 0; c < H; ++c) z[c] = tc::tf32_rna(z[c]);
-#pragma unroll
-                for (int c = 0; c < H; c += 16) tc::tmem_st16(t_row + c, z + c);
+                for (int c = 0; c < HQ; c += 16) tc::tmem_st16(t_row + q * HQ + c, z + c / 2);
             } else {
 #pragma unroll
-                for (int c = 0; c < H; c += 16) {
-                    float hi[16], lo[16];
+                for (int c = 0; c < HQ; c += 16) {
+                    float2 hi[8], lo[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) tc::split_tf32(z[c + j], hi[j], lo[j]);
-                    tc::tmem_st16(t_row + c, hi);
-                    tc::tmem_st16(t_row + COL_Y1LO + c, lo);
+                    for (int j = 0; j < 8; ++j) tc::split_tf32(z[c / 2 + j], hi[j], lo[j]);
+                    tc::tmem_st16(t_row + q * HQ + c, hi);
+                    tc::tmem_st16(t_row + COL_Y1LO + q * HQ + c, lo);
                 }
             }
             tc::tmem_wait_st();
-        }
-        tc::tc_fence_before();
-        __syncthreads();
+            tc::tc_fence_before();
+            bar_arrive(BAR_Y_READY, NALL);          // -> MMA warp issues GEMM2
+            tick(5);
 
-        // ---- (d) GEMM2: D2 = y1 * W2^T, A from TMEM ----
-        if (tid == 0) {
+            // ---- while GEMM2 runs: the next tile's projection gathers (consumed by its epilogue 1) ----
+            if (has_next) {
+                cp_async_wait<0>();
+                group_sync(BAR_WORKERS, NW);        // every warp's staged rows are visible
+                gather(z, n_t);
+            }
+            t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last;
+            tick(6);
+
+            // ---- (e) epilogue 2: message = act(norm(D2 + b2)) -> stage ----
+            float2 m[CQ / 2];
+#pragma unroll
+            for (int c = 0; c < CQ / 2; ++c)
+                m[c] = a.b2 ? __ldg(reinterpret_cast<const float2*>(a.b2 + q * CQ) + c) : make_float2(0.f, 0.f);
+            tc::mbar_wait(&bars[1], phase);
             tc::tc_fence_after();
-            bool acc = false;
-            const int np = a.passes == 1 ? 1 : 3;
-            for (int p = 0; p < np; ++p) {
-                const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                const uint32_t acol = tmem + (pa ? COL_Y1LO : 0);
-                const uint32_t bbase = sW2 + pb * (L::W2 * 4);
+            tick(7);
+            {
+                float2 d[CQ / 2];
 #pragma unroll
-                for (int ks = 0; ks < H / 8; ++ks) {
-                    const uint64_t bd = tc::smem_desc(bbase + ks * 2 * LBO_W2, LBO_W2, SBO);
-                    tc::mma_tf32_ts(tmem + COL_D2, acol + ks * 8, bd, IDESC2, acc);
-                    acc = true;
-                }
+                for (int c = 0; c < CQ; c += 16) tc::tmem_ld16(t_row + COL_D2 + q * CQ + c, d + c / 2);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(m[c], d[c]);
             }
-            tc::mma_commit(&bars[1]);
-        }
-        __syncwarp();
-
-        // ---- (e) epilogue 2 -> staging ----
-        tc::mbar_wait(&bars[1], phase);
-        tc::tc_fence_after();
-        {
-            float m[CN];
+            row_norm_act<CQ / 2, NQ>(m, CN, a.s2, a.m2, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
 #pragma unroll
-            for (int c = 0; c < CN; c += 16) tc::tmem_ld16(t_row + COL_D2 + c, m + c);
-            tc::tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < CN; ++c) m[c] += b2s[c];
-            row_norm_act<CN>(m, a.s2, a.m2, a.act2 != 0);
-            float4* srow = reinterpret_cast<float4*>(stage + tid * L::LDS);
-#pragma unroll
-            for (int c4 = 0; c4 < CN / 4; ++c4) srow[c4] = make_float4(m[4 * c4], m[4 * c4 + 1], m[4 * c4 + 2], m[4 * c4 + 3]);
-        }
-        tc::tc_fence_before();
-        __syncthreads();
-
-        // ---- (f) segmented sum over equal consecutive targets.  A target whose whole CSR row lies inside this
-        //      thread's row range is stored (source-ascending order, like the reference's index_add_); a row cut
-        //      by a range boundary is completed with atomicAdd onto the zero-initialised output.
-        {
-            constexpr int PARTS = 128 / CN, RP = TM / PARTS;
-            const int j = tid % CN, part = tid / CN;
-            int r = part * RP;
-            const int rend = min(r + RP, nvalid);
-            while (r < rend) {
-                const int tn = tgt_s[r];
-                float s = 0.f;
-                int r1 = r;
-                while (r1 < rend && tgt_s[r1] == tn) {
-                    s += stage[r1 * L::LDS + j];
-                    ++r1;
-                }
-                const bool whole = (__ldg(a.row_ptr + tn) == row0 + r) && (__ldg(a.row_ptr + tn + 1) == row0 + r1);
-                float* o = a.agg + (size_t)tn * CN + j;
-                if (whole) *o = s; else atomicAdd(o, s);
-                r = r1;
+            for (int c4 = 0; c4 < CQ / 4; ++c4) {
+                const int chunk = (q * (CQ / 4) + c4) ^ (row & 7);
+                *reinterpret_cast<float4*>(stage + row * CN + chunk * 4) = make_float4(m[2 * c4].x, m[2 * c4].y, m[2 * c4 + 1].x, m[2 * c4 + 1].y);
             }
+            tc::tc_fence_before();
+            group_sync(BAR_WORKERS, NW);
+            tick(8);
+            have_prev = true;
         }
-        __syncthreads();
+        if (have_prev) segsum(buf ^ 1);
+        tick(9);
+        if (PROFILE && tid == 0 && a.prof != nullptr)
+            for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];
     }
 
     tc::tc_fence_before();
@@ -347,9 +533,41 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
     return RGNN_OK;
 }
 
+template <int NQ>
+static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
+    using L = MpTcLayout<64, 128, 64, NQ>;
+    static bool configured = false;
+    if (!configured) {
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        configured = true;
+    }
+    const int n_tiles = (n_edges + L::TM - 1) / L::TM;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    if (g_debug & 8) {   // developer aid: per-phase cycle counters of thread 0, printed to stderr (synchronises!)
+        long long* prof = nullptr;
+        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid));
+        a.prof = prof;
+        mp_edge_tc_kernel<64, 128, 64, NQ, true><<<grid, L::NT + 32, L::BYTES, stream>>>(a);
+        RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
+        long long* h = new long long[12 * grid];
+        RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost));
+        double tot[12] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) tot[i] += (double)h[b * 12 + i];
+        fprintf(stderr, "[mp_edge_tc profile NQ=%d] cycles per tile (thread 0 view):", NQ);
+        for (int i = 0; i < 12; ++i) fprintf(stderr, " p%d=%.0f", i, tot[i] / (double)n_tiles);
+        fprintf(stderr, "\n");
+        delete[] h;
+        cudaFree(prof);
+        return RGNN_OK;
+    }
+    mp_edge_tc_kernel<64, 128, 64, NQ, false><<<grid, L::NT + 32, L::BYTES, stream>>>(a);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
 int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
                       const float* wpack, float* agg, cudaStream_t stream) {
-    using L = MpTcLayout<64, 128, 64>;
     const rgnn_linear& m0 = c.msg.layer[0];
     const rgnn_linear& m1 = c.msg.layer[1];
     MpTcArgs a;
@@ -360,17 +578,10 @@ int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g
     a.agg = agg; a.n_edges = g.n_edges;
     a.act1 = m0.activation; a.act2 = m1.activation;
     a.passes = g_tf32_passes;
-    static bool configured = false;
-    if (!configured) {
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        configured = true;
-    }
-    const int n_tiles = (g.n_edges + L::TM - 1) / L::TM;
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    a.debug = g_debug;
+    a.prof = nullptr;
     (void)d;
-    mp_edge_tc_kernel<64, 128, 64><<<grid, 128, L::BYTES, stream>>>(a);
-    RGNN_CHECK_CUDA(cudaGetLastError());
-    return RGNN_OK;
+    return (g_debug & 16) ? launch_mp_tc<4>(a, g.n_edges, stream) : launch_mp_tc<2>(a, g.n_edges, stream);
 }
 
 }  // namespace rgnn
@@ -379,6 +590,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     using namespace rgnn;
     if (name != nullptr && strcmp(name, "tf32_passes") == 0 && (value == 1 || value == 3)) { g_tf32_passes = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores = value; return RGNN_OK; }
+    if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; return RGNN_OK; }
     set_error("rgnn_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
     return RGNN_ERR_INVALID;
 }

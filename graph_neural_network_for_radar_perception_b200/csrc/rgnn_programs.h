@@ -35,11 +35,18 @@ struct ConvDims {
 };
 bool conv_dims(const rgnn_conv& c, ConvDims* d);
 // packed layout of msg.0: [Wt_P (cn_pad x round_up(2h,64))] [Wt_c (ce_pad x round_up(h,64))] [WP_nat (2h x round_up(cn,64))]
+//                          [bias2h (round_up(2h,64))] [tensor-core operands, rgnn_mp_tc.cu]
 //   Wt_P  : k-major node projection  [x W_target^T | x W_source^T]      (forward, per node)
 //   Wt_c  : k-major edge part W_edge^T                                  (forward, per edge)
 //   WP_nat: rows = projection column c, cols = node channel k           (backward: dX = dP * WP_nat)
 inline size_t conv_msg0_proj_floats(const ConvDims& d) { return (size_t)round_up(d.cn, 8) * round_up(2 * d.h, 64); }
 inline size_t conv_msg0_edge_floats(const ConvDims& d) { return (size_t)round_up(d.ce, 8) * round_up(d.h, 64); }
 inline size_t conv_msg0_projnat_floats(const ConvDims& d) { return (size_t)2 * d.h * round_up(d.cn, 64); }
+//   bias2h: [msg.0.bias (h) | zeros]  -- the Linear bias rides on the target half of the node projection P, so the
+//           per-edge kernels add nothing but P_t[target] + P_s[source]
+inline size_t conv_msg0_bias_floats(const ConvDims& d) { return (size_t)round_up(2 * d.h, 64); }
+inline size_t conv_msg0_tc_offset(const ConvDims& d) {
+    return conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d) + conv_msg0_bias_floats(d);
+}
 
 }  // namespace rgnn

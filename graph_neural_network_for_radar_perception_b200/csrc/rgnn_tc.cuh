@@ -115,15 +115,52 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         : "memory");
 }
 
+// single column / four columns (per-row scalars exchanged between the threads that share a row)
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float& a, float& b, float& c, float& d) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(taddr) : "memory");
+}
+
+// same, 16 columns as 8 register pairs (packed f32x2 arithmetic operates on aligned pairs)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+          "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y)
+        : "memory");
+}
+
 // ---- 3xTF32 split: x ~= hi + lo, both exactly representable in tf32 --------------------------------
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// hi = x rounded to the nearest tf32 value (ties away from zero; integer add + mask, exact in tf32 whatever
+// rounding the tensor core applies to its inputs); lo = x - hi is exact in fp32 and at most 2^-11 |x|, so its own
+// tf32 rounding inside the tensor core costs <= 2^-21 |x|.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    hi = tf32_hi(x);
+    lo = x - hi;
+}
+__device__ __forceinline__ void split_tf32(float2 x, float2& hi, float2& lo) {
+    hi.x = tf32_hi(x.x);
+    hi.y = tf32_hi(x.y);
+    lo = __ffma2_rn(hi, make_float2(-1.f, -1.f), x);
 }
 
 }  // namespace tc

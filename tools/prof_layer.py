@@ -32,7 +32,11 @@ def main():
     ap.add_argument('--points', type=int, default=3000)
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--what', default='layer')
+    ap.add_argument('--opt', action='append', default=[], help='name=value for rgnn_set_option')
     args = ap.parse_args()
+    for o in args.opt:
+        k, v = o.split('=')
+        check(lib().rgnn_set_option(k.encode(), int(v)), 'set_option')
     dev = torch.device('cuda:0')
     torch.cuda.set_device(dev)
     model = Model_Training(config(), dev)
