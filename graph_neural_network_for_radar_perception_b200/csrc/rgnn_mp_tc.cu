@@ -150,9 +150,12 @@ __device__ __forceinline__ void ldg256(const float* p, float2& a, float2& b, flo
 // + one extra warp whose lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy,
 // so it must not sit on a worker's critical path).
 template <int CE, int H, int CN, int NQ, bool PROFILE>
-__global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
+__global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
     using L = MpTcLayout<CE, H, CN, NQ>;
-    constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 32, HQ = H / NQ, CQ = CN / NQ;
+    constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 128, HQ = H / NQ, CQ = CN / NQ;
+    constexpr int NMMA = NW + 32;            // threads that take part in the worker <-> MMA-warp barriers
+    // register budget: the issue warpgroup keeps 24 registers, the workers take the rest (setmaxnreg)
+    constexpr int WORKER_REGS = NQ == 4 ? 112 : 232;
     extern __shared__ __align__(1024) float smem[];
     float* w1s = smem + L::OFF_W1;
     float* w2s = smem + L::OFF_W2;
@@ -196,14 +199,16 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
     const int np = a.passes == 1 ? 1 : 3;
 
     if (tid >= NW) {
-        // =========================== MMA issue warp ===========================
+        // =========================== MMA issue warpgroup (only its first warp works) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid >= NW + 32) goto teardown;
         constexpr uint32_t IDESC1 = tc::idesc_tf32(TM, H);
         constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
         constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
         const uint32_t sA = tc::smem_u32(As), sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // GEMM1: D1 = A * W1e^T.  3xTF32: small terms first (lo*hi, hi*lo), then hi*hi
-            group_sync(BAR_A_READY, NALL);
+            group_sync(BAR_A_READY, NMMA);
             tc::tc_fence_after();
             if (lane == 0) {
                 bool acc = false;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             }
             __syncwarp();
             // GEMM2: D2 = y1 * W2^T, A operand from TMEM
-            group_sync(BAR_Y_READY, NALL);
+            group_sync(BAR_Y_READY, NMMA);
             tc::tc_fence_after();
             if (lane == 0) {
                 bool acc = false;
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
         }
     } else {
         // =========================== worker warps ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
         const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
 
         // emb tile -> A operand mapping: a warp instruction reads 8 rows x 64 B (4 chunks per row) and each
@@ -291,20 +297,21 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
         };
         // z = P_t[target] + P_s[source] for this thread's quarter of the row (the hoisted node part of msg.0; the
         // Linear bias is already inside P_t).  P_t rows repeat over consecutive edges: few distinct sectors per warp.
-        auto gather = [&](float2 (&z)[HQ / 2], int t_my) {
+        auto load_pt = [&](float2 (&z)[HQ / 2], int t_my) {
             const bool v = t_my >= 0;
             const float* Pt = a.P + (size_t)(v ? t_my : 0) * (2 * H) + q * HQ;
 #pragma unroll
             for (int c8 = 0; c8 < HQ / 8; ++c8) {
-                float2 t0, t1, t2, t3;
-                t0 = t1 = t2 = t3 = make_float2(0.f, 0.f);
-                if (v && !(a.debug & 2)) ldg256(Pt + 8 * c8, t0, t1, t2, t3);
-                const float4 s0 = *reinterpret_cast<const float4*>(Gs + row * H + (((q * (HQ / 4) + 2 * c8) ^ (row & 7)) << 2));
-                const float4 s1 = *reinterpret_cast<const float4*>(Gs + row * H + (((q * (HQ / 4) + 2 * c8 + 1) ^ (row & 7)) << 2));
-                z[4 * c8] = __fadd2_rn(t0, make_float2(s0.x, s0.y));
-                z[4 * c8 + 1] = __fadd2_rn(t1, make_float2(s0.z, s0.w));
-                z[4 * c8 + 2] = __fadd2_rn(t2, make_float2(s1.x, s1.y));
-                z[4 * c8 + 3] = __fadd2_rn(t3, make_float2(s1.z, s1.w));
+                z[4 * c8] = z[4 * c8 + 1] = z[4 * c8 + 2] = z[4 * c8 + 3] = make_float2(0.f, 0.f);
+                if (v && !(a.debug & 2)) ldg256(Pt + 8 * c8, z[4 * c8], z[4 * c8 + 1], z[4 * c8 + 2], z[4 * c8 + 3]);
+            }
+        };
+        auto add_ps = [&](float2 (&z)[HQ / 2]) {
+#pragma unroll
+            for (int c4 = 0; c4 < HQ / 4; ++c4) {
+                const float4 s0 = *reinterpret_cast<const float4*>(Gs + row * H + (((q * (HQ / 4) + c4) ^ (row & 7)) << 2));
+                z[2 * c4] = __fadd2_rn(z[2 * c4], make_float2(s0.x, s0.y));
+                z[2 * c4 + 1] = __fadd2_rn(z[2 * c4 + 1], make_float2(s0.z, s0.w));
             }
         };
 
@@ -354,7 +361,8 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             stage_ps(s_my);
             cp_async_wait<0>();
             group_sync(BAR_WORKERS, NW);
-            gather(z, t_my);
+            load_pt(z, t_my);
+            add_ps(z);
             group_sync(BAR_WORKERS, NW);     // the A region is about to be overwritten by the first tile's operand
         }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1, buf ^= 1) {
@@ -391,8 +399,7 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             }
             tc::fence_async_smem();
             tc::tc_fence_before();
-            bar_arrive(BAR_A_READY, NALL);          // -> MMA warp issues GEMM1
-            group_sync(BAR_WORKERS, NW);
+            bar_arrive(BAR_A_READY, NMMA);          // -> MMA warp issues GEMM1
             tick(1);
 
             // ---- while GEMM1 runs: issue the next tile's emb / index loads, finish the previous tile's segsum ----
@@ -402,19 +409,6 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             if (has_next) {
                 prefetch(next);
                 load_idx(next, n_t, n_s, n_first, n_last);
-            }
-            if (tid < TM) {   // segment start rows of this tile (consumed by the deferred segsum)
-                const unsigned* mk = mask_s + buf * 4;
-                const unsigned m = mk[warp];
-                int base = 0;
-                for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
-                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = tid;
-                if (tid == TM - 1) {
-                    const int n = base + __popc(m);
-                    seg_s[buf * L::SEG + n] = nvalid;
-                    nseg_s[buf] = n;
-                    cut_s[buf] = cut_first_s[buf] | cut_last_s[buf];
-                }
             }
             tick(2);
             if (have_prev && !(a.debug & 4)) segsum(buf ^ 1);
@@ -449,15 +443,27 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             }
             tc::tmem_wait_st();
             tc::tc_fence_before();
-            bar_arrive(BAR_Y_READY, NALL);          // -> MMA warp issues GEMM2
+            bar_arrive(BAR_Y_READY, NMMA);          // -> MMA warp issues GEMM2
             tick(5);
 
             // ---- while GEMM2 runs: the next tile's projection gathers (consumed by its epilogue 1) ----
-            if (has_next) {
-                cp_async_wait<0>();
-                group_sync(BAR_WORKERS, NW);        // every warp's staged rows are visible
-                gather(z, n_t);
+            if (has_next) load_pt(z, n_t);          // issue first: their latency overlaps the barrier below
+            cp_async_wait<0>();
+            group_sync(BAR_WORKERS, NW);            // every warp's staged rows (and this tile's ballots) are visible
+            if (tid < TM) {   // segment start rows of this tile (consumed by the deferred segsum)
+                const unsigned* mk = mask_s + buf * 4;
+                const unsigned m = mk[warp];
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
+                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = tid;
+                if (tid == TM - 1) {
+                    const int n = base + __popc(m);
+                    seg_s[buf * L::SEG + n] = nvalid;
+                    nseg_s[buf] = n;
+                    cut_s[buf] = cut_first_s[buf] | cut_last_s[buf];
+                }
             }
+            if (has_next) add_ps(z);
             t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last;
             tick(6);
 
@@ -494,6 +500,7 @@ __global__ void __launch_bounds__(128 * NQ + 32, 1) mp_edge_tc_kernel(const __gr
             for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];
     }
 
+teardown:
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, L::TMEM_COLS);
@@ -548,7 +555,7 @@ static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
         long long* prof = nullptr;
         RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid));
         a.prof = prof;
-        mp_edge_tc_kernel<64, 128, 64, NQ, true><<<grid, L::NT + 32, L::BYTES, stream>>>(a);
+        mp_edge_tc_kernel<64, 128, 64, NQ, true><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
         long long* h = new long long[12 * grid];
         RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost));
@@ -561,7 +568,7 @@ static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
         cudaFree(prof);
         return RGNN_OK;
     }
-    mp_edge_tc_kernel<64, 128, 64, NQ, false><<<grid, L::NT + 32, L::BYTES, stream>>>(a);
+    mp_edge_tc_kernel<64, 128, 64, NQ, false><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
