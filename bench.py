@@ -235,7 +235,7 @@ def run_gpu(args):
         ms_fwd = timed(lambda: det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False), args.steps)
     ms_graph = timed(lambda: gf.build_graph_batch(pts_dev, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH), args.steps)
     roof = measure_roofline(det, bf0, dev, args.steps)
-    train = measure_train(model, bf0, frames, fp, dev, args, timed) if args.train else None
+    train = measure_train(dev, args, timed, rank, world) if not args.no_train else None
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -272,10 +272,11 @@ def run_gpu(args):
 
 
 def launches_per_step(det):
-    # graph build: knn, 2 memsets excluded; kernels only: knn, sym_count, add, 3 scan, copy_last, sym_fill, sort,
-    # finalize (rows, 3 scan, und, copy_last), node feat, edge feat = 17; model: pack 2, node enc, edge enc,
-    # 7 x (edge, node), 6 head programs = 24
-    return 17 + 2 + 2 + 2 * len(det.pass_messages.conv_blk) + 6
+    # kernels only (memsets excluded).  graph build: knn, sym_count, add, 3 scan, copy_last, sym_fill, sort, finalize
+    # (rows, 3 scan, und, copy_last), node feat, edge feat = 17; weight packing: 2 pack_kernel + 2 pack_split per conv
+    # block; model: node enc, edge enc, per conv block (tcgen05 edge kernel, node program), 6 head programs
+    L = len(det.pass_messages.conv_blk)
+    return 17 + 2 + 2 * L + 2 + 2 * L + 6
 
 
 def measure_roofline(det, bf, dev, steps):
@@ -311,13 +312,49 @@ def measure_roofline(det, bf, dev, steps):
     ms = e0.elapsed_time(e1) / reps
     bytes_alg = 512.0 * N + 260.0 * E
     flops_alg = 65536.0 * E + 16384.0 * N
-    return {'kernel': 'message-passing layer fwd (chain_fwd_kernel: edge program + node program)', 'bound': 'hbm',
+    return {'kernel': 'message-passing layer fwd: mp_edge_tc_kernel (tcgen05, 3xTF32) + node tile program (projection, update)',
+            'bound': 'hbm',
             'achieved': bytes_alg / (ms * 1e-3) / 1e9, 'unit': 'GB/s', 'traffic': None,
             'ms_per_launch': ms, 'algorithmic_bytes': bytes_alg, 'algorithmic_tflops': flops_alg / (ms * 1e-3) / 1e12}
 
 
-def measure_train(model, bf, frames, fp, dev, args, timed):
-    return None
+def measure_train(dev, args, timed, rank, world):
+    """BASELINE.json configs[2]: full multi-task training step (forward, 4 losses, backward, gradient all-reduce
+    over NCCL when world > 1, fused SGD) on `--train-frames` frames per GPU (weak scaling)."""
+    from graph_neural_network_for_radar_perception_b200 import config, Model_Training
+    from graph_neural_network_for_radar_perception_b200 import graph_features as gf
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
+    model = Model_Training(config(), dev)
+    model.load_state_dict(torch.load(CKPT, map_location='cpu', weights_only=True))
+    model = model.to(dev).train()
+    trainer = DataParallelTrainer(model)
+    nfr = args.train_frames
+    frames = make_frames(nfr, args.points, seed0=5000 + 1000 * rank)
+    pts, fp = gf.frames_to_device([f[0] for f in frames], dev)
+    bf = gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+    gb = bf.gb
+    # synthetic labels (synth.make_labels needs the edge list of each frame: take it from the GPU graph)
+    ei = bf.edge_index().cpu().numpy()
+    row_ptr = gb.row_ptr.cpu().numpy()
+    labs, cl_lists = [], []
+    for i, (d, src) in enumerate(frames):
+        e0, e1 = int(row_ptr[fp[i]]), int(row_ptr[fp[i + 1]])
+        lab = synth.make_labels(d, src, ei[:, e0:e1] - fp[i])
+        labs.append(lab)
+        cl_lists.append([torch.from_numpy(c) for c in lab['cluster_node_idx']])
+    gb.set_clusters(cl_lists, fp[:-1], dev)
+    labels = {k: torch.cat([torch.from_numpy(l[k]) for l in labs]).to(dev)
+              for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
+    step = lambda: trainer.step(gb, bf.node_features, bf.edge_features, labels)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ms = timed(step, args.steps) / args.steps
+    loss, _ = step()
+    return {'metric': 'radar_frames_per_s_gnn_fwd_bwd', 'value': nfr * world / (ms * 1e-3), 'unit': 'frames/s',
+            'ms_per_step': ms, 'frames_per_gpu': nfr, 'edges_per_s': gb.n_edges * world / (ms * 1e-3),
+            'directed_edges_per_gpu': gb.n_edges, 'collective': 'nccl all-reduce of 463144 fp32 gradients + 3 counts' if world > 1 else 'none (1 GPU)',
+            'includes': 'forward + 4 losses + backward + SGD(momentum, weight decay) update; graph prebuilt',
+            'loss_after': float(sum(v.item() for v in loss.values()))}
 
 
 def cpu_baseline(args):
@@ -351,7 +388,8 @@ def main():
     ap.add_argument('--points', type=int, default=3000)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--ref-frames', type=int, default=4)
-    ap.add_argument('--train', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--train-frames', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

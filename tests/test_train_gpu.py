@@ -162,3 +162,30 @@ def test_sgd_step_matches_torch():
         ref.grad = g.clone(); opt.step()
         check(lib().rgnn_sgd_step(ptr(p), ptr(g), ptr(buf), p.numel(), 0.005, 0.9, 1e-4, 1.0, int(i == 0), stream_ptr()), 'sgd')
     torch.testing.assert_close(p, ref.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_trainer_step_equals_reference_sgd_step(golden_dir, ckpt_state_dict):
+    """DataParallelTrainer.step (world size 1): two optimisation steps == torch.optim.SGD on the oracle's gradients."""
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
+    from oracle import model_torch as mt
+    g = np.load(os.path.join(golden_dir, 'train_2frames.npz'))
+    m = load_model(ckpt_state_dict).train()
+    trainer = DataParallelTrainer(m, lr=0.005, momentum=0.9, weight_decay=1e-4)
+    nf, ef, ei, labels = _golden_batch(g, 'cuda')
+    gb, nfp, efp = m.pack_batch(nf, ef, ei, labels['cluster_node_idx'])
+    # reference: the oracle + torch.optim.SGD on the CPU
+    sd = {k: torch.nn.Parameter(v.clone()) for k, v in ckpt_state_dict.items()}
+    opt = torch.optim.SGD(list(sd.values()), lr=0.005, momentum=0.9, weight_decay=1e-4)
+    nf_c, ef_c, ei_c, lab_c = _golden_batch(g, 'cpu')
+    for step in range(2):
+        loss, _ = trainer.step(gb, nfp, efp, labels)
+        opt.zero_grad()
+        loss_o, _, _ = mt.training_forward(sd, nf_c, ef_c, ei_c, lab_c)
+        sum(loss_o.values()).backward()
+        opt.step()
+        for k in loss:
+            assert_close(loss[k].item(), loss_o[k].item(), 2e-4, 1e-6, f'step {step} {k}')
+    for n, p in m.named_parameters():
+        ref = sd[n].detach().numpy()
+        if ref.size > 1:
+            assert_close(p.detach().cpu().numpy(), ref, 1e-5, 1e-6, n)
