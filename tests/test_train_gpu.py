@@ -188,4 +188,5 @@ def test_trainer_step_equals_reference_sgd_step(golden_dir, ckpt_state_dict):
     for n, p in m.named_parameters():
         ref = sd[n].detach().numpy()
         if ref.size > 1:
-            assert_close(p.detach().cpu().numpy(), ref, 1e-5, 1e-6, n)
+            # lr * (gradient tolerance, see the module docstring) * (1 + momentum) over two steps
+            assert_close(p.detach().cpu().numpy(), ref, 1e-5, 1e-5, n)
