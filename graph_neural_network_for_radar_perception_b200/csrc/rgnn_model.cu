@@ -54,6 +54,8 @@ struct Packer {
         if (L.weight == nullptr || L.weight_t == nullptr) { set_error("pack: null weight pointer"); rc = RGNN_ERR_INVALID; return; }
         const int Kpad = round_up(L.in_features, 8), Cpad = round_up(L.out_features, 64);
         push({L.weight, const_cast<float*>(L.weight_t), L.in_features, 0, L.in_features, L.out_features, Kpad, Cpad, 0, Cpad});
+        const int r = tc_pack_linear(L, stream);     // chunked hi/lo operands of the tensor-core programs
+        if (r != RGNN_OK) rc = r;
     }
     void stack(const rgnn_stack& s) { for (int i = 0; i < s.n; ++i) linear(s.layer[i]); }
     void conv(const rgnn_conv& c) {
@@ -83,7 +85,8 @@ struct Packer {
         stack(c.upd);
         // hi/lo split operands of the tcgen05 message kernel (after the three FFMA-path blocks)
         if (c.msg.n == 2 && c.msg.layer[1].weight != nullptr) {
-            const int r = mp_tc_pack(c, d, wp + conv_msg0_tc_offset(d), stream);
+            int r = mp_tc_pack(c, d, wp + conv_msg0_tc_offset(d), stream);
+            if (r == RGNN_OK) r = tc_pack_projection(c, d, stream);
             if (r != RGNN_OK) rc = r;
         }
     }
@@ -136,6 +139,7 @@ struct FwdBuilder : ProgBuilder {
 
 int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream) {
     RGNN_REQUIRE(s.n >= 1 && s.n <= RGNN_MAX_STACK, "stack with %d layers", s.n);
+    if (tc_stack_supported(s)) return tc_run_stack(s, x, nullptr, n_rows, y, stream);
     FwdBuilder b(n_rows);
     b.load_rows(b.cur, x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
     b.stack(s);
@@ -196,6 +200,14 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
                    const rgnn_conv* next, float* P_next, cudaStream_t stream) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
+    if (tc_stack_supported(c.upd) && c.upd.n == 1 && (next == nullptr || tc_proj_supported(d))) {
+        if (next != nullptr) {
+            ConvDims dn;
+            if (!conv_dims(*next, &dn)) return RGNN_ERR_INVALID;
+            RGNN_REQUIRE(dn.cn == d.cn && dn.h == d.h, "conv blocks with different channel plans");
+        }
+        return tc_run_conv_nodes(c, d, n_nodes, x, agg, out, next, P_next, stream);
+    }
     FwdBuilder b(n_nodes);
     b.load_rows(b.cur, x, d.cn, d.cn, 0);
     b.load_rows(b.cur, agg, d.cn, d.cn, d.cn);
@@ -266,7 +278,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     const ConvDims& d = pl.d;
     const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
     int rc;
-    {   // node encoder (+ first layer's projections)
+    if (tc_stack_supported(net.node_enc) && tc_proj_supported(d)) {
+        if ((rc = tc_run_node_encoder(net.node_enc, net.conv[0], d, node_features, N, pl.x[0], pl.P[0], stream))) return rc;
+    } else {   // node encoder (+ first layer's projections)
         FwdBuilder b(N);
         const int in = stack_in(net.node_enc);
         b.load_rows(b.cur, node_features, in, in, 0, round_up(in, 8));
@@ -276,7 +290,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if (E > 0) {   // edge encoder, rows gathered into target-major order
+    if (E > 0 && tc_stack_supported(net.edge_enc)) {
+        if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream))) return rc;
+    } else if (E > 0) {   // edge encoder, rows gathered into target-major order
         FwdBuilder b(E);
         const int in = stack_in(net.edge_enc);
         b.load_rows(b.cur, edge_features, in, in, 0, round_up(in, 8), g.perm);
@@ -295,7 +311,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     if ((rc = run_stack_fwd(net.head_node, xL, N, node_cls, stream))) return rc;
     if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream))) return rc;
     if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream))) return rc;
-    if (g.n_und > 0) {
+    if (g.n_und > 0 && tc_stack_supported(net.head_link)) {
+        if ((rc = tc_run_pairsum_stack(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream))) return rc;
+    } else if (g.n_und > 0) {
         FwdBuilder b(g.n_und);
         Step* s = b.add(OP_LOAD_PAIRSUM, b.cur);
         s->p0 = pl.hlink; s->p1 = g.und_a; s->p2 = g.und_b; s->i0 = pl.link_w; s->i1 = pl.link_w;
@@ -305,7 +323,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if ((rc = launch_program(b.p, stream))) return rc;
     }
     if ((rc = run_stack_fwd(net.class_node, xL, N, pl.gcls, stream))) return rc;
-    if (g.n_clusters > 0) {
+    if (g.n_clusters > 0 && tc_stack_supported(net.head_class)) {
+        if ((rc = tc_run_segmax_stack(net.head_class, pl.gcls, pl.cls_w, g.cl_ptr, g.cl_members, g.n_clusters, obj_cls, stream))) return rc;
+    } else if (g.n_clusters > 0) {
         FwdBuilder b(g.n_clusters);
         Step* s = b.add(OP_LOAD_SEGMAX, b.cur);
         s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
@@ -325,7 +345,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
 using namespace rgnn;
 
 extern "C" size_t rgnn_packed_weight_floats(int in_features, int out_features) {
-    return (size_t)round_up(in_features, 8) * round_up(out_features, 64);
+    return (size_t)round_up(in_features, 8) * round_up(out_features, 64) + tc_linear_pack_floats(in_features, out_features);
 }
 
 extern "C" int rgnn_pack_linear(const float* weight, int in_features, int out_features, float* weight_t, void* stream) {
@@ -402,5 +422,5 @@ extern "C" int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, 
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d);
+    return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d) + tc_proj_pack_floats(d);
 }

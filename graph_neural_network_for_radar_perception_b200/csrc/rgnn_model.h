@@ -43,4 +43,21 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
 int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
                       const float* wpack, float* agg, cudaStream_t stream);
 
+// tensor-core row-MLP programs, rgnn_model_tc.cu
+bool tc_stack_supported(const rgnn_stack& s);
+bool tc_proj_supported(const ConvDims& d);
+size_t tc_proj_pack_floats(const ConvDims& d);
+int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream);
+int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t stream);
+int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream);
+int tc_run_node_encoder(const rgnn_stack& enc, const rgnn_conv& first, const ConvDims& d, const float* node_features, int n_nodes,
+                        float* x0, float* P0, cudaStream_t stream);
+int tc_run_conv_nodes(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
+                      const rgnn_conv* next, float* P_next, cudaStream_t stream);
+int tc_run_pairsum_stack(const rgnn_stack& s, const float* h, int ld, const int* ia, const int* ib, int n_rows, float* y,
+                         cudaStream_t stream);
+int tc_run_segmax_stack(const rgnn_stack& s, const float* g, int ld, const int* ptr, const int* members, int n_rows, float* y,
+                        cudaStream_t stream);
+size_t tc_linear_pack_floats(int in_features, int out_features);
+
 }  // namespace rgnn

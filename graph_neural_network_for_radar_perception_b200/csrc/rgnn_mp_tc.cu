@@ -18,6 +18,7 @@
 #include "rgnn_model.h"
 #include "rgnn_tc.cuh"
 #include "rgnn_tile.cuh"
+#include "rgnn_tc_rows.cuh"
 
 namespace rgnn {
 
@@ -75,76 +76,6 @@ struct MpTcLayout {
     static_assert(NQ == 2 || NQ == 4, "row statistics exchange through TMEM");
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
-
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// sum of one value per thread over the NQ threads that share an edge row (same lane, different warps): the partials
-// meet in NQ spare TMEM columns of the row's lane.
-template <int NQ>
-__device__ __forceinline__ float row_allreduce(float v, uint32_t t_cols, int q, int bar_id) {
-    tc::tmem_st1(t_cols + q, v);
-    tc::tmem_wait_st();
-    tc::tc_fence_before();
-    group_sync(bar_id, 32 * NQ);
-    tc::tc_fence_after();
-    float p0, p1, p2 = 0.f, p3 = 0.f;
-    if (NQ == 4) tc::tmem_ld4(t_cols, p0, p1, p2, p3); else tc::tmem_ld2(t_cols, p0, p1);
-    tc::tmem_wait_ld();
-    return (p0 + p1) + (p2 + p3);
-}
-
-// channel_normalization + LeakyReLU on a row whose C columns are spread over NQ threads (2*CP each, held as
-// register pairs for the packed f32x2 pipe).  Two-pass mean / unbiased std like the reference (common.py:215-220).
-template <int CP, int NQ>
-__device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, const float* __restrict__ sp, const float* __restrict__ mp,
-                                             bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id) {
-    if (sp != nullptr) {
-        float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) s2 = __fadd2_rn(s2, z[c]);
-        const float mean = row_allreduce<NQ>(s2.x + s2.y, t_cols, q, bar_id) / (float)C;
-        const float2 nm = make_float2(-mean, -mean);
-        float2 ss2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            z[c] = __fadd2_rn(z[c], nm);
-            ss2 = __ffma2_rn(z[c], z[c], ss2);
-        }
-        const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
-        const float sd = sqrtf(ss / (float)(C - 1));
-        const float k = __ldg(sp) / (sd + NORM_EPS);
-        const float sh = __ldg(mp);
-        const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
-    }
-    if (act) {   // LeakyReLU(0.01): max(v, 0.01 v)
-        const float2 sl = make_float2(LEAKY, LEAKY);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            const float2 t = __fmul2_rn(z[c], sl);
-            z[c].x = fmaxf(z[c].x, t.x);
-            z[c].y = fmaxf(z[c].y, t.y);
-        }
-    }
-}
-
-// named barriers (0 = __syncthreads, 1..4 = the NQ warps sharing 32 rows)
-constexpr int BAR_WORKERS = 5;   // all worker warps
-constexpr int BAR_A_READY = 6;   // workers arrive, MMA warp waits: A operand (smem) written
-constexpr int BAR_Y_READY = 7;   // workers arrive, MMA warp waits: y1 (TMEM) written
-__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// 32 bytes per lane and request: a full L2 sector (the 16-byte form fetches the sector twice when L1 is tiny)
-__device__ __forceinline__ void ldg256(const float* p, float2& a, float2& b, float2& c, float2& d) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y)
-                 : "l"(p));
-}
 
 // Thread roles: 128*NQ worker threads (thread = edge row x column quarter; loads, both epilogues, segmented sum)
 // + one extra warp whose lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy,
@@ -521,6 +452,8 @@ __global__ void pack_split_kernel(const float* __restrict__ W, int ldW, int koff
         lo[i] = l;
     }
 }
+
+int g_use_tensor_cores_flag() { return g_use_tensor_cores; }
 
 bool mp_tc_supported(const ConvDims& d) { return g_use_tensor_cores && d.cn == 64 && d.ce == 64 && d.h == 128; }
 

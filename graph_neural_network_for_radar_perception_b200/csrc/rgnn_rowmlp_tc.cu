@@ -1,0 +1,348 @@
+// Interpreter kernel for row-MLP chains on the tensor cores (program format: rgnn_rowmlp_tc.cuh).
+// Roles inside the CTA (1 CTA / SM, persistent over tiles of 128 rows):
+//   256 worker threads   thread = (row, half of the columns): input rows -> TMEM, all epilogues, stores
+//   MMA warp  (lane 0)   issues every tcgen05.mma (A operand from TMEM, weights from the shared-memory ring)
+//   load warp (lane 0)   streams the weight chunks of every stage, L2 -> shared memory, with cp.async.bulk
+// Synchronisation: mbarriers full[slot] (bulk copy landed) / empty[slot] (tcgen05.commit: the MMAs that read the slot
+// are done) / d_ready (tcgen05.commit: a stage's accumulator is complete), and a named barrier on which the workers
+// arrive when the next A operand is in TMEM.
+#include "rgnn_rowmlp_tc.cuh"
+#include "rgnn_tc_rows.cuh"
+
+namespace rgnn {
+
+constexpr int RM_NQ = 2;                    // threads per row
+constexpr int RM_NW = 128 * RM_NQ;          // worker threads
+constexpr int RM_NT = RM_NW + 128;          // + one warpgroup holding the MMA and the load warp
+constexpr size_t RM_SMEM = (size_t)TC_SLOTS * TC_SLOT_FLOATS * 4 + 128;
+
+namespace tc {
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// input rows -> A operand in TMEM (hi | lo)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_input_block(const TcInput& in, int row_g, bool valid, int c, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (!valid) return;
+    if (in.mode == TC_IN_ROWS) {
+        const size_t r = in.i0 ? (size_t)__ldg(in.i0 + row_g) : (size_t)row_g;
+        if (c + 8 <= in.w0 && ((in.ld0 | in.w0) & 3) == 0) {
+            const float4* p = reinterpret_cast<const float4*>(in.p0 + r * in.ld0 + c);
+            const float4 a = __ldg(p), b = __ldg(p + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else if (c >= in.w0 && c + 8 <= in.w0 + in.w1 && ((in.ld1 | in.w0 | in.w1) & 3) == 0) {
+            const float4* p = reinterpret_cast<const float4*>(in.p1 + r * in.ld1 + (c - in.w0));
+            const float4 a = __ldg(p), b = __ldg(p + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cc = c + j;
+                if (cc < in.w0) v[j] = __ldg(in.p0 + r * in.ld0 + cc);
+                else if (cc - in.w0 < in.w1) v[j] = __ldg(in.p1 + r * in.ld1 + (cc - in.w0));
+            }
+        }
+    } else if (in.mode == TC_IN_PAIRSUM) {
+        const size_t a = (size_t)__ldg(in.i0 + row_g), b = (size_t)__ldg(in.i1 + row_g);
+        const float4* pa = reinterpret_cast<const float4*>(in.p0 + a * in.ld0 + c);
+        const float4* pb = reinterpret_cast<const float4*>(in.p0 + b * in.ld0 + c);
+        const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+        v[0] = a0.x + b0.x; v[1] = a0.y + b0.y; v[2] = a0.z + b0.z; v[3] = a0.w + b0.w;
+        v[4] = a1.x + b1.x; v[5] = a1.y + b1.y; v[6] = a1.z + b1.z; v[7] = a1.w + b1.w;
+    } else {   // TC_IN_SEGMAX: max over the member rows of cluster row_g (reference gnn_blocks.py:384-386)
+        const int m0 = __ldg(in.i0 + row_g), m1 = __ldg(in.i0 + row_g + 1);
+        if (m1 > m0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = -INFINITY;
+            for (int m = m0; m < m1; ++m) {
+                const float4* p = reinterpret_cast<const float4*>(in.p0 + (size_t)__ldg(in.i1 + m) * in.ld0 + c);
+                const float4 a = __ldg(p), b = __ldg(p + 1);
+                v[0] = fmaxf(v[0], a.x); v[1] = fmaxf(v[1], a.y); v[2] = fmaxf(v[2], a.z); v[3] = fmaxf(v[3], a.w);
+                v[4] = fmaxf(v[4], b.x); v[5] = fmaxf(v[5], b.y); v[6] = fmaxf(v[6], b.z); v[7] = fmaxf(v[7], b.w);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+// result pairs z[CP] (columns col0 .. col0 + 2 CP of the row): residual, store, next A operand
+template <int CP>
+__device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, int row_g, bool valid, int col0, uint32_t t_row) {
+    if (e.resid != nullptr && valid) {
+        const float2* r = reinterpret_cast<const float2*>(e.resid + (size_t)row_g * e.resid_ld + col0);
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+            if (col0 + 2 * c < e.n_true) z[c] = __fadd2_rn(z[c], __ldg(r + c));
+    }
+    if (e.store != nullptr && valid) {
+        float* o = e.store + (size_t)row_g * e.store_ld + col0;
+        if (((e.store_ld | e.store_w) & 3) == 0) {
+#pragma unroll
+            for (int c = 0; c < CP; c += 2)
+                if (col0 + 2 * c < e.store_w) *reinterpret_cast<float4*>(o + 2 * c) = make_float4(z[c].x, z[c].y, z[c + 1].x, z[c + 1].y);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (col0 + 2 * c < e.store_w) o[2 * c] = z[c].x;
+                if (col0 + 2 * c + 1 < e.store_w) o[2 * c + 1] = z[c].y;
+            }
+        }
+    }
+    if (e.y_hi >= 0) {
+#pragma unroll
+        for (int c = 0; c < CP; c += 8) {
+            float2 hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split_tf32(z[c + j], hi[j], lo[j]);
+            tc::tmem_st16(t_row + e.y_hi + col0 + 2 * c, hi);
+            tc::tmem_st16(t_row + e.y_lo + col0 + 2 * c, lo);
+        }
+    }
+}
+
+template <int CP>
+__device__ __forceinline__ void load_acc_bias(float2 (&z)[CP], const TcEpi& e, int col0, uint32_t t_row) {
+#pragma unroll
+    for (int c = 0; c < CP; c += 8) tc::tmem_ld16(t_row + e.d + col0 + 2 * c, z + c);
+    tc::tmem_wait_ld();
+    if (e.bias != nullptr) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            const int cc = col0 + 2 * c;
+            if (cc + 1 < e.n_true) z[c] = __fadd2_rn(z[c], __ldg(reinterpret_cast<const float2*>(e.bias + cc)));
+            else if (cc < e.n_true) z[c].x += __ldg(e.bias + cc);
+        }
+    }
+}
+
+// whole (per-thread share of the) row in registers: needed when the layer normalises over the row
+template <int CPT>
+__device__ __forceinline__ void epilogue_norm(const TcEpi& e, int row, int row_g, bool valid, int q, uint32_t t_row, int bar_id) {
+    float2 z[CPT / 2];
+    const int col0 = q * CPT;
+    load_acc_bias<CPT / 2>(z, e, col0, t_row);
+    row_norm_act<CPT / 2, RM_NQ>(z, e.n_true, e.scale, e.shift, e.act != 0, t_row + TC_XS_COL, q, bar_id);
+    finish_columns<CPT / 2>(z, e, row_g, valid, col0, t_row);
+    (void)row;
+}
+
+// no normalisation: 16 columns at a time
+__device__ __forceinline__ void epilogue_plain(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row) {
+    const int cpt = e.n_cols / RM_NQ;
+    for (int b = 0; b < cpt; b += 16) {
+        float2 z[8];
+        const int col0 = q * cpt + b;
+        load_acc_bias<8>(z, e, col0, t_row);
+        if (e.act) {
+            const float2 sl = make_float2(LEAKY, LEAKY);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float2 t = __fmul2_rn(z[c], sl);
+                z[c].x = fmaxf(z[c].x, t.x);
+                z[c].y = fmaxf(z[c].y, t.y);
+            }
+        }
+        finish_columns<8>(z, e, row_g, valid, col0, t_row);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_constant__ TcProgram pg) {
+    extern __shared__ __align__(1024) float smem[];
+    float* ring = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SLOTS * TC_SLOT_FLOATS);   // full[3] empty[3] d_ready
+    uint64_t* full = bars;
+    uint64_t* empty = bars + TC_SLOTS;
+    uint64_t* d_ready = bars + 2 * TC_SLOTS;
+    uint32_t* slot_ptr = reinterpret_cast<uint32_t*>(bars + 2 * TC_SLOTS + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < TC_SLOTS; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(d_ready, 1);
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(slot_ptr, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+    const int n_tiles = (pg.n_rows + 127) / 128;
+    const int np = 3;
+
+    if (tid >= RM_NW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int w = warp - RM_NW / 32;
+        if (w == 0) {
+            // =========================== MMA issue warp ===========================
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < pg.n_stages; ++s) {
+                    const TcStage& st = pg.st[s];
+                    group_sync(BAR_Y_READY, RM_NW + 32);      // this stage's A operand is in TMEM
+                    tc::tc_fence_after();
+                    if (lane == 0) {
+                        for (int j = 0; j < st.n_mma; ++j, ++cnt) {
+                            const TcMma& m = st.mma[j];
+                            const uint32_t slot = cnt % TC_SLOTS, par = (cnt / TC_SLOTS) & 1u;
+                            tc::mbar_wait(&full[slot], par);
+                            tc::tc_fence_after();
+                            const uint32_t sb = tc::smem_u32(ring + slot * TC_SLOT_FLOATS);
+                            const uint32_t lbo = (uint32_t)m.ldn * 16u;
+                            const uint32_t idesc = tc::idesc_tf32(128, m.N);
+                            bool acc = m.acc != 0;
+                            for (int p = 0; p < np; ++p) {     // 3xTF32, small terms first: lo*hi, hi*lo, hi*hi
+                                const int pa = p == 0 ? 1 : 0, pb = p == 1 ? 1 : 0;
+                                const uint32_t acol = tmem + (pa ? m.a_lo : m.a_hi);
+                                const uint64_t bd0 = tc::smem_desc(sb + pb * (uint32_t)(m.K * m.ldn * 4) + (uint32_t)m.n_off * 16u, lbo, 128);
+                                for (int ks = 0; ks < m.K / 8; ++ks) {
+                                    tc::mma_tf32_ts(tmem + m.d, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc, acc);
+                                    acc = true;
+                                }
+                            }
+                            tc::mma_commit(&empty[slot]);     // slot reusable once these MMAs have read it
+                        }
+                        tc::mma_commit(d_ready);              // accumulator of the stage complete
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (w == 1) {
+            // =========================== weight load warp ===========================
+            if (lane == 0) {
+                uint32_t cnt = 0;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    for (int s = 0; s < pg.n_stages; ++s) {
+                        const TcStage& st = pg.st[s];
+                        for (int j = 0; j < st.n_mma; ++j, ++cnt) {
+                            const TcMma& m = st.mma[j];
+                            const uint32_t slot = cnt % TC_SLOTS, par = (cnt / TC_SLOTS) & 1u;
+                            tc::mbar_wait(&empty[slot], par ^ 1u);
+                            const uint32_t bytes = (uint32_t)(m.K * m.ldn * 8);
+                            tc::mbar_expect_tx(&full[slot], bytes);
+                            tc::bulk_g2s(ring + slot * TC_SLOT_FLOATS, m.w, bytes, &full[slot]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== worker warps ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int row = tid & 127, q = tid >> 7;
+        const int bar_id = 1 + (row >> 5);
+        const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);
+        uint32_t dphase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int row_g = tile * 128 + row;
+            const bool valid = row_g < pg.n_rows;
+            // ---- input rows -> TMEM (hi | lo) ----
+            {
+                const TcInput& in = pg.in;
+                const bool split = (in.k_pad % (8 * RM_NQ)) == 0;
+                const int cw = split ? in.k_pad / RM_NQ : in.k_pad;
+                const int c0 = split ? q * cw : 0;
+                if (split || q == 0) {
+                    for (int c = c0; c < c0 + cw; c += 8) {
+                        float v[8], hi[8], lo[8];
+                        load_input_block(in, row_g, valid, c, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], hi[j], lo[j]);
+                        tc::tmem_st8(t_row + in.a_hi + c, hi);
+                        tc::tmem_st8(t_row + in.a_lo + c, lo);
+                    }
+                }
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                bar_arrive(BAR_Y_READY, RM_NW + 32);
+            }
+            for (int s = 0; s < pg.n_stages; ++s) {
+                const TcEpi& e = pg.st[s].epi;
+                tc::mbar_wait(d_ready, dphase);
+                dphase ^= 1u;
+                tc::tc_fence_after();
+                if (e.scale != nullptr) {
+                    const int cpt = e.n_cols / RM_NQ;
+                    if (cpt == 64) epilogue_norm<64>(e, row, row_g, valid, q, t_row, bar_id);
+                    else if (cpt == 32) epilogue_norm<32>(e, row, row_g, valid, q, t_row, bar_id);
+                    else epilogue_norm<16>(e, row, row_g, valid, q, t_row, bar_id);
+                } else {
+                    epilogue_plain(e, row_g, valid, q, t_row);
+                }
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                if (s + 1 < pg.n_stages) bar_arrive(BAR_Y_READY, RM_NW + 32);
+            }
+            group_sync(BAR_WORKERS, RM_NW);     // every worker is done with this tile's TMEM columns
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
+    if (pg.n_rows <= 0) return RGNN_OK;
+    static bool configured = false;
+    if (!configured) {
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
+        configured = true;
+    }
+    const int n_tiles = (pg.n_rows + 127) / 128;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    rowmlp_tc_kernel<<<grid, RM_NT, RM_SMEM, stream>>>(pg);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing for the chunk stream: rows [n0, n0+Nt) x columns [k0 + c*kc, ...) of W (row stride ldW) ->
+// per K chunk:  hi (kc/4, Np, 4)  |  lo (kc/4, Np, 4),   zero padded to Np rows / Kp columns
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_tc_kernel(const float* __restrict__ W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp,
+                               int kc, int n_loop, float* __restrict__ dst) {
+    const int tot = Kp * n_loop;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+        const int k = i / n_loop, n = i - k * n_loop;
+        float w = 0.f;
+        if (k < Kt && n < Nt) w = W[(size_t)(n0 + n) * ldW + k0 + k];
+        float h, l;
+        tc::split_tf32(w, h, l);
+        const int chunk = k / kc, kk = k - chunk * kc;
+        float* base = dst + (size_t)chunk * (2 * kc * Np);
+        const int off = ((kk >> 2) * Np + nd0 + n) * 4 + (kk & 3);
+        base[off] = h;
+        base[kc * Np + off] = l;
+    }
+}
+
+int pack_tc(const float* W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp, int kc, bool pad_rows, float* dst,
+            cudaStream_t stream) {
+    const int n_loop = pad_rows ? Np - nd0 : Nt;
+    const int blocks = (Kp * n_loop + 255) / 256;
+    pack_tc_kernel<<<blocks > 64 ? 64 : blocks, 256, 0, stream>>>(W, ldW, n0, Nt, nd0, Np, k0, Kt, Kp, kc, n_loop, dst);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+}  // namespace rgnn

