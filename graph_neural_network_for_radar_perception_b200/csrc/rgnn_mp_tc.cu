@@ -43,6 +43,7 @@ struct MpTcArgs {
     long long* prof;        // PROFILE builds: [grid][12] cycle counters of thread 0
 };
 
+extern int g_rowmlp_profile;
 static int g_tf32_passes = 3;
 static int g_use_tensor_cores = 1;
 static int g_debug = 0;
@@ -281,6 +282,14 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             if (PROFILE && tid == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
         };
         if (PROFILE) tlast = clock64();
+        // per-layer constants once, in registers (no global load may sit in the epilogues' dependent chains)
+        const bool norm1 = a.s1 != nullptr, norm2 = a.s2 != nullptr;
+        const float s1v = norm1 ? __ldg(a.s1) : 1.f, m1v = norm1 ? __ldg(a.m1) : 0.f;
+        const float s2v = norm2 ? __ldg(a.s2) : 1.f, m2v = norm2 ? __ldg(a.m2) : 0.f;
+        float2 b2v[CQ / 2];
+#pragma unroll
+        for (int c = 0; c < CQ / 2; ++c)
+            b2v[c] = a.b2 ? __ldg(reinterpret_cast<const float2*>(a.b2 + q * CQ) + c) : make_float2(0.f, 0.f);
         uint32_t phase = 0;
         int buf = 0;
         bool have_prev = false;
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
 #pragma unroll
                 for (int c = 0; c < HQ / 2; ++c) z[c] = __fadd2_rn(z[c], d[c]);
             }
-            row_norm_act<HQ / 2, NQ>(z, H, a.s1, a.m1, a.act1 != 0, t_row + COL_XS, q, bar_id);
+            row_norm_act<HQ / 2, NQ>(z, H, norm1, s1v, m1v, a.act1 != 0, t_row + COL_XS, q, bar_id);
             if (np == 1) {
 #pragma unroll
                 for (int c = 0; c < HQ; c += 16) tc::tmem_st16(t_row + q * HQ + c, z + c / 2);
@@ -400,9 +409,6 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
 
             // ---- (e) epilogue 2: message = act(norm(D2 + b2)) -> stage ----
             float2 m[CQ / 2];
-#pragma unroll
-            for (int c = 0; c < CQ / 2; ++c)
-                m[c] = a.b2 ? __ldg(reinterpret_cast<const float2*>(a.b2 + q * CQ) + c) : make_float2(0.f, 0.f);
             tc::mbar_wait(&bars[1], phase);
             tc::tc_fence_after();
             tick(7);
@@ -412,9 +418,9 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 for (int c = 0; c < CQ; c += 16) tc::tmem_ld16(t_row + COL_D2 + q * CQ + c, d + c / 2);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(m[c], d[c]);
+                for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(b2v[c], d[c]);
             }
-            row_norm_act<CQ / 2, NQ>(m, CN, a.s2, a.m2, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
+            row_norm_act<CQ / 2, NQ>(m, CN, norm2, s2v, m2v, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
 #pragma unroll
             for (int c4 = 0; c4 < CQ / 4; ++c4) {
                 const int chunk = (q * (CQ / 4) + c4) ^ (row & 7);
@@ -530,7 +536,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     using namespace rgnn;
     if (name != nullptr && strcmp(name, "tf32_passes") == 0 && (value == 1 || value == 3)) { g_tf32_passes = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores = value; return RGNN_OK; }
-    if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; return RGNN_OK; }
+    if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; g_rowmlp_profile = (value & 8) != 0; return RGNN_OK; }
     set_error("rgnn_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
     return RGNN_ERR_INVALID;
 }

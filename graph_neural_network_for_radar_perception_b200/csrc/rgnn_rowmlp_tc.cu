@@ -8,13 +8,20 @@
 // arrive when the next A operand is in TMEM.
 #include "rgnn_rowmlp_tc.cuh"
 #include "rgnn_tc_rows.cuh"
+#include "rgnn_tile.cuh"
 
 namespace rgnn {
 
 constexpr int RM_NQ = 2;                    // threads per row
 constexpr int RM_NW = 128 * RM_NQ;          // worker threads
 constexpr int RM_NT = RM_NW + 128;          // + one warpgroup holding the MMA and the load warp
-constexpr size_t RM_SMEM = (size_t)TC_SLOTS * TC_SLOT_FLOATS * 4 + 128;
+constexpr int RM_STG_FLOATS = 128 * 128;     // input staging: 128 rows x up to 128 columns (64 KB)
+constexpr int RM_CST_LD = 256 + 4;          // per stage: bias[256] (zero padded), scale, shift
+constexpr int RM_OFF_STG = TC_SLOTS * TC_SLOT_FLOATS;
+constexpr int RM_OFF_CST = RM_OFF_STG + RM_STG_FLOATS;
+constexpr int RM_OFF_BAR = RM_OFF_CST + TC_MAX_STAGES * RM_CST_LD;
+constexpr size_t RM_SMEM = (size_t)(RM_OFF_BAR + 32) * 4;
+static_assert(RM_SMEM <= 227 * 1024 && (RM_OFF_BAR % 2) == 0, "shared memory budget / mbarrier alignment");
 
 namespace tc {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -84,12 +91,11 @@ __device__ __forceinline__ void load_input_block(const TcInput& in, int row_g, b
 // ---------------------------------------------------------------------------------------------
 // result pairs z[CP] (columns col0 .. col0 + 2 CP of the row): residual, store, next A operand
 template <int CP>
-__device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, int row_g, bool valid, int col0, uint32_t t_row) {
-    if (e.resid != nullptr && valid) {
-        const float2* r = reinterpret_cast<const float2*>(e.resid + (size_t)row_g * e.resid_ld + col0);
+__device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, int row_g, bool valid, int col0, uint32_t t_row,
+                                               const float2 (&res)[CP] /* prefetched residual */, bool has_res) {
+    if (has_res) {
 #pragma unroll
-        for (int c = 0; c < CP; ++c)
-            if (col0 + 2 * c < e.n_true) z[c] = __fadd2_rn(z[c], __ldg(r + c));
+        for (int c = 0; c < CP; ++c) z[c] = __fadd2_rn(z[c], res[c]);
     }
     if (e.store != nullptr && valid) {
         float* o = e.store + (size_t)row_g * e.store_ld + col0;
@@ -117,39 +123,41 @@ __device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, 
     }
 }
 
+// accumulator columns + bias; `cb` = this stage's constants in shared memory (bias zero padded to 256, scale, shift)
 template <int CP>
-__device__ __forceinline__ void load_acc_bias(float2 (&z)[CP], const TcEpi& e, int col0, uint32_t t_row) {
+__device__ __forceinline__ void load_acc_bias(float2 (&z)[CP], const TcEpi& e, int col0, uint32_t t_row, const float* __restrict__ cb) {
 #pragma unroll
     for (int c = 0; c < CP; c += 8) tc::tmem_ld16(t_row + e.d + col0 + 2 * c, z + c);
     tc::tmem_wait_ld();
-    if (e.bias != nullptr) {
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            const int cc = col0 + 2 * c;
-            if (cc + 1 < e.n_true) z[c] = __fadd2_rn(z[c], __ldg(reinterpret_cast<const float2*>(e.bias + cc)));
-            else if (cc < e.n_true) z[c].x += __ldg(e.bias + cc);
-        }
-    }
+    for (int c = 0; c < CP; ++c) z[c] = __fadd2_rn(z[c], *reinterpret_cast<const float2*>(cb + col0 + 2 * c));
 }
 
 // whole (per-thread share of the) row in registers: needed when the layer normalises over the row
 template <int CPT>
-__device__ __forceinline__ void epilogue_norm(const TcEpi& e, int row, int row_g, bool valid, int q, uint32_t t_row, int bar_id) {
+__device__ __forceinline__ void epilogue_norm(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row, int bar_id,
+                                              const float* __restrict__ cb) {
     float2 z[CPT / 2];
     const int col0 = q * CPT;
-    load_acc_bias<CPT / 2>(z, e, col0, t_row);
-    row_norm_act<CPT / 2, RM_NQ>(z, e.n_true, e.scale, e.shift, e.act != 0, t_row + TC_XS_COL, q, bar_id);
-    finish_columns<CPT / 2>(z, e, row_g, valid, col0, t_row);
-    (void)row;
+    // the residual row (identity residual of the conv block) is requested before anything else so that its L2 round
+    // trip overlaps the normalisation
+    float2 res[CPT / 2];
+    const bool has_res = e.resid != nullptr;
+#pragma unroll
+    for (int c = 0; c < CPT / 2; ++c)
+        res[c] = (has_res && valid) ? __ldg(reinterpret_cast<const float2*>(e.resid + (size_t)row_g * e.resid_ld + col0) + c) : make_float2(0.f, 0.f);
+    load_acc_bias<CPT / 2>(z, e, col0, t_row, cb);
+    row_norm_act<CPT / 2, RM_NQ>(z, e.n_true, true, cb[256], cb[257], e.act != 0, t_row + TC_XS_COL, q, bar_id);
+    finish_columns<CPT / 2>(z, e, row_g, valid, col0, t_row, res, has_res);
 }
 
 // no normalisation: 16 columns at a time
-__device__ __forceinline__ void epilogue_plain(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row) {
+__device__ __forceinline__ void epilogue_plain(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row, const float* __restrict__ cb) {
     const int cpt = e.n_cols / RM_NQ;
     for (int b = 0; b < cpt; b += 16) {
         float2 z[8];
         const int col0 = q * cpt + b;
-        load_acc_bias<8>(z, e, col0, t_row);
+        load_acc_bias<8>(z, e, col0, t_row, cb);
         if (e.act) {
             const float2 sl = make_float2(LEAKY, LEAKY);
 #pragma unroll
@@ -159,17 +167,23 @@ __device__ __forceinline__ void epilogue_plain(const TcEpi& e, int row_g, bool v
                 z[c].y = fmaxf(z[c].y, t.y);
             }
         }
-        finish_columns<8>(z, e, row_g, valid, col0, t_row);
+        float2 none[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) none[c] = make_float2(0.f, 0.f);
+        finish_columns<8>(z, e, row_g, valid, col0, t_row, none, false);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_constant__ TcProgram pg) {
+template <bool PROFILE>
+__global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_constant__ TcProgram pg, long long* prof) {
     extern __shared__ __align__(1024) float smem[];
     float* ring = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SLOTS * TC_SLOT_FLOATS);   // full[3] empty[3] d_ready
+    float* stg = smem + RM_OFF_STG;
+    float* cst = smem + RM_OFF_CST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_OFF_BAR);   // full[] empty[] d_ready
     uint64_t* full = bars;
     uint64_t* empty = bars + TC_SLOTS;
     uint64_t* d_ready = bars + 2 * TC_SLOTS;
@@ -182,6 +196,15 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(slot_ptr, 512);
+    for (int i = tid; i < pg.n_stages * RM_CST_LD; i += RM_NT) {     // per-stage constants -> shared memory, once
+        const int s = i / RM_CST_LD, c = i - s * RM_CST_LD;
+        const TcEpi& e = pg.st[s].epi;
+        float v = 0.f;
+        if (c < 256) v = (e.bias != nullptr && c < e.n_true) ? __ldg(e.bias + c) : 0.f;
+        else if (c == 256) v = e.scale != nullptr ? __ldg(e.scale) : 1.f;
+        else if (c == 257) v = e.shift != nullptr ? __ldg(e.shift) : 0.f;
+        cst[i] = v;
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -252,16 +275,77 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         const int bar_id = 1 + (row >> 5);
         const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);
         uint32_t dphase = 0;
+        long long pt[2 * TC_MAX_STAGES + 2], tlast = 0;
+        if (PROFILE) {
+            for (int i = 0; i < 2 * TC_MAX_STAGES + 2; ++i) pt[i] = 0;
+            tlast = clock64();
+        }
+        auto tick = [&](int i) {
+            if (PROFILE && tid == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
+        };
+        // Input staging: rows that can be fetched as whole 16-byte-aligned pieces (plain / concatenated rows without
+        // a row index, pair sums) are copied by cp.async into shared memory ONE TILE AHEAD, with every warp
+        // instruction covering whole rows (coalesced); the row-owning threads then pick their columns out of the
+        // XOR-swizzled staging tile.  Per-thread sector gathers of 256-byte rows cost ~9k cycles per tile here.
+        const TcInput& in = pg.in;
+        const bool pair = in.mode == TC_IN_PAIRSUM;
+        const int srow = pair ? 2 * in.k_pad : in.k_pad;          // staged floats per row
+        const bool staged_in = (in.mode == TC_IN_ROWS && in.i0 == nullptr && (in.k_pad % 32) == 0 && in.w0 + in.w1 == in.k_pad &&
+                                ((in.ld0 | in.w0 | in.ld1 | in.w1) & 3) == 0) ||
+                               (pair && (in.k_pad % 32) == 0 && (in.ld0 & 3) == 0 && in.w0 == in.k_pad && srow <= 128);
+        auto stage_input = [&](int tile) {
+            const int c4n = srow >> 2;                            // 16-byte chunks per staged row
+            const int rows_here = min(128, pg.n_rows - tile * 128);
+            for (int i = tid; i < 128 * c4n; i += RM_NW) {
+                const int r = i / c4n, c4 = i - r * c4n;
+                if (r >= rows_here) continue;
+                const int rg = tile * 128 + r, c = 4 * c4;
+                const float* src;
+                if (pair) {
+                    const int node = c < in.k_pad ? __ldg(in.i0 + rg) : __ldg(in.i1 + rg);
+                    src = in.p0 + (size_t)node * in.ld0 + (c < in.k_pad ? c : c - in.k_pad);
+                } else {
+                    src = c < in.w0 ? in.p0 + (size_t)rg * in.ld0 + c : in.p1 + (size_t)rg * in.ld1 + (c - in.w0);
+                }
+                cp_async16(stg + r * srow + ((c4 ^ (r & 7)) << 2), src);
+            }
+            cp_async_commit();
+        };
+        if (staged_in && (int)blockIdx.x < n_tiles) stage_input(blockIdx.x);
+
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int row_g = tile * 128 + row;
             const bool valid = row_g < pg.n_rows;
             // ---- input rows -> TMEM (hi | lo) ----
             {
-                const TcInput& in = pg.in;
                 const bool split = (in.k_pad % (8 * RM_NQ)) == 0;
                 const int cw = split ? in.k_pad / RM_NQ : in.k_pad;
                 const int c0 = split ? q * cw : 0;
-                if (split || q == 0) {
+                if (staged_in) {
+                    cp_async_wait<0>();
+                    group_sync(BAR_WORKERS, RM_NW);               // every thread's copies have landed
+                    for (int c = c0; c < c0 + cw; c += 8) {
+                        float v[8], hi[8], lo[8];
+                        const float4 a0 = *reinterpret_cast<const float4*>(stg + row * srow + (((c >> 2) ^ (row & 7)) << 2));
+                        const float4 a1 = *reinterpret_cast<const float4*>(stg + row * srow + ((((c >> 2) + 1) ^ (row & 7)) << 2));
+                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                        if (pair) {
+                            const int cb = (c + in.k_pad) >> 2;
+                            const float4 b0 = *reinterpret_cast<const float4*>(stg + row * srow + ((cb ^ (row & 7)) << 2));
+                            const float4 b1 = *reinterpret_cast<const float4*>(stg + row * srow + (((cb + 1) ^ (row & 7)) << 2));
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (!valid) v[j] = 0.f;
+                            tc::split_tf32(v[j], hi[j], lo[j]);
+                        }
+                        tc::tmem_st8(t_row + in.a_hi + c, hi);
+                        tc::tmem_st8(t_row + in.a_lo + c, lo);
+                    }
+                    group_sync(BAR_WORKERS, RM_NW);               // staging consumed: the next tile's rows may land
+                    if (tile + (int)gridDim.x < n_tiles) stage_input(tile + gridDim.x);
+                } else if (split || q == 0) {
                     for (int c = c0; c < c0 + cw; c += 8) {
                         float v[8], hi[8], lo[8];
                         load_input_block(in, row_g, valid, c, v);
@@ -275,25 +359,32 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 tc::tc_fence_before();
                 bar_arrive(BAR_Y_READY, RM_NW + 32);
             }
+            tick(0);
             for (int s = 0; s < pg.n_stages; ++s) {
                 const TcEpi& e = pg.st[s].epi;
                 tc::mbar_wait(d_ready, dphase);
                 dphase ^= 1u;
                 tc::tc_fence_after();
+                tick(2 + 2 * s);
+                const float* cb = cst + s * RM_CST_LD;
                 if (e.scale != nullptr) {
                     const int cpt = e.n_cols / RM_NQ;
-                    if (cpt == 64) epilogue_norm<64>(e, row, row_g, valid, q, t_row, bar_id);
-                    else if (cpt == 32) epilogue_norm<32>(e, row, row_g, valid, q, t_row, bar_id);
-                    else epilogue_norm<16>(e, row, row_g, valid, q, t_row, bar_id);
+                    if (cpt == 64) epilogue_norm<64>(e, row_g, valid, q, t_row, bar_id, cb);
+                    else if (cpt == 32) epilogue_norm<32>(e, row_g, valid, q, t_row, bar_id, cb);
+                    else epilogue_norm<16>(e, row_g, valid, q, t_row, bar_id, cb);
                 } else {
-                    epilogue_plain(e, row_g, valid, q, t_row);
+                    epilogue_plain(e, row_g, valid, q, t_row, cb);
                 }
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 if (s + 1 < pg.n_stages) bar_arrive(BAR_Y_READY, RM_NW + 32);
+                tick(3 + 2 * s);
             }
             group_sync(BAR_WORKERS, RM_NW);     // every worker is done with this tile's TMEM columns
+            tick(1);
         }
+        if (PROFILE && tid == 0 && prof != nullptr)
+            for (int i = 0; i < 2 * TC_MAX_STAGES + 2; ++i) prof[blockIdx.x * (2 * TC_MAX_STAGES + 2) + i] = pt[i];
     }
 
     tc::tc_fence_before();
@@ -301,16 +392,36 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+int g_rowmlp_profile = 0;
+
 int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
     if (pg.n_rows <= 0) return RGNN_OK;
     static bool configured = false;
     if (!configured) {
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
         configured = true;
     }
     const int n_tiles = (pg.n_rows + 127) / 128;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    rowmlp_tc_kernel<<<grid, RM_NT, RM_SMEM, stream>>>(pg);
+    if (g_rowmlp_profile) {   // developer aid (rgnn_set_option("debug", 8)): per-stage cycles of worker thread 0; synchronises
+        constexpr int NP = 2 * TC_MAX_STAGES + 2;
+        long long* prof = nullptr;
+        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * NP * grid));
+        rowmlp_tc_kernel<true><<<grid, RM_NT, RM_SMEM, stream>>>(pg, prof);
+        RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
+        long long* h = new long long[NP * grid];
+        RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * NP * grid, cudaMemcpyDeviceToHost));
+        double tot[NP] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < NP; ++i) tot[i] += (double)h[b * NP + i];
+        fprintf(stderr, "[rowmlp_tc profile rows=%d stages=%d] cycles/tile: input=%.0f end=%.0f |", pg.n_rows, pg.n_stages, tot[0] / n_tiles, tot[1] / n_tiles);
+        for (int s = 0; s < pg.n_stages; ++s) fprintf(stderr, " s%d wait=%.0f epi=%.0f", s, tot[2 + 2 * s] / n_tiles, tot[3 + 2 * s] / n_tiles);
+        fprintf(stderr, "\n");
+        delete[] h;
+        cudaFree(prof);
+        return RGNN_OK;
+    }
+    rowmlp_tc_kernel<false><<<grid, RM_NT, RM_SMEM, stream>>>(pg, nullptr);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }

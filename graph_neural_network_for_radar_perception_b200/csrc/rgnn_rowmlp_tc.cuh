@@ -17,7 +17,7 @@ namespace rgnn {
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_MMA = 3;
 constexpr int TC_SLOT_FLOATS = 16384;     // 64 KB weight ring slot: hi + lo copies of a (K chunk x N) block, K*N <= 8192
-constexpr int TC_SLOTS = 3;
+constexpr int TC_SLOTS = 2;
 constexpr int TC_XS_COL = 496;            // 16 spare TMEM columns for the per-row statistics exchange
 
 enum TcInMode : int { TC_IN_ROWS = 0, TC_IN_PAIRSUM = 1, TC_IN_SEGMAX = 2 };

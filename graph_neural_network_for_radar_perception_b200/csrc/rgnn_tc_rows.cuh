@@ -28,9 +28,11 @@ __device__ __forceinline__ float row_allreduce(float v, uint32_t t_cols, int q, 
 // channel_normalization + LeakyReLU on a row whose C columns are spread over NQ threads (2*CP each, held as
 // register pairs for the packed f32x2 pipe).  Two-pass mean / unbiased std like the reference (common.py:215-220).
 template <int CP, int NQ>
-__device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, const float* __restrict__ sp, const float* __restrict__ mp,
+__device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_norm, float scale, float shift,
                                              bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id) {
-    if (sp != nullptr) {
+    // scale / shift are passed BY VALUE: with ~226 KB of shared memory per CTA the L1 is a few KB, and a global load
+    // inside this dependent chain costs an L2 round trip per row tile
+    if (has_norm) {
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < CP; ++c) s2 = __fadd2_rn(s2, z[c]);
@@ -44,9 +46,8 @@ __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, const float
         }
         const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
         const float sd = sqrtf(ss / (float)(C - 1));
-        const float k = __ldg(sp) / (sd + NORM_EPS);
-        const float sh = __ldg(mp);
-        const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh);
+        const float k = scale / (sd + NORM_EPS);
+        const float2 k2 = make_float2(k, k), sh2 = make_float2(shift, shift);
 #pragma unroll
         for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
     }
