@@ -18,6 +18,7 @@ struct Tile {
     int* ibuf;      // [2*TR]
     float* red;     // [32]
     double* dacc;   // [2*MAX_STEPS] per-CTA running sums of the scalar norm-parameter gradients
+    float* wacc;    // per-CTA weight / bias gradient accumulators of the OP_WGRAD steps that fit (Step::i5 = offset)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -382,8 +383,11 @@ __device__ __forceinline__ void op_actnorm_bwd(const Tile& t, const Step& st, in
 }
 
 // dW[c][i3 + k] += sum_r dZ[r][i4 + c] X[r][k]   (c < i0, k < i1), db[c] += sum_r dZ[r][i4 + c].
-// Work item = 4 output rows (c) x 8 columns (k); the tile sum is added to global memory with one RED per
-// element (fp32 atomics: run-to-run summation order across tiles is not fixed).
+// Work item = 4 output rows (c) x 8 columns (k).  When the step owns a shared-memory accumulator (i5 >= 0; assigned
+// by launch_program while they fit) the tile sums are added there -- every element is always updated by the same
+// thread, so no atomics are needed -- and the CTA publishes its totals once, at the end of the kernel; one RED per
+// element and TILE measured ~4x the cost of the wgrad arithmetic itself.  Otherwise the tile sum goes to global
+// memory with one RED per element.
 template <int TR>
 __device__ __forceinline__ void op_wgrad(const Tile& t, const Step& st) {
     const float* dz = t.reg(st.ra);
@@ -392,6 +396,7 @@ __device__ __forceinline__ void op_wgrad(const Tile& t, const Step& st) {
     const int C = st.i0, K = st.i1, ldW = st.i2, wcol = st.i3, zcol = st.i4;
     float* __restrict__ dW = static_cast<float*>(const_cast<void*>(st.p0));
     float* __restrict__ db = static_cast<float*>(const_cast<void*>(st.p1));
+    float* __restrict__ wacc = st.i5 >= 0 ? t.wacc + st.i5 : nullptr;       // [C][K] then [C]
     if (dW != nullptr) {
         const int kg = (K + 7) >> 3, cg = (C + 3) >> 2;
         for (int item = threadIdx.x; item < kg * cg; item += NT) {
@@ -419,10 +424,17 @@ __device__ __forceinline__ void op_wgrad(const Tile& t, const Step& st) {
             for (int i = 0; i < 4; ++i) {
                 const int c = 4 * cq + i;
                 if (c < C) {
-                    float* o = dW + (size_t)c * ldW + wcol + 8 * kq;
+                    if (wacc != nullptr) {
+                        float* o = wacc + c * K + 8 * kq;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (8 * kq + j < K) atomicAdd(o + j, acc[i][j]);
+                        for (int j = 0; j < 8; ++j)
+                            if (8 * kq + j < K) o[j] += acc[i][j];
+                    } else {
+                        float* o = dW + (size_t)c * ldW + wcol + 8 * kq;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (8 * kq + j < K) atomicAdd(o + j, acc[i][j]);
+                    }
                 }
             }
         }
@@ -431,7 +443,7 @@ __device__ __forceinline__ void op_wgrad(const Tile& t, const Step& st) {
         for (int c = threadIdx.x; c < C; c += NT) {
             float s = 0.f;
             for (int r = 0; r < TR; ++r) s += dz[r * ldz + zcol + c];
-            atomicAdd(db + c, s);
+            if (wacc != nullptr) wacc[(dW != nullptr ? C * K : 0) + c] += s; else atomicAdd(db + c, s);
         }
     }
     __syncthreads();
@@ -451,7 +463,9 @@ __global__ void __launch_bounds__(NT, 1) tile_program_kernel(const __grid_consta
     t.ibuf = reinterpret_cast<int*>(t.wst + 2 * KC * CBMAX);
     t.red = reinterpret_cast<float*>(t.ibuf + 2 * TR);
     t.dacc = reinterpret_cast<double*>(t.red + 32);
+    t.wacc = reinterpret_cast<float*>(t.dacc + 2 * MAX_STEPS);
     for (int i = threadIdx.x; i < 2 * MAX_STEPS; i += NT) t.dacc[i] = 0.;
+    for (int i = threadIdx.x; i < prog.wacc_floats; i += NT) t.wacc[i] = 0.f;
     __syncthreads();
 
     const int n_tiles = (prog.n_rows + TR - 1) / TR;
@@ -488,6 +502,18 @@ __global__ void __launch_bounds__(NT, 1) tile_program_kernel(const __grid_consta
         }
     }
     __syncthreads();
+    for (int s = 0; s < prog.n_steps; ++s) {      // publish the shared-memory weight-gradient accumulators
+        const Step& st = prog.steps[s];
+        if (st.op != OP_WGRAD || st.i5 < 0) continue;
+        const int C = st.i0, K = st.i1, ldW = st.i2, wcol = st.i3;
+        float* dW = static_cast<float*>(const_cast<void*>(st.p0));
+        float* db = static_cast<float*>(const_cast<void*>(st.p1));
+        const float* wa = t.wacc + st.i5;
+        if (dW != nullptr)
+            for (int i = threadIdx.x; i < C * K; i += NT) atomicAdd(dW + (size_t)(i / K) * ldW + wcol + (i % K), wa[i]);
+        if (db != nullptr)
+            for (int c = threadIdx.x; c < C; c += NT) atomicAdd(db + c, wa[(dW != nullptr ? C * K : 0) + c]);
+    }
     for (int s = threadIdx.x; s < prog.n_steps; s += NT) {
         const Step& st = prog.steps[s];
         if (st.op == OP_ACTNORM_BWD && st.p0 != nullptr && st.p2 != nullptr) {
@@ -498,14 +524,29 @@ __global__ void __launch_bounds__(NT, 1) tile_program_kernel(const __grid_consta
 }
 
 static size_t program_smem_bytes(const Program& p) {
-    return ((size_t)p.region_floats + MAX_SIGMA * p.tr + 2 * KC * CBMAX + 32) * sizeof(float) + 2 * p.tr * sizeof(int) +
+    return ((size_t)p.region_floats + MAX_SIGMA * p.tr + 2 * KC * CBMAX + 32 + p.wacc_floats) * sizeof(float) + 2 * p.tr * sizeof(int) +
            2 * MAX_STEPS * sizeof(double);
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-int launch_program(const Program& p, cudaStream_t stream) {
-    if (p.n_rows <= 0) return RGNN_OK;
+int launch_program(const Program& p_in, cudaStream_t stream) {
+    if (p_in.n_rows <= 0) return RGNN_OK;
+    Program p = p_in;
+    // give weight-gradient steps a shared-memory accumulator while they fit (in program order)
+    p.wacc_floats = 0;
+    for (int s = 0; s < p.n_steps; ++s) {
+        Step& st = p.steps[s];
+        if (st.op != OP_WGRAD) continue;
+        st.i5 = -1;
+        const int need = (st.p0 != nullptr ? st.i0 * st.i1 : 0) + (st.p1 != nullptr ? st.i0 : 0);
+        Program q = p;
+        q.wacc_floats = p.wacc_floats + need;
+        if (need > 0 && program_smem_bytes(q) <= SMEM_LIMIT) {
+            st.i5 = p.wacc_floats;
+            p.wacc_floats += need;
+        }
+    }
     const size_t smem = program_smem_bytes(p);
     RGNN_REQUIRE(smem <= SMEM_LIMIT, "tile program needs %zu bytes of shared memory (> %zu)", smem, SMEM_LIMIT);
     RGNN_REQUIRE(p.tr == 64 || p.tr == 32, "tile program with tr=%d", p.tr);

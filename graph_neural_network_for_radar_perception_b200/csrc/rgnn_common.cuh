@@ -80,6 +80,7 @@ struct Program {
     int n_rows;
     int tr;                 // rows per tile (64 forward, 32 backward)
     int region_floats;      // total shared-memory floats of all regions
+    int wacc_floats;        // shared-memory weight-gradient accumulators (assigned by launch_program)
     int reg_off[MAX_REGIONS];
     int reg_ld[MAX_REGIONS];
     Step steps[MAX_STEPS];

@@ -20,7 +20,7 @@ constexpr int RM_CST_LD = 256 + 4;          // per stage: bias[256] (zero padded
 constexpr int RM_OFF_STG = TC_SLOTS * TC_SLOT_FLOATS;
 constexpr int RM_OFF_CST = RM_OFF_STG + RM_STG_FLOATS;
 constexpr int RM_OFF_BAR = RM_OFF_CST + TC_MAX_STAGES * RM_CST_LD;
-constexpr size_t RM_SMEM = (size_t)(RM_OFF_BAR + 32) * 4;
+constexpr size_t RM_SMEM = (size_t)(RM_OFF_BAR + 16 + 256) * 4;   // barriers, TMEM slot, 256 pair-sum node ids
 static_assert(RM_SMEM <= 227 * 1024 && (RM_OFF_BAR % 2) == 0, "shared memory budget / mbarrier alignment");
 
 namespace tc {
@@ -293,16 +293,29 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         const bool staged_in = (in.mode == TC_IN_ROWS && in.i0 == nullptr && (in.k_pad % 32) == 0 && in.w0 + in.w1 == in.k_pad &&
                                 ((in.ld0 | in.w0 | in.ld1 | in.w1) & 3) == 0) ||
                                (pair && (in.k_pad % 32) == 0 && (in.ld0 & 3) == 0 && in.w0 == in.k_pad && srow <= 128);
+        // pair sums: the two node ids of every row of a tile, fetched one call ahead (thread t < 128: first node of
+        // row t, else second node of row t - 128) and published to shared memory when the tile is staged -- a global
+        // index load inside the copy loop would put an L2 round trip in front of every 16-byte copy
+        int* idx_s = reinterpret_cast<int*>(smem + RM_OFF_BAR + 16);
+        int my_idx = 0;
+        auto load_pair_idx = [&](int tile) {
+            const int rg = tile * 128 + (tid & 127);
+            my_idx = (pair && rg < pg.n_rows) ? __ldg((tid < 128 ? in.i0 : in.i1) + rg) : 0;
+        };
         auto stage_input = [&](int tile) {
             const int c4n = srow >> 2;                            // 16-byte chunks per staged row
             const int rows_here = min(128, pg.n_rows - tile * 128);
+            if (pair) {
+                idx_s[tid] = my_idx;
+                group_sync(BAR_WORKERS, RM_NW);
+            }
             for (int i = tid; i < 128 * c4n; i += RM_NW) {
                 const int r = i / c4n, c4 = i - r * c4n;
                 if (r >= rows_here) continue;
                 const int rg = tile * 128 + r, c = 4 * c4;
                 const float* src;
                 if (pair) {
-                    const int node = c < in.k_pad ? __ldg(in.i0 + rg) : __ldg(in.i1 + rg);
+                    const int node = idx_s[(c < in.k_pad ? 0 : 128) + r];
                     src = in.p0 + (size_t)node * in.ld0 + (c < in.k_pad ? c : c - in.k_pad);
                 } else {
                     src = c < in.w0 ? in.p0 + (size_t)rg * in.ld0 + c : in.p1 + (size_t)rg * in.ld1 + (c - in.w0);
@@ -310,8 +323,15 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 cp_async16(stg + r * srow + ((c4 ^ (r & 7)) << 2), src);
             }
             cp_async_commit();
+            if (pair) {
+                group_sync(BAR_WORKERS, RM_NW);                   // idx_s may be overwritten by the next call
+                if (tile + (int)gridDim.x < n_tiles) load_pair_idx(tile + gridDim.x);
+            }
         };
-        if (staged_in && (int)blockIdx.x < n_tiles) stage_input(blockIdx.x);
+        if (staged_in && (int)blockIdx.x < n_tiles) {
+            load_pair_idx(blockIdx.x);
+            stage_input(blockIdx.x);
+        }
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int row_g = tile * 128 + row;
