@@ -453,7 +453,7 @@ __device__ __forceinline__ void op_wgrad(const Tile& t, const Step& st) {
 // interpreter
 // ---------------------------------------------------------------------------------------------
 template <int TR>
-__global__ void __launch_bounds__(NT, 1) tile_program_kernel(const __grid_constant__ Program prog) {
+__global__ void __launch_bounds__(NT, 2) tile_program_kernel(const __grid_constant__ Program prog) {
     extern __shared__ __align__(16) float smem[];
     Tile t;
     t.smem = smem;
@@ -533,8 +533,11 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 int launch_program(const Program& p_in, cudaStream_t stream) {
     if (p_in.n_rows <= 0) return RGNN_OK;
     Program p = p_in;
-    // give weight-gradient steps a shared-memory accumulator while they fit (in program order)
+    // Two CTAs share an SM when their shared memory allows it (one CTA's global-memory phases overlap the other's
+    // math); that budget takes precedence over the weight-gradient accumulators, which get what is left.
     p.wacc_floats = 0;
+    const size_t half = (SMEM_LIMIT - 2048) / 2;
+    const size_t budget = program_smem_bytes(p) <= half ? half : SMEM_LIMIT;
     for (int s = 0; s < p.n_steps; ++s) {
         Step& st = p.steps[s];
         if (st.op != OP_WGRAD) continue;
@@ -542,7 +545,7 @@ int launch_program(const Program& p_in, cudaStream_t stream) {
         const int need = (st.p0 != nullptr ? st.i0 * st.i1 : 0) + (st.p1 != nullptr ? st.i0 : 0);
         Program q = p;
         q.wacc_floats = p.wacc_floats + need;
-        if (need > 0 && program_smem_bytes(q) <= SMEM_LIMIT) {
+        if (need > 0 && program_smem_bytes(q) <= budget) {
             st.i5 = p.wacc_floats;
             p.wacc_floats += need;
         }
@@ -557,7 +560,9 @@ int launch_program(const Program& p_in, cudaStream_t stream) {
         configured = true;
     }
     const int n_tiles = (p.n_rows + p.tr - 1) / p.tr;
-    const int grid = min(n_tiles, sm_count());
+    // two CTAs share an SM when their shared memory allows it: one CTA's global-memory phases overlap the other's math
+    const int per_sm = smem <= half ? 2 : 1;
+    const int grid = min(n_tiles, per_sm * sm_count());
     if (p.tr == 64)
         tile_program_kernel<64><<<grid, NT, smem, stream>>>(p);
     else
