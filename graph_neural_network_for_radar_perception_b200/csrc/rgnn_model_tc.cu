@@ -78,8 +78,46 @@ struct TcBuilder {
     TcEpi* layer(const rgnn_linear& L, bool feed) {
         return layer(tc_weights(L), L.in_features, L.out_features, L.bias, L.norm_scale, L.norm_shift, L.activation, feed);
     }
-    // First two layers of an encoder: L0 = (<= 8 inputs -> 256, no norm), L1 = (256 -> <= 128).  L0 is evaluated in four
-    // 64-column blocks (double buffered in R1 / R2) that L1 consumes as K chunks, accumulating in R0.
+    // First two layers of an encoder: L0 = (<= 7 inputs -> 256, no norm), L1 = (256 -> <= 128).  L0 is so narrow that the
+    // workers evaluate it on the CUDA cores straight into the A operand (input mode LIN0), 128 columns at a time; L1
+    // consumes the two halves as K chunks 0-1 and 2-3 of its accumulator.
+    bool encoder_head_lin0(const rgnn_linear& L0, const rgnn_linear& L1) {
+        const int Np1 = tc_np(L1.out_features);
+        if (L0.in_features > 7 || L0.out_features != 256 || L0.norm_scale != nullptr || L1.in_features != 256 || Np1 > 128 ||
+            Np1 != L1.out_features || tc_chunk_k(256, Np1) != 64 || p.in.mode != TC_IN_ROWS || p.in.p1 != nullptr) {
+            ok = false;
+            set_error("encoder head %dx%d / %dx%d not expressible on tensor cores", L0.out_features, L0.in_features, L1.out_features, L1.in_features);
+            return false;
+        }
+        p.in.mode = TC_IN_LIN0;
+        p.in.p1 = L0.weight;
+        p.in.lin_b = L0.bias;
+        p.in.lin_act = L0.activation;
+        p.in.k_pad = 128;
+        p.in.a_hi = R0; p.in.a_lo = R1;
+        const float* w1 = tc_weights(L1);
+        for (int half = 0; half < 2; ++half) {
+            TcStage* s = new_stage();
+            s->n_mma = 2;
+            for (int c = 0; c < 2; ++c) {
+                TcMma& m = s->mma[c];
+                m.a_hi = R0 + 64 * c; m.a_lo = R1 + 64 * c; m.d = R2;
+                m.N = Np1; m.K = 64; m.ldn = Np1; m.n_off = 0; m.acc = (half | c) != 0;
+                m.w = w1 + (size_t)(2 * half + c) * 2 * 64 * Np1;
+            }
+            if (half == 0) {
+                s->epi.refill = 1;
+            } else {
+                fill_epi(s->epi, R2, L1.out_features, L1.bias, L1.norm_scale, L1.norm_shift, L1.activation);
+                s->epi.y_hi = R2; s->epi.y_lo = R1;
+            }
+        }
+        hi = R2; lo = R1; d = R0;
+        width = Np1;
+        return true;
+    }
+    // (kept for reference / other shapes) L0 evaluated on the tensor cores in four 64-column blocks (double buffered in
+    // R1 / R2) that L1 consumes as K chunks, accumulating in R0.
     bool encoder_head(const rgnn_linear& L0, const rgnn_linear& L1) {
         const int Kp0 = tc_kp(L0.in_features), N0 = L0.out_features, Np1 = tc_np(L1.out_features);
         if (Kp0 != 8 || N0 != 256 || L0.norm_scale != nullptr || L1.in_features != 256 || Np1 > 128 || Np1 != L1.out_features ||
@@ -121,6 +159,14 @@ struct TcBuilder {
     TcEpi& last_epi() { return p.st[p.n_stages - 1].epi; }
     int run(cudaStream_t stream) {
         if (!ok) return RGNN_ERR_INVALID;
+        // must mirror the kernel's `staged_in` test: staged input rows occupy ring slot 2
+        const TcInput& in = p.in;
+        const bool pair = in.mode == TC_IN_PAIRSUM;
+        const int srow = pair ? 2 * in.k_pad : in.k_pad;
+        const bool staged = (in.mode == TC_IN_ROWS && in.i0 == nullptr && (in.k_pad % 32) == 0 && in.w0 + in.w1 == in.k_pad &&
+                             ((in.ld0 | in.w0 | in.ld1 | in.w1) & 3) == 0) ||
+                            (pair && (in.k_pad % 32) == 0 && (in.ld0 & 3) == 0 && in.w0 == in.k_pad && srow <= 128);
+        p.n_slots = staged ? 2 : 3;
         return launch_rowmlp_tc(p, stream);
     }
 };
@@ -154,9 +200,13 @@ bool tc_stack_supported(const rgnn_stack& s) {
 static void add_stack(TcBuilder& b, const rgnn_stack& s, bool feed_last) {
     int first = 0;
     if (s.layer[0].in_features <= 8 && s.layer[0].out_features == 256 && s.n >= 2) {
-        b.p.in.a_hi = R_IN;             // the narrow raw input lives outside the rotating regions
-        b.p.in.a_lo = R_IN + 8;
-        b.encoder_head(s.layer[0], s.layer[1]);
+        if (s.layer[0].in_features <= 7) {
+            b.encoder_head_lin0(s.layer[0], s.layer[1]);
+        } else {
+            b.p.in.a_hi = R_IN;             // the narrow raw input lives outside the rotating regions
+            b.p.in.a_lo = R_IN + 8;
+            b.encoder_head(s.layer[0], s.layer[1]);
+        }
         first = 2;
     }
     for (int i = first; i < s.n; ++i) b.layer(s.layer[i], feed_last || i + 1 < s.n);

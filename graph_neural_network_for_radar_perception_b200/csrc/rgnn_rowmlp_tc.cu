@@ -17,9 +17,11 @@ constexpr int RM_NW = 128 * RM_NQ;          // worker threads
 constexpr int RM_NT = RM_NW + 128;          // + one warpgroup holding the MMA and the load warp
 constexpr int RM_STG_FLOATS = 128 * 128;     // input staging: 128 rows x up to 128 columns (64 KB)
 constexpr int RM_CST_LD = 256 + 4;          // per stage: bias[256] (zero padded), scale, shift
-constexpr int RM_OFF_STG = TC_SLOTS * TC_SLOT_FLOATS;
-constexpr int RM_OFF_CST = RM_OFF_STG + RM_STG_FLOATS;
-constexpr int RM_OFF_BAR = RM_OFF_CST + TC_MAX_STAGES * RM_CST_LD;
+constexpr int RM_OFF_STG = 2 * TC_SLOT_FLOATS;                     // aliases ring slot 2
+constexpr int RM_OFF_CST = TC_SLOTS * TC_SLOT_FLOATS;
+static_assert(RM_STG_FLOATS <= TC_SLOT_FLOATS, "input staging must fit in one ring slot");
+constexpr int RM_OFF_W0 = RM_OFF_CST + TC_MAX_STAGES * RM_CST_LD;   // LIN0: [8][256] = W0^T rows 0..6, bias in row 7
+constexpr int RM_OFF_BAR = RM_OFF_W0 + 8 * 256;
 constexpr size_t RM_SMEM = (size_t)(RM_OFF_BAR + 16 + 256) * 4;   // barriers, TMEM slot, 256 pair-sum node ids
 static_assert(RM_SMEM <= 227 * 1024 && (RM_OFF_BAR % 2) == 0, "shared memory budget / mbarrier alignment");
 
@@ -205,6 +207,16 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         else if (c == 257) v = e.shift != nullptr ? __ldg(e.shift) : 0.f;
         cst[i] = v;
     }
+    float* w0s = smem + RM_OFF_W0;
+    if (pg.in.mode == TC_IN_LIN0) {
+        for (int i = tid; i < 8 * 256; i += RM_NT) {
+            const int k = i >> 8, c = i & 255;
+            float v = 0.f;
+            if (k < pg.in.w0) v = __ldg(pg.in.p1 + (size_t)c * pg.in.w0 + k);
+            else if (k == 7 && pg.in.lin_b != nullptr) v = __ldg(pg.in.lin_b + c);
+            w0s[i] = v;
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -226,7 +238,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                     if (lane == 0) {
                         for (int j = 0; j < st.n_mma; ++j, ++cnt) {
                             const TcMma& m = st.mma[j];
-                            const uint32_t slot = cnt % TC_SLOTS, par = (cnt / TC_SLOTS) & 1u;
+                            const uint32_t slot = cnt % (uint32_t)pg.n_slots, par = (cnt / (uint32_t)pg.n_slots) & 1u;
                             tc::mbar_wait(&full[slot], par);
                             tc::tc_fence_after();
                             const uint32_t sb = tc::smem_u32(ring + slot * TC_SLOT_FLOATS);
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                         const TcStage& st = pg.st[s];
                         for (int j = 0; j < st.n_mma; ++j, ++cnt) {
                             const TcMma& m = st.mma[j];
-                            const uint32_t slot = cnt % TC_SLOTS, par = (cnt / TC_SLOTS) & 1u;
+                            const uint32_t slot = cnt % (uint32_t)pg.n_slots, par = (cnt / (uint32_t)pg.n_slots) & 1u;
                             tc::mbar_wait(&empty[slot], par ^ 1u);
                             const uint32_t bytes = (uint32_t)(m.K * m.ldn * 8);
                             tc::mbar_expect_tx(&full[slot], bytes);
@@ -290,9 +302,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         const TcInput& in = pg.in;
         const bool pair = in.mode == TC_IN_PAIRSUM;
         const int srow = pair ? 2 * in.k_pad : in.k_pad;          // staged floats per row
-        const bool staged_in = (in.mode == TC_IN_ROWS && in.i0 == nullptr && (in.k_pad % 32) == 0 && in.w0 + in.w1 == in.k_pad &&
-                                ((in.ld0 | in.w0 | in.ld1 | in.w1) & 3) == 0) ||
-                               (pair && (in.k_pad % 32) == 0 && (in.ld0 & 3) == 0 && in.w0 == in.k_pad && srow <= 128);
+        const bool staged_in = pg.n_slots == 2;                  // decided by the host (TcBuilder::run): staging aliases ring slot 2
         // pair sums: the two node ids of every row of a tile, fetched one call ahead (thread t < 128: first node of
         // row t, else second node of row t - 128) and published to shared memory when the tile is staged -- a global
         // index load inside the copy loop would put an L2 round trip in front of every 16-byte copy
@@ -332,6 +342,53 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
             load_pair_idx(blockIdx.x);
             stage_input(blockIdx.x);
         }
+        // LIN0: raw feature row of this thread's row (f[7] = 1 multiplies the bias row), fetched one tile ahead
+        const bool lin0 = in.mode == TC_IN_LIN0;
+        float fcur[8], fnext[8];
+        auto load_feat = [&](int tile, float (&f)[8]) {
+            const int rg = tile * 128 + row;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = 0.f;
+            if (rg < pg.n_rows) {
+                const size_t r = in.i0 ? (size_t)__ldg(in.i0 + rg) : (size_t)rg;
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (k < in.w0) f[k] = __ldg(in.p0 + r * in.ld0 + k);
+                f[7] = 1.f;
+            }
+        };
+        // y[64] = act(W0 f + b0) for columns [128 half + 64 q, +64), then hi/lo -> the A operand
+        auto lin0_compute = [&](const float (&f)[8], int half, float2 (&y)[32]) {
+            const float* w = w0s + half * 128 + q * 64;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) y[c] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float2 fk = make_float2(f[k], f[k]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) y[c] = __ffma2_rn(*reinterpret_cast<const float2*>(w + k * 256 + 2 * c), fk, y[c]);
+            }
+            if (in.lin_act) {
+                const float2 sl = make_float2(LEAKY, LEAKY);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float2 t = __fmul2_rn(y[c], sl);
+                    y[c].x = fmaxf(y[c].x, t.x);
+                    y[c].y = fmaxf(y[c].y, t.y);
+                }
+            }
+        };
+        auto lin0_store = [&](float2 (&y)[32]) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+                float2 hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tc::split_tf32(y[c + j], hi[j], lo[j]);
+                tc::tmem_st16(t_row + in.a_hi + q * 64 + 2 * c, hi);
+                tc::tmem_st16(t_row + in.a_lo + q * 64 + 2 * c, lo);
+            }
+        };
+        if (lin0 && (int)blockIdx.x < n_tiles) load_feat(blockIdx.x, fcur);
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int row_g = tile * 128 + row;
@@ -341,7 +398,12 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 const bool split = (in.k_pad % (8 * RM_NQ)) == 0;
                 const int cw = split ? in.k_pad / RM_NQ : in.k_pad;
                 const int c0 = split ? q * cw : 0;
-                if (staged_in) {
+                if (lin0) {
+                    float2 y[32];
+                    lin0_compute(fcur, 0, y);
+                    lin0_store(y);
+                    if (tile + (int)gridDim.x < n_tiles) load_feat(tile + gridDim.x, fnext);
+                } else if (staged_in) {
                     cp_async_wait<0>();
                     group_sync(BAR_WORKERS, RM_NW);               // every thread's copies have landed
                     for (int c = c0; c < c0 + cw; c += 8) {
@@ -382,6 +444,19 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
             tick(0);
             for (int s = 0; s < pg.n_stages; ++s) {
                 const TcEpi& e = pg.st[s].epi;
+                if (e.refill) {     // second LIN0 half: computed while this stage's MMAs run, stored once they have read the first half
+                    float2 y[32];
+                    lin0_compute(fcur, 1, y);
+                    tc::mbar_wait(d_ready, dphase);
+                    dphase ^= 1u;
+                    tc::tc_fence_after();
+                    lin0_store(y);
+                    tc::tmem_wait_st();
+                    tc::tc_fence_before();
+                    bar_arrive(BAR_Y_READY, RM_NW + 32);
+                    tick(2 + 2 * s);
+                    continue;
+                }
                 tc::mbar_wait(d_ready, dphase);
                 dphase ^= 1u;
                 tc::tc_fence_after();
@@ -401,6 +476,10 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 tick(3 + 2 * s);
             }
             group_sync(BAR_WORKERS, RM_NW);     // every worker is done with this tile's TMEM columns
+            if (lin0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) fcur[k] = fnext[k];
+            }
             tick(1);
         }
         if (PROFILE && tid == 0 && prof != nullptr)

@@ -17,10 +17,10 @@ namespace rgnn {
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_MMA = 3;
 constexpr int TC_SLOT_FLOATS = 16384;     // 64 KB weight ring slot: hi + lo copies of a (K chunk x N) block, K*N <= 8192
-constexpr int TC_SLOTS = 2;
+constexpr int TC_SLOTS = 3;               // ring slots; the third one doubles as the input staging tile of programs that stage rows
 constexpr int TC_XS_COL = 496;            // 16 spare TMEM columns for the per-row statistics exchange
 
-enum TcInMode : int { TC_IN_ROWS = 0, TC_IN_PAIRSUM = 1, TC_IN_SEGMAX = 2 };
+enum TcInMode : int { TC_IN_ROWS = 0, TC_IN_PAIRSUM = 1, TC_IN_SEGMAX = 2, TC_IN_LIN0 = 3 };
 
 struct TcMma {
     int a_hi, a_lo;     // TMEM columns of the A operand (K columns each)
@@ -43,7 +43,8 @@ struct TcEpi {
     int store_ld, store_w;
     float* store;       // optional: rows written to global memory (first store_w columns)
     const float* resid; // optional residual row added to the result (identity residual of the conv block)
-    int resid_ld, pad;
+    int resid_ld;
+    int refill;         // 1: no epilogue; once the stage's MMAs are done the workers write the second LIN0 half into the A operand
 };
 
 struct TcStage {
@@ -61,10 +62,15 @@ struct TcInput {
     int ld0, w0, ld1, w1;
     const int* i0;      // ROWS: optional row index; PAIRSUM: first node; SEGMAX: segment pointer
     const int* i1;      // PAIRSUM: second node; SEGMAX: members
+    // LIN0: the A operand is act(W0 f + b0), 128 columns at a time, computed by the workers on the CUDA cores from the raw
+    // feature row f (p0, <= 7 columns, optional row index i0); W0 = p1 (256 x w0, row-major), b0 = lin_b
+    const float* lin_b;
+    int lin_act, pad;
 };
 
 struct TcProgram {
     int n_rows, n_stages;
+    int n_slots, pad;       // 2 when the input rows are staged through shared memory (the staging tile aliases slot 2), else 3
     TcInput in;
     TcStage st[TC_MAX_STAGES];
 };
