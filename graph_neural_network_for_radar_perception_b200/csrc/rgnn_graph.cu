@@ -87,10 +87,10 @@ __global__ void scan_apply_kernel(const int* __restrict__ in, int n, const int* 
     }
 }
 
-static size_t scan_ws_ints(int n) { return (size_t)(n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1; }
+size_t scan_ws_ints(int n) { return (size_t)(n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1; }
 
 // out has n+1 entries.  in and out may alias only if identical pointers are NOT used (they must differ).
-static int exclusive_scan(const int* in, int n, int* out, int* ws, cudaStream_t stream) {
+int exclusive_scan(const int* in, int n, int* out, int* ws, cudaStream_t stream) {
     if (n <= 0) {
         RGNN_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(int), stream));
         return RGNN_OK;

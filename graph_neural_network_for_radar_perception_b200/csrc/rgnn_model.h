@@ -23,6 +23,8 @@ struct DetPlan {
     float* demb;     // (E, ce) accumulated over all conv layers
     float* dh;       // (N, link_w)
     float* dg;       // (N, cls_w)
+    float* escr;     // per-edge scratch of the tensor-core backward: y1 (E,h) | dz1 (E,h) | dz2 (E,cn)
+    int* sidx;       // workspace of the source-major edge index (build_src_index)
     size_t bytes;
 };
 
@@ -42,6 +44,21 @@ size_t mp_tc_pack_floats(const ConvDims& d);      // extra floats at the end of 
 int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
 int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
                       const float* wpack, float* agg, cudaStream_t stream);
+
+// tensor-core backward of the message function (rgnn_mp_bwd_tc.cu) and the generic weight-gradient GEMM (rgnn_wgrad_tc.cu)
+bool mp_bwd_tc_supported(const ConvDims& d);
+size_t mp_bwd_tc_scratch_floats(const ConvDims& d, int n_edges);
+int run_conv_edges_bwd_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
+                          const float* dagg, float* dP, float* demb, bool first_demb, float* scratch, const int* sptr,
+                          const int* slist, cudaStream_t stream);
+// source-major index of the target-major edge list (edge positions grouped by source node), built once per backward call
+size_t src_index_ints(int n_nodes, int n_edges);
+int build_src_index(const rgnn_graph& g, int* ws, const int** sptr_out, const int** slist_out, cudaStream_t stream);
+// device-wide exclusive scan of int32 (rgnn_graph.cu)
+size_t scan_ws_ints(int n);
+int exclusive_scan(const int* in, int n, int* out, int* ws, cudaStream_t stream);
+int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, int wb, long long rows, float* dst, long long sm,
+                    long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream);
 
 // tensor-core row-MLP programs, rgnn_model_tc.cu
 bool tc_stack_supported(const rgnn_stack& s);

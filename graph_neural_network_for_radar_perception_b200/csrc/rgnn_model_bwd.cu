@@ -187,6 +187,13 @@ void plan_detector_bwd(const rgnn_detector&, const rgnn_graph& g, const TakeFn& 
     pl->demb = take((E > 0 ? E : 1) * pl->d.ce);
     pl->dh = take(N * pl->link_w);
     pl->dg = take(N * pl->cls_w);
+    // tensor-core backward of the message function: per-edge scratch (y1 | dz1 | dz2) and the source-major edge index
+    pl->escr = nullptr;
+    pl->sidx = nullptr;
+    if (mp_bwd_tc_supported(pl->d)) {
+        pl->escr = take(mp_bwd_tc_scratch_floats(pl->d, g.n_edges));
+        pl->sidx = reinterpret_cast<int*>(take(src_index_ints(g.n_nodes, g.n_edges)));
+    }
 }
 
 static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const float* node_features,
@@ -240,13 +247,20 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     if ((rc = stack_bwd(net.class_node, xL, nullptr, pl.dg, N, pl.dx, true, stream))) return rc;
 
     // ---- message-passing layers, last to first ----
+    const bool tc_edges = pl.escr != nullptr && E > 0;
+    const int* sptr = nullptr;
+    const int* slist = nullptr;
+    if (tc_edges && (rc = build_src_index(g, pl.sidx, &sptr, &slist, stream))) return rc;
     for (int l = L - 1; l >= 0; --l) {
         const bool has_next = l + 1 < L;
         if ((rc = conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], has_next ? &net.conv[l + 1] : nullptr,
                                  has_next ? pl.x[l + 1] : nullptr, has_next ? pl.dP : nullptr, pl.dx, pl.dagg, stream)))
             return rc;
-        if ((rc = conv_edges_bwd(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, stream)))
-            return rc;
+        if (tc_edges && net.conv[l].msg.n == 2)
+            rc = run_conv_edges_bwd_tc(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, pl.escr, sptr, slist, stream);
+        else
+            rc = conv_edges_bwd(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, stream);
+        if (rc) return rc;
     }
     // ---- node encoder (receives dL/dx_0 and the projection gradient of layer 0) ----
     {

@@ -46,6 +46,7 @@ struct MpTcArgs {
 extern int g_rowmlp_profile;
 static int g_tf32_passes = 3;
 static int g_use_tensor_cores = 1;
+static int g_use_tensor_cores_bwd = 1;
 static int g_debug = 0;
 
 template <int CE, int H, int CN, int NQ>
@@ -444,14 +445,14 @@ teardown:
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W[n][koff + k] (row stride ldW) -> hi/lo chunk-major operands [K/4][N][4]
+// weight packing: element (n, k) = W[off + n * sn + k * sk] -> hi/lo chunk-major operands [K/4][N][4]
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_split_kernel(const float* __restrict__ W, int ldW, int koff, int K, int N, float* __restrict__ hi,
+__global__ void pack_split_kernel(const float* __restrict__ W, int off, int sn, int sk, int K, int N, float* __restrict__ hi,
                                   float* __restrict__ lo) {
     const int tot = K * N;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
         const int q = i & 3, n = (i >> 2) % N, kc = (i >> 2) / N;
-        const float w = W[(size_t)n * ldW + koff + 4 * kc + q];
+        const float w = W[(size_t)off + (size_t)n * sn + (size_t)(4 * kc + q) * sk];
         float h, l;
         tc::split_tf32(w, h, l);
         hi[i] = h;
@@ -464,8 +465,9 @@ int g_use_tensor_cores_flag() { return g_use_tensor_cores; }
 bool mp_tc_supported(const ConvDims& d) { return g_use_tensor_cores && d.cn == 64 && d.ce == 64 && d.h == 128; }
 
 size_t mp_tc_pack_floats(const ConvDims& d) {
-    // the buffer exists whenever the shape is one the tensor-core kernel is instantiated for
-    return (d.cn == 64 && d.ce == 64 && d.h == 128) ? (size_t)2 * d.ce * d.h + (size_t)2 * d.h * d.cn : 0;
+    // the buffer exists whenever the shape is one the tensor-core kernels are instantiated for: the two forward images
+    // (W_e, W_2) followed by their transposes for the backward (W_2^T, W_e^T), each hi | lo
+    return (d.cn == 64 && d.ce == 64 && d.h == 128) ? 2 * ((size_t)2 * d.ce * d.h + (size_t)2 * d.h * d.cn) : 0;
 }
 
 int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream) {
@@ -473,8 +475,14 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
     const rgnn_linear& m0 = c.msg.layer[0];
     const rgnn_linear& m1 = c.msg.layer[1];
     const int W1 = d.ce * d.h, W2 = d.h * d.cn;
-    pack_split_kernel<<<16, 256, 0, stream>>>(m0.weight, m0.in_features, 2 * d.cn, d.ce, d.h, dst, dst + W1);
-    pack_split_kernel<<<16, 256, 0, stream>>>(m1.weight, m1.in_features, 0, d.h, d.cn, dst + 2 * W1, dst + 2 * W1 + W2);
+    float* w1 = dst;                 // (n = h, k = c)  = msg.0.weight[h][2cn + c]
+    float* w2 = w1 + 2 * W1;         // (n = i, k = h)  = msg.1.weight[i][h]
+    float* w2t = w2 + 2 * W2;        // (n = h, k = i)  = msg.1.weight[i][h]         (d y1 = dz2 W_2)
+    float* w1t = w2t + 2 * W2;       // (n = c, k = h)  = msg.0.weight[h][2cn + c]   (d emb = dz1 W_e)
+    pack_split_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, m0.in_features, 1, d.ce, d.h, w1, w1 + W1);
+    pack_split_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, m1.in_features, 1, d.h, d.cn, w2, w2 + W2);
+    pack_split_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, 1, m1.in_features, d.cn, d.h, w2t, w2t + W2);
+    pack_split_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, 1, m0.in_features, d.h, d.ce, w1t, w1t + W1);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
@@ -536,6 +544,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     using namespace rgnn;
     if (name != nullptr && strcmp(name, "tf32_passes") == 0 && (value == 1 || value == 3)) { g_tf32_passes = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores = value; return RGNN_OK; }
+    if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores_bwd = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; g_rowmlp_profile = (value & 8) != 0; return RGNN_OK; }
     set_error("rgnn_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
     return RGNN_ERR_INVALID;
@@ -545,5 +554,6 @@ extern "C" int rgnn_get_option(const char* name) {
     using namespace rgnn;
     if (name != nullptr && strcmp(name, "tf32_passes") == 0) return g_tf32_passes;
     if (name != nullptr && strcmp(name, "tensor_cores") == 0) return g_use_tensor_cores;
+    if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0) return g_use_tensor_cores_bwd;
     return -1;
 }

@@ -40,6 +40,7 @@ const char* rgnn_last_error(void);
  *   "tf32_passes"  3 (default) = 3xTF32 split-operand tensor-core products, fp32-equivalent (parity mode);
  *                  1           = single TF32 pass (faster, ~1e-3 relative error per layer; never the default)
  *   "tensor_cores" 1 (default) = tcgen05 kernels where the channel plan allows; 0 = FFMA tile programs only.
+ *   "tensor_cores_bwd" 1 (default) = tcgen05 backward of the message function; 0 = FFMA backward tile programs.
  * rgnn_get_option returns -1 for an unknown name. */
 int rgnn_set_option(const char* name, int value);
 int rgnn_get_option(const char* name);
@@ -207,6 +208,15 @@ int rgnn_detector_bwd(const rgnn_detector* net, const rgnn_graph* g, const float
                       const float* edge_features, const float* grad_node_cls, const float* grad_node_off,
                       const float* grad_link_cls, const float* grad_obj_cls,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weight gradient of one nn.Linear on the tensor cores (what autograd's addmm backward computes, common.py:185-205):
+ * dst (wa x wb, row-major) += A^T B with A (rows x wa, leading dimension lda, wa <= 128) and B (rows x wb, ldb,
+ * wb <= 256) row-major in device memory; colsum_a (wa) += column sums of A, colsum_b (wb) += column sums of B (bias
+ * gradients); either may be NULL.  3xTF32 split products, fp32 accumulation (option "tf32_passes").
+ * rgnn_detector_bwd uses it for the message-function weights; option "tensor_cores_bwd" = 0 selects the FFMA
+ * tile programs for the whole backward instead. */
+int rgnn_wgrad(const float* A, int lda, int wa, const float* B, int ldb, int wb, long long rows, float* dst,
+               float* colsum_a, float* colsum_b, void* stream);
 
 /* Loss_Graph.forward + its gradient w.r.t. the logits, and compute_accuracy (gnn_detector.py:23-28).
  * counts_* are the GLOBAL batch sizes each sum is divided by (loss.py:58,62,66,70) -- under data parallelism
