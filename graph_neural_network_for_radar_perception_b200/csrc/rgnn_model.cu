@@ -267,6 +267,10 @@ int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, v
     pl->emb = take(E * d.ce);
     pl->hlink = take(N * pl->link_w);
     pl->gcls = take(N * pl->cls_w);
+    pl->enc_tc_bwd = pl->link_tc_bwd = false;
+    memset(&pl->enc_save, 0, sizeof(TcSave));
+    memset(&pl->link_save, 0, sizeof(TcSave));
+    pl->cscr = nullptr;
     if (training) plan_detector_bwd(net, g, take, pl);
     pl->bytes = off;
     return RGNN_OK;
@@ -291,7 +295,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if ((rc = launch_program(b.p, stream))) return rc;
     }
     if (E > 0 && tc_stack_supported(net.edge_enc)) {
-        if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream))) return rc;
+        if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream, pl.enc_tc_bwd ? &pl.enc_save : nullptr))) return rc;
     } else if (E > 0) {   // edge encoder, rows gathered into target-major order
         FwdBuilder b(E);
         const int in = stack_in(net.edge_enc);
@@ -312,7 +316,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream))) return rc;
     if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream))) return rc;
     if (g.n_und > 0 && tc_stack_supported(net.head_link)) {
-        if ((rc = tc_run_pairsum_stack(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream))) return rc;
+        if ((rc = tc_run_pairsum_stack(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream,
+                                       pl.link_tc_bwd ? &pl.link_save : nullptr)))
+            return rc;
     } else if (g.n_und > 0) {
         FwdBuilder b(g.n_und);
         Step* s = b.add(OP_LOAD_PAIRSUM, b.cur);

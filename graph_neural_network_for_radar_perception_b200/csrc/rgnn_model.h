@@ -6,6 +6,14 @@
 
 namespace rgnn {
 
+// what the forward of a training step leaves behind for tc_stack_bwd: layer outputs (post-activation), norm sigmas, the
+// assembled input rows (pair sums); nullptr entries are not saved
+struct TcSave {
+    float* x_in;
+    float* y[RGNN_MAX_STACK];
+    float* sd[RGNN_MAX_STACK];
+};
+
 // Where everything lives inside the caller-provided detector workspace.
 struct DetPlan {
     ConvDims d;
@@ -25,6 +33,10 @@ struct DetPlan {
     float* dg;       // (N, cls_w)
     float* escr;     // per-edge scratch of the tensor-core backward: y1 (E,h) | dz1 (E,h) | dz2 (E,cn)
     int* sidx;       // workspace of the source-major edge index (build_src_index)
+    // training with the tensor-core chain backward: saved layer outputs / sigmas of the edge encoder and the link head
+    bool enc_tc_bwd, link_tc_bwd;
+    TcSave enc_save, link_save;
+    float* cscr;     // scratch of tc_stack_bwd (dz per layer), shared by the two chains
     size_t bytes;
 };
 
@@ -58,7 +70,7 @@ int build_src_index(const rgnn_graph& g, int* ws, const int** sptr_out, const in
 size_t scan_ws_ints(int n);
 int exclusive_scan(const int* in, int n, int* out, int* ws, cudaStream_t stream);
 int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, int wb, long long rows, float* dst, long long sm,
-                    long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream);
+                    long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream, const int* b_ridx = nullptr);
 
 // tensor-core row-MLP programs, rgnn_model_tc.cu
 bool tc_stack_supported(const rgnn_stack& s);
@@ -66,13 +78,20 @@ bool tc_proj_supported(const ConvDims& d);
 size_t tc_proj_pack_floats(const ConvDims& d);
 int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream);
 int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t stream);
-int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream);
+int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream,
+                 const TcSave* save = nullptr);
+bool tc_stack_bwd_supported(const rgnn_stack& s);
+size_t tc_stack_bwd_scratch_floats(const rgnn_stack& s, int n_rows);
+// dx_mode: 0 = overwrite, 1 = accumulate, 2 = atomic pair scatter onto rows ia[], ib[] of dx (dx may be nullptr: not wanted)
+int tc_stack_bwd(const rgnn_stack& s, const TcSave& save, const float* x_rows, const int* x_ridx, const float* y_out,
+                 const float* g_top, int n_rows, float* scratch, float* dx, int dx_mode, const int* ia, const int* ib,
+                 cudaStream_t stream);
 int tc_run_node_encoder(const rgnn_stack& enc, const rgnn_conv& first, const ConvDims& d, const float* node_features, int n_nodes,
                         float* x0, float* P0, cudaStream_t stream);
 int tc_run_conv_nodes(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
                       const rgnn_conv* next, float* P_next, cudaStream_t stream);
 int tc_run_pairsum_stack(const rgnn_stack& s, const float* h, int ld, const int* ia, const int* ib, int n_rows, float* y,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const TcSave* save = nullptr);
 int tc_run_segmax_stack(const rgnn_stack& s, const float* g, int ld, const int* ptr, const int* members, int n_rows, float* y,
                         cudaStream_t stream);
 size_t tc_linear_pack_floats(int in_features, int out_features);

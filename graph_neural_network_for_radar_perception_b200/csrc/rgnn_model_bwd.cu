@@ -179,7 +179,7 @@ static int conv_edges_bwd(const rgnn_conv& c, const ConvDims& d, const rgnn_grap
     return launch_program(b.p, stream);
 }
 
-void plan_detector_bwd(const rgnn_detector&, const rgnn_graph& g, const TakeFn& take, DetPlan* pl) {
+void plan_detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const TakeFn& take, DetPlan* pl) {
     const size_t N = (size_t)g.n_nodes, E = (size_t)g.n_edges;
     pl->dx = take(N * pl->d.cn);
     pl->dP = take(N * 2 * pl->d.h);
@@ -194,6 +194,23 @@ void plan_detector_bwd(const rgnn_detector&, const rgnn_graph& g, const TakeFn& 
         pl->escr = take(mp_bwd_tc_scratch_floats(pl->d, g.n_edges));
         pl->sidx = reinterpret_cast<int*>(take(src_index_ints(g.n_nodes, g.n_edges)));
     }
+    // tensor-core chain backward of the edge encoder and the link head: the forward saves layer outputs and sigmas
+    size_t cscr = 0;
+    auto plan_save = [&](const rgnn_stack& s, size_t rows, bool want_x_in, TcSave* sv) {
+        if (want_x_in) sv->x_in = take(rows * round_up(stack_in(s), 8));
+        for (int i = 0; i < s.n; ++i) {
+            const rgnn_linear& L = s.layer[i];
+            if (i + 1 < s.n && !(i == 0 && L.in_features <= 8)) sv->y[i] = take(rows * L.out_features);
+            if (L.norm_scale != nullptr) sv->sd[i] = take(rows);
+        }
+        const size_t need = tc_stack_bwd_scratch_floats(s, (int)rows);
+        cscr = cscr > need ? cscr : need;
+    };
+    pl->enc_tc_bwd = E > 0 && tc_stack_bwd_supported(net.edge_enc);
+    if (pl->enc_tc_bwd) plan_save(net.edge_enc, E, false, &pl->enc_save);
+    pl->link_tc_bwd = g.n_und > 0 && tc_stack_bwd_supported(net.head_link);
+    if (pl->link_tc_bwd) plan_save(net.head_link, (size_t)g.n_und, true, &pl->link_save);
+    if (cscr > 0) pl->cscr = take(cscr);
 }
 
 static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const float* node_features,
@@ -207,7 +224,11 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     if ((rc = stack_bwd(net.head_node, xL, nullptr, g_node_cls, N, pl.dx, false, stream))) return rc;
     if ((rc = stack_bwd(net.head_offset, xL, nullptr, g_node_off, N, pl.dx, true, stream))) return rc;
     RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dh, 0, (size_t)N * pl.link_w * sizeof(float), stream));
-    if (g.n_und > 0) {
+    if (g.n_und > 0 && pl.link_tc_bwd) {
+        if ((rc = tc_stack_bwd(net.head_link, pl.link_save, nullptr, nullptr, nullptr, g_link, g.n_und, pl.cscr, pl.dh, 2, g.und_a,
+                               g.und_b, stream)))
+            return rc;
+    } else if (g.n_und > 0) {
         int lw = pl.link_w;
         for (int i = 0; i < net.head_link.n; ++i) lw = lw > net.head_link.layer[i].out_features ? lw : net.head_link.layer[i].out_features;
         lw = round_up(lw, 64);
@@ -280,7 +301,11 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
         if ((rc = launch_program(b.p, stream))) return rc;
     }
     // ---- edge encoder ----
-    if (E > 0) {
+    if (E > 0 && pl.enc_tc_bwd) {
+        if ((rc = tc_stack_bwd(net.edge_enc, pl.enc_save, edge_features, g.perm, pl.emb, pl.demb, E, pl.cscr, nullptr, 0, nullptr,
+                               nullptr, stream)))
+            return rc;
+    } else if (E > 0) {
         if ((rc = stack_bwd(net.edge_enc, edge_features, g.perm, pl.demb, E, nullptr, false, stream))) return rc;
     }
     return RGNN_OK;

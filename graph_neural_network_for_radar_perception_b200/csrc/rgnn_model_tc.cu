@@ -17,6 +17,28 @@ static const float* tc_weights(const rgnn_linear& L) {
     return L.weight_t + (size_t)round_up(L.in_features, 8) * round_up(L.out_features, 64);
 }
 
+// Transposed images for the backward (d input = dz W): the layer W^T has K' = out_features and N' = in_features; inputs
+// wider than 128 are packed as independent blocks of 128 output columns (each its own chunk stream).
+static bool tc_has_transposed(int in_features, int out_features) {
+    return in_features >= 16 && in_features % 8 == 0 && in_features <= 256 && out_features <= 256 && tc_kp(out_features) <= 128;
+}
+static int tc_t_blocks(int in_features) { return (in_features + 127) / 128; }
+static int tc_t_block_cols(int in_features, int blk) { return in_features - 128 * blk < 128 ? in_features - 128 * blk : 128; }
+static size_t tc_t_block_floats(int in_features, int out_features, int blk) {
+    return tc_pack_floats(out_features, tc_t_block_cols(in_features, blk));
+}
+static size_t tc_t_pack_floats(int in_features, int out_features) {
+    if (!tc_has_transposed(in_features, out_features)) return 0;
+    size_t n = 0;
+    for (int b = 0; b < tc_t_blocks(in_features); ++b) n += tc_t_block_floats(in_features, out_features, b);
+    return n;
+}
+static const float* tc_weights_t(const rgnn_linear& L, int blk) {
+    const float* p = tc_weights(L) + tc_pack_floats(L.in_features, L.out_features);
+    for (int b = 0; b < blk; ++b) p += tc_t_block_floats(L.in_features, L.out_features, b);
+    return p;
+}
+
 struct TcBuilder {
     TcProgram p;
     bool ok = true;
@@ -197,7 +219,18 @@ bool tc_stack_supported(const rgnn_stack& s) {
     return s.n + 2 <= TC_MAX_STAGES && stack_layers_ok(s, 0);
 }
 
-static void add_stack(TcBuilder& b, const rgnn_stack& s, bool feed_last) {
+static void set_store(TcEpi& e, float* dst, int ld, int w) {
+    e.store = dst; e.store_ld = ld; e.store_w = w;
+}
+
+// training step: what the forward leaves behind for the tensor-core backward (tc_stack_bwd)
+static void apply_save(TcEpi& e, const rgnn_linear& L, const TcSave* save, int i, bool is_last) {
+    if (save == nullptr) return;
+    if (L.norm_scale != nullptr) e.sd_store = save->sd[i];
+    if (!is_last && save->y[i] != nullptr) set_store(e, save->y[i], L.out_features, L.out_features);
+}
+
+static void add_stack(TcBuilder& b, const rgnn_stack& s, bool feed_last, const TcSave* save = nullptr) {
     int first = 0;
     if (s.layer[0].in_features <= 8 && s.layer[0].out_features == 256 && s.n >= 2) {
         if (s.layer[0].in_features <= 7) {
@@ -207,13 +240,14 @@ static void add_stack(TcBuilder& b, const rgnn_stack& s, bool feed_last) {
             b.p.in.a_lo = R_IN + 8;
             b.encoder_head(s.layer[0], s.layer[1]);
         }
+        apply_save(b.last_epi(), s.layer[1], save, 1, s.n == 2);
         first = 2;
     }
-    for (int i = first; i < s.n; ++i) b.layer(s.layer[i], feed_last || i + 1 < s.n);
-}
-
-static void set_store(TcEpi& e, float* dst, int ld, int w) {
-    e.store = dst; e.store_ld = ld; e.store_w = w;
+    for (int i = first; i < s.n; ++i) {
+        TcEpi* e = b.layer(s.layer[i], feed_last || i + 1 < s.n);
+        apply_save(*e, s.layer[i], save, i, i + 1 == s.n);
+    }
+    if (save != nullptr && save->x_in != nullptr) b.p.in.in_store = save->x_in;
 }
 
 // hoisted node part of the next conv block's msg.0: P = [x W_t^T + b | x W_s^T], two 128-column stages
@@ -231,14 +265,22 @@ bool tc_proj_supported(const ConvDims& d) { return g_use_tensor_cores_flag() && 
 size_t tc_proj_pack_floats(const ConvDims& d) { return (d.cn == 64 && d.h == 128) ? tc_pack_floats(d.cn, 2 * d.h) : 0; }
 
 size_t tc_linear_pack_floats(int in_features, int out_features) {
-    return (in_features > 256 || out_features > 256) ? 0 : tc_pack_floats(in_features, out_features);
+    return (in_features > 256 || out_features > 256) ? 0 : tc_pack_floats(in_features, out_features) + tc_t_pack_floats(in_features, out_features);
 }
 
 int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream) {
     if (L.in_features > 256 || L.out_features > 256) return RGNN_OK;
     const int Kp = tc_kp(L.in_features), Np = tc_np(L.out_features);
     float* dst = const_cast<float*>(tc_weights(L));
-    return pack_tc(L.weight, L.in_features, 0, L.out_features, 0, Np, 0, L.in_features, Kp, tc_chunk_k(Kp, Np), true, dst, stream);
+    int rc = pack_tc(L.weight, L.in_features, 0, L.out_features, 0, Np, 0, L.in_features, Kp, tc_chunk_k(Kp, Np), true, dst, stream);
+    if (rc || !tc_has_transposed(L.in_features, L.out_features)) return rc;
+    for (int b = 0; b < tc_t_blocks(L.in_features); ++b) {     // W^T: rows (n) = input channels of block b, columns (k) = output channels
+        const int Nt = tc_t_block_cols(L.in_features, b), Npt = tc_np(Nt), Kpt = tc_kp(L.out_features);
+        rc = pack_tc(L.weight, L.in_features, 128 * b, Nt, 0, Npt, 0, L.out_features, Kpt, tc_chunk_k(Kpt, Npt), true,
+                     const_cast<float*>(tc_weights_t(L, b)), stream, true);
+        if (rc) return rc;
+    }
+    return RGNN_OK;
 }
 
 int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t stream) {
@@ -253,10 +295,10 @@ int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t strea
 
 // ---- the programs of the detector forward ----------------------------------------------------------------
 
-int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream) {
+int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream, const TcSave* save) {
     TcBuilder b(n_rows);
     b.input(TC_IN_ROWS, x, stack_in(s), stack_in(s), nullptr, 0, 0, ridx, nullptr);
-    add_stack(b, s, false);
+    add_stack(b, s, false, save);
     set_store(b.last_epi(), y, stack_out(s), stack_out(s));
     return b.run(stream);
 }
@@ -285,10 +327,10 @@ int tc_run_conv_nodes(const rgnn_conv& c, const ConvDims& d, int n_nodes, const 
 }
 
 int tc_run_pairsum_stack(const rgnn_stack& s, const float* h, int ld, const int* ia, const int* ib, int n_rows, float* y,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const TcSave* save) {
     TcBuilder b(n_rows);
     b.input(TC_IN_PAIRSUM, h, ld, stack_in(s), nullptr, 0, 0, ia, ib);
-    add_stack(b, s, false);
+    add_stack(b, s, false, save);
     set_store(b.last_epi(), y, stack_out(s), stack_out(s));
     return b.run(stream);
 }
@@ -300,6 +342,126 @@ int tc_run_segmax_stack(const rgnn_stack& s, const float* g, int ld, const int* 
     add_stack(b, s, false);
     set_store(b.last_epi(), y, stack_out(s), stack_out(s));
     return b.run(stream);
+}
+
+// ---- backward of a row-MLP chain on the tensor cores ------------------------------------------------------------
+// The forward of the training step saved every layer's output rows and norm sigmas (TcSave), so the backward is the
+// dgrad chain alone: dz_l = norm'(act'(g_l)) in the epilogue / input transform, g_{l-1} = dz_l W_l on the tensor cores
+// (transposed weight images), every dz_l written to a scratch buffer; the weight gradients dW_l = dz_l^T x_l and the
+// bias gradients are contracted afterwards by rgnn_wgrad_tc.cu.  Shapes covered: every layer <= 128 wide, optionally
+// behind the encoder head (<= 7 -> 256 no norm, 256 -> 128), whose activation mask is recomputed from the raw features.
+
+static bool lin0_head(const rgnn_stack& s) {
+    return s.n >= 2 && s.layer[0].in_features <= 7 && s.layer[0].out_features == 256 && s.layer[0].norm_scale == nullptr &&
+           s.layer[1].in_features == 256 && s.layer[1].out_features == 128;
+}
+
+bool tc_stack_bwd_supported(const rgnn_stack& s) {
+    if (!tc_stack_supported(s) || rgnn_get_option("tensor_cores_bwd") == 0) return false;
+    const int first = lin0_head(s) ? 1 : 0;
+    if (!lin0_head(s) && s.layer[0].in_features <= 8) return false;
+    for (int i = first; i < s.n; ++i) {
+        const rgnn_linear& L = s.layer[i];
+        if (!tc_has_transposed(L.in_features, L.out_features)) return false;
+        if (i > first || !lin0_head(s)) {
+            if (L.in_features != 32 && L.in_features != 64 && L.in_features != 128) return false;
+        }
+        const bool has_fn = L.norm_scale != nullptr || L.activation;
+        if (has_fn && L.out_features != 32 && L.out_features != 64 && L.out_features != 128) return false;
+        if (has_fn && L.norm_scale == nullptr) return false;          // act without norm only in the encoder head
+    }
+    return s.n - first + 3 <= TC_MAX_STAGES;
+}
+
+// scratch: dz_l (rows x out_l) for every layer, plus the recomputed first activation a0 (rows x 256) behind an encoder head
+size_t tc_stack_bwd_scratch_floats(const rgnn_stack& s, int n_rows) {
+    size_t per_row = 0;
+    for (int i = 0; i < s.n; ++i) per_row += round_up(s.layer[i].out_features, 8);
+    if (lin0_head(s)) per_row += 256;
+    return (size_t)(n_rows > 0 ? n_rows : 1) * per_row;
+}
+
+int tc_stack_bwd(const rgnn_stack& s, const TcSave& save, const float* x_rows, const int* x_ridx, const float* y_out,
+                 const float* g_top, int n_rows, float* scratch, float* dx, int dx_mode, const int* ia, const int* ib,
+                 cudaStream_t stream) {
+    if (n_rows <= 0) return RGNN_OK;
+    const bool head = lin0_head(s);
+    const int n = s.n, first = head ? 1 : 0;
+    // scratch layout
+    float* dz[RGNN_MAX_STACK];
+    float* p = scratch;
+    for (int i = 0; i < n; ++i) { dz[i] = p; p += (size_t)n_rows * round_up(s.layer[i].out_features, 8); }
+    float* a0 = head ? p : nullptr;
+    auto fill_bwd = [&](TcBwd& b, int i, const float* y, int y_ld) {
+        const rgnn_linear& L = s.layer[i];
+        memset(&b, 0, sizeof(b));
+        b.y = y; b.y_ld = y_ld; b.sd = L.norm_scale ? save.sd[i] : nullptr;
+        b.scale = L.norm_scale; b.shift = L.norm_shift; b.g_scale = L.grad_norm_scale; b.g_shift = L.grad_norm_shift;
+        b.act = L.activation;
+    };
+    TcBuilder b(n_rows);
+    const rgnn_linear& Lt = s.layer[n - 1];
+    const float* dz_top;
+    if (Lt.norm_scale != nullptr || Lt.activation) {
+        b.input(TC_IN_BWD, g_top, Lt.out_features, Lt.out_features, nullptr, 0, 0, nullptr, nullptr);
+        fill_bwd(b.p.in.bwd, n - 1, y_out, Lt.out_features);
+        b.p.in.bwd_store = dz[n - 1];
+        dz_top = dz[n - 1];
+    } else {
+        b.input(TC_IN_ROWS, g_top, Lt.out_features, Lt.out_features, nullptr, 0, 0, nullptr, nullptr);
+        dz_top = g_top;
+    }
+    int dz_top_ld = (Lt.norm_scale != nullptr || Lt.activation) ? b.p.in.k_pad : Lt.out_features;
+    for (int l = n - 1; l >= first; --l) {
+        const rgnn_linear& L = s.layer[l];
+        if (l == 1 && head) {
+            // d a0 = dz_1 W_1 (256 wide, two blocks of 128 columns sharing the A operand); dz_0 = act'(d a0) with the mask of
+            // a0 = act(W_0 f + b_0) recomputed from the raw features; a0 itself is the operand of dW_1
+            for (int half = 0; half < 2; ++half) {
+                TcEpi* e = b.layer(tc_weights_t(L, half), L.out_features, 128, nullptr, nullptr, nullptr, 0, false);
+                e->is_bwd = 1;
+                memset(&e->bwd, 0, sizeof(e->bwd));
+                e->bwd.lin0 = 1; e->bwd.lin0_off = 128 * half; e->bwd.act = s.layer[0].activation;
+                e->bwd.y_store = a0; e->bwd.y_ld = 256;
+                set_store(*e, dz[0] + 128 * half, 256, 128);
+            }
+            b.p.lin0.f = x_rows; b.p.lin0.ridx = x_ridx; b.p.lin0.W = s.layer[0].weight; b.p.lin0.b = s.layer[0].bias;
+            b.p.lin0.ld = s.layer[0].in_features; b.p.lin0.w = s.layer[0].in_features; b.p.lin0.act = s.layer[0].activation;
+        } else if (l > 0) {
+            const rgnn_linear& Lp = s.layer[l - 1];
+            TcEpi* e = b.layer(tc_weights_t(L, 0), L.out_features, L.in_features, nullptr, nullptr, nullptr, 0, true);
+            e->is_bwd = 1;
+            fill_bwd(e->bwd, l - 1, save.y[l - 1], Lp.out_features);
+            set_store(*e, dz[l - 1], round_up(Lp.out_features, 8), Lp.out_features);
+        } else if (dx != nullptr) {
+            TcEpi* e = b.layer(tc_weights_t(L, 0), L.out_features, L.in_features, nullptr, nullptr, nullptr, 0, false);
+            set_store(*e, dx, L.in_features, L.in_features);
+            e->store_mode = dx_mode; e->ia = ia; e->ib = ib;
+        }
+    }
+    int rc = b.run(stream);
+    if (rc) return rc;
+    // weight and bias gradients: dW_l (out x in) += dz_l^T x_l, db_l += column sums of dz_l
+    for (int l = n - 1; l >= 0; --l) {
+        const rgnn_linear& L = s.layer[l];
+        const float* dzl = l == n - 1 ? dz_top : dz[l];
+        const int dz_ld = l == n - 1 ? dz_top_ld : round_up(L.out_features, 8);
+        const float* xl;
+        int x_ld;
+        const int* xidx = nullptr;
+        if (l == 0) { xl = head ? x_rows : save.x_in; x_ld = head ? L.in_features : round_up(L.in_features, 8); xidx = head ? x_ridx : nullptr; }
+        else if (l == 1 && head) { xl = a0; x_ld = 256; }
+        else { xl = save.y[l - 1]; x_ld = s.layer[l - 1].out_features; }
+        if (L.grad_weight == nullptr && L.grad_bias == nullptr) continue;
+        for (int m0 = 0; m0 < L.out_features; m0 += 128) {
+            const int wa = L.out_features - m0 < 128 ? L.out_features - m0 : 128;
+            rc = launch_wgrad_tc(dzl + m0, dz_ld, wa, xl, x_ld, L.in_features, n_rows,
+                                 L.grad_weight ? L.grad_weight + (size_t)m0 * L.in_features : nullptr, L.in_features, 1,
+                                 L.grad_bias ? L.grad_bias + m0 : nullptr, nullptr, stream, xidx);
+            if (rc) return rc;
+        }
+    }
+    return RGNN_OK;
 }
 
 }  // namespace rgnn

@@ -53,30 +53,7 @@ __device__ __forceinline__ void bulk_g2s_b(void* smem_dst, const void* gsrc, uin
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
-}
 }  // namespace tc
-
-__device__ __forceinline__ void stg256(float* p, float2 a, float2 b, float2 c, float2 d) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y)
-                 : "memory");
-}
-
-// two sums per row over the 2 threads that share it (same lane, warps w and w + 4), exchanged through 4 spare TMEM columns
-__device__ __forceinline__ void row_allreduce2(float& u, float& v, uint32_t t_cols, int q, int bar_id) {
-    tc::tmem_st2(t_cols + 2 * q, u, v);
-    tc::tmem_wait_st();
-    tc::tc_fence_before();
-    group_sync(bar_id, 64);
-    tc::tc_fence_after();
-    float p0, p1, p2, p3;
-    tc::tmem_ld4(t_cols, p0, p1, p2, p3);
-    tc::tmem_wait_ld();
-    u = p0 + p2;
-    v = p1 + p3;
-}
 
 constexpr int MB_TM = 128, MB_CE = 64, MB_H = 128, MB_CN = 64;
 constexpr int MB_NW = 256;                       // worker threads: (row, half of the columns)

@@ -6,6 +6,8 @@
 // Synchronisation: mbarriers full[slot] (bulk copy landed) / empty[slot] (tcgen05.commit: the MMAs that read the slot
 // are done) / d_ready (tcgen05.commit: a stage's accumulator is complete), and a named barrier on which the workers
 // arrive when the next A operand is in TMEM.
+#include <type_traits>
+
 #include "rgnn_rowmlp_tc.cuh"
 #include "rgnn_tc_rows.cuh"
 #include "rgnn_tile.cuh"
@@ -22,7 +24,10 @@ constexpr int RM_OFF_CST = TC_SLOTS * TC_SLOT_FLOATS;
 static_assert(RM_STG_FLOATS <= TC_SLOT_FLOATS, "input staging must fit in one ring slot");
 constexpr int RM_OFF_W0 = RM_OFF_CST + TC_MAX_STAGES * RM_CST_LD;   // LIN0: [8][256] = W0^T rows 0..6, bias in row 7
 constexpr int RM_OFF_BAR = RM_OFF_W0 + 8 * 256;
-constexpr size_t RM_SMEM = (size_t)(RM_OFF_BAR + 16 + 256) * 4;   // barriers, TMEM slot, 256 pair-sum node ids
+constexpr int RM_OFF_DACC = RM_OFF_BAR + 16 + 256;                // barriers, TMEM slot, 256 pair-sum node ids
+constexpr int RM_DACC_N = 2 * (TC_MAX_STAGES + 1);                // doubles: (d scale, d shift) per stage, last pair = input transform
+constexpr size_t RM_SMEM = (size_t)(RM_OFF_DACC + 2 * RM_DACC_N) * 4;
+static_assert((RM_OFF_DACC % 2) == 0, "double alignment");
 static_assert(RM_SMEM <= 227 * 1024 && (RM_OFF_BAR % 2) == 0, "shared memory budget / mbarrier alignment");
 
 namespace tc {
@@ -99,7 +104,22 @@ __device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, 
 #pragma unroll
         for (int c = 0; c < CP; ++c) z[c] = __fadd2_rn(z[c], res[c]);
     }
-    if (e.store != nullptr && valid) {
+    if (e.store != nullptr && valid && e.store_mode == 2) {      // d(pair sum): both end points receive the row
+        float* oa = e.store + (size_t)__ldg(e.ia + row_g) * e.store_ld + col0;
+        float* ob = e.store + (size_t)__ldg(e.ib + row_g) * e.store_ld + col0;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (col0 + 2 * c < e.store_w) { atomicAdd(oa + 2 * c, z[c].x); atomicAdd(ob + 2 * c, z[c].x); }
+            if (col0 + 2 * c + 1 < e.store_w) { atomicAdd(oa + 2 * c + 1, z[c].y); atomicAdd(ob + 2 * c + 1, z[c].y); }
+        }
+    } else if (e.store != nullptr && valid && e.store_mode == 1) {
+        float* o = e.store + (size_t)row_g * e.store_ld + col0;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (col0 + 2 * c < e.store_w) o[2 * c] += z[c].x;
+            if (col0 + 2 * c + 1 < e.store_w) o[2 * c + 1] += z[c].y;
+        }
+    } else if (e.store != nullptr && valid) {
         float* o = e.store + (size_t)row_g * e.store_ld + col0;
         if (((e.store_ld | e.store_w) & 3) == 0) {
 #pragma unroll
@@ -149,8 +169,105 @@ __device__ __forceinline__ void epilogue_norm(const TcEpi& e, int row_g, bool va
     for (int c = 0; c < CPT / 2; ++c)
         res[c] = (has_res && valid) ? __ldg(reinterpret_cast<const float2*>(e.resid + (size_t)row_g * e.resid_ld + col0) + c) : make_float2(0.f, 0.f);
     load_acc_bias<CPT / 2>(z, e, col0, t_row, cb);
-    row_norm_act<CPT / 2, RM_NQ>(z, e.n_true, true, cb[256], cb[257], e.act != 0, t_row + TC_XS_COL, q, bar_id);
+    float sd = 0.f;
+    row_norm_act<CPT / 2, RM_NQ>(z, e.n_true, true, cb[256], cb[257], e.act != 0, t_row + TC_XS_COL, q, bar_id, &sd);
+    if (e.sd_store != nullptr && valid && q == 0) e.sd_store[row_g] = sd;
     finish_columns<CPT / 2>(z, e, row_g, valid, col0, t_row, res, has_res);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of norm + activation on a gradient row (TcBwd): g (CPT columns of this thread, in registers) -> dz in place.
+// y: the layer's forward output for the same columns.  Scalar-gradient partials are returned for the caller to pool.
+// ---------------------------------------------------------------------------------------------
+template <int CPT>
+__device__ __forceinline__ void bwd_transform(float2 (&g)[CPT / 2], const float2 (&y)[CPT / 2], const TcBwd& b, int n_true, bool has_y,
+                                              float scale, float shift, float sd, uint32_t t_xs, int q, int bar_id, float& ps,
+                                              float& pm) {
+    const bool norm = b.scale != nullptr, act = b.act != 0;
+    ps = 0.f; pm = 0.f;
+    if (!has_y) return;                    // plain Linear: dz = g
+    if (!norm) {
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < CPT / 2; ++c) {
+                if (!(y[c].x > 0.f)) g[c].x *= LEAKY;
+                if (!(y[c].y > 0.f)) g[c].y *= LEAKY;
+            }
+        }
+        return;
+    }
+    const float inv_scale = scale != 0.f ? 1.f / scale : 0.f;
+    float sum_dn = 0.f, dot = 0.f;
+    float2 nv[CPT / 2];
+#pragma unroll
+    for (int c = 0; c < CPT / 2; ++c) {
+        const bool px = !act || y[c].x > 0.f, py = !act || y[c].y > 0.f;
+        if (!px) g[c].x *= LEAKY;
+        if (!py) g[c].y *= LEAKY;
+        nv[c].x = ((px ? y[c].x : y[c].x / LEAKY) - shift) * inv_scale;
+        nv[c].y = ((py ? y[c].y : y[c].y / LEAKY) - shift) * inv_scale;
+        ps = fmaf(g[c].x, nv[c].x, ps); ps = fmaf(g[c].y, nv[c].y, ps);
+        pm += g[c].x + g[c].y;
+        g[c].x *= scale; g[c].y *= scale;
+        sum_dn += g[c].x + g[c].y;
+        dot = fmaf(g[c].x, nv[c].x, dot); dot = fmaf(g[c].y, nv[c].y, dot);
+    }
+    row_allreduce2(sum_dn, dot, t_xs, q, bar_id);
+    const float inv_den = 1.f / (sd + NORM_EPS);
+    const float mean_dn = sum_dn / (float)n_true;
+    const float coef = sd > 0.f ? dot / ((float)(n_true - 1) * sd) : 0.f;
+#pragma unroll
+    for (int c = 0; c < CPT / 2; ++c) {
+        g[c].x = (g[c].x - mean_dn) * inv_den - nv[c].x * coef;
+        g[c].y = (g[c].y - mean_dn) * inv_den - nv[c].y * coef;
+    }
+}
+
+// forward output columns of this thread's row (32-byte loads: y_ld and col0 are multiples of 8)
+template <int CPT>
+__device__ __forceinline__ void load_y(float2 (&y)[CPT / 2], const TcBwd& b, int row_g, bool valid, int col0) {
+#pragma unroll
+    for (int c = 0; c < CPT / 2; ++c) y[c] = make_float2(0.f, 0.f);
+    if (b.y == nullptr || !valid) return;
+    const float* p = b.y + (size_t)row_g * b.y_ld + col0;
+#pragma unroll
+    for (int c8 = 0; c8 < CPT / 8; ++c8) ldg256(p + 8 * c8, y[4 * c8], y[4 * c8 + 1], y[4 * c8 + 2], y[4 * c8 + 3]);
+}
+
+// pool the per-thread partials of the scalar gradients of one stage: warp sum, then one shared-memory atomic per warp
+__device__ __forceinline__ void pool_scalar_grads(float ps, float pm, bool valid, double* dacc, int lane) {
+    if (!valid) { ps = 0.f; pm = 0.f; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        pm += __shfl_xor_sync(0xffffffffu, pm, o);
+    }
+    if (lane == 0) {
+        atomicAdd(dacc, (double)ps);
+        atomicAdd(dacc + 1, (double)pm);
+    }
+}
+
+// backward epilogue of a stage: D = d(layer output) -> dz = norm'(act'(D)) -> store / next A operand
+template <int CPT>
+__device__ __forceinline__ void epilogue_bwd(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row, int bar_id,
+                                             const float2 (&y)[CPT / 2], double* dacc, int lane) {
+    float2 z[CPT / 2];
+    const int col0 = q * CPT;
+#pragma unroll
+    for (int c = 0; c < CPT / 2; c += 8) tc::tmem_ld16(t_row + e.d + col0 + 2 * c, z + c);
+    tc::tmem_wait_ld();
+    const TcBwd& b = e.bwd;
+    const bool norm = b.scale != nullptr;
+    const float scale = norm ? __ldg(b.scale) : 1.f, shift = norm ? __ldg(b.shift) : 0.f;
+    const float sd = (norm && valid) ? __ldg(b.sd + row_g) : 0.f;
+    float ps, pm;
+    bwd_transform<CPT>(z, y, b, e.n_true, b.y != nullptr || b.lin0 != 0, scale, shift, sd, t_row + TC_XS_COL + 4, q, bar_id, ps, pm);
+    if (norm && b.g_scale != nullptr) pool_scalar_grads(ps, pm, valid, dacc, lane);
+    float2 none[CPT / 2];
+#pragma unroll
+    for (int c = 0; c < CPT / 2; ++c) none[c] = make_float2(0.f, 0.f);
+    finish_columns<CPT / 2>(z, e, row_g, valid, col0, t_row, none, false);
 }
 
 // no normalisation: 16 columns at a time
@@ -208,12 +325,23 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         cst[i] = v;
     }
     float* w0s = smem + RM_OFF_W0;
-    if (pg.in.mode == TC_IN_LIN0) {
+    double* dacc = reinterpret_cast<double*>(smem + RM_OFF_DACC);
+    for (int i = tid; i < RM_DACC_N; i += RM_NT) dacc[i] = 0.;
+    // first encoder Linear (<= 7 inputs): evaluated on the CUDA cores, either as the input (LIN0 mode) or to recompute the
+    // activation mask of that layer in a backward program (pg.lin0)
+    const bool lin0_in = pg.in.mode == TC_IN_LIN0;
+    const float* l0_f = lin0_in ? pg.in.p0 : pg.lin0.f;
+    const int* l0_idx = lin0_in ? pg.in.i0 : pg.lin0.ridx;
+    const float* l0_W = lin0_in ? pg.in.p1 : pg.lin0.W;
+    const float* l0_b = lin0_in ? pg.in.lin_b : pg.lin0.b;
+    const int l0_ld = lin0_in ? pg.in.ld0 : pg.lin0.ld, l0_w = lin0_in ? pg.in.w0 : pg.lin0.w;
+    const int l0_act = lin0_in ? pg.in.lin_act : pg.lin0.act;
+    if (l0_W != nullptr && (lin0_in || pg.lin0.f != nullptr)) {
         for (int i = tid; i < 8 * 256; i += RM_NT) {
             const int k = i >> 8, c = i & 255;
             float v = 0.f;
-            if (k < pg.in.w0) v = __ldg(pg.in.p1 + (size_t)c * pg.in.w0 + k);
-            else if (k == 7 && pg.in.lin_b != nullptr) v = __ldg(pg.in.lin_b + c);
+            if (k < l0_w) v = __ldg(l0_W + (size_t)c * l0_w + k);
+            else if (k == 7 && l0_b != nullptr) v = __ldg(l0_b + c);
             w0s[i] = v;
         }
     }
@@ -344,16 +472,17 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         }
         // LIN0: raw feature row of this thread's row (f[7] = 1 multiplies the bias row), fetched one tile ahead
         const bool lin0 = in.mode == TC_IN_LIN0;
+        const bool lin0_aux = !lin0 && pg.lin0.f != nullptr;
         float fcur[8], fnext[8];
         auto load_feat = [&](int tile, float (&f)[8]) {
             const int rg = tile * 128 + row;
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = 0.f;
             if (rg < pg.n_rows) {
-                const size_t r = in.i0 ? (size_t)__ldg(in.i0 + rg) : (size_t)rg;
+                const size_t r = l0_idx ? (size_t)__ldg(l0_idx + rg) : (size_t)rg;
 #pragma unroll
                 for (int k = 0; k < 7; ++k)
-                    if (k < in.w0) f[k] = __ldg(in.p0 + r * in.ld0 + k);
+                    if (k < l0_w) f[k] = __ldg(l0_f + r * l0_ld + k);
                 f[7] = 1.f;
             }
         };
@@ -368,7 +497,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int c = 0; c < 32; ++c) y[c] = __ffma2_rn(*reinterpret_cast<const float2*>(w + k * 256 + 2 * c), fk, y[c]);
             }
-            if (in.lin_act) {
+            if (l0_act) {
                 const float2 sl = make_float2(LEAKY, LEAKY);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -388,7 +517,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 tc::tmem_st16(t_row + in.a_lo + q * 64 + 2 * c, lo);
             }
         };
-        if (lin0 && (int)blockIdx.x < n_tiles) load_feat(blockIdx.x, fcur);
+        if ((lin0 || lin0_aux) && (int)blockIdx.x < n_tiles) load_feat(blockIdx.x, fcur);
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int row_g = tile * 128 + row;
@@ -398,11 +527,49 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 const bool split = (in.k_pad % (8 * RM_NQ)) == 0;
                 const int cw = split ? in.k_pad / RM_NQ : in.k_pad;
                 const int c0 = split ? q * cw : 0;
+                if (lin0_aux && tile + (int)gridDim.x < n_tiles) load_feat(tile + gridDim.x, fnext);
                 if (lin0) {
                     float2 y[32];
                     lin0_compute(fcur, 0, y);
                     lin0_store(y);
                     if (tile + (int)gridDim.x < n_tiles) load_feat(tile + gridDim.x, fnext);
+                } else if (in.mode == TC_IN_BWD) {
+                    // gradient rows -> dz = norm'(act'(g)) -> A operand (and the scratch buffer of the weight gradient)
+                    const TcBwd& b = in.bwd;
+                    const bool norm = b.scale != nullptr;
+                    const float scale = norm ? __ldg(b.scale) : 1.f, shift = norm ? __ldg(b.shift) : 0.f;
+                    const float sd = (norm && valid) ? __ldg(b.sd + row_g) : 0.f;
+                    auto run = [&](auto tag) {
+                        constexpr int CPT = decltype(tag)::value;
+                        float2 g[CPT / 2], y[CPT / 2];
+                        const int col0 = q * CPT;
+                        const size_t r = in.i0 ? (size_t)__ldg(in.i0 + (valid ? row_g : 0)) : (size_t)row_g;
+#pragma unroll
+                        for (int c8 = 0; c8 < CPT / 8; ++c8) {
+                            g[4 * c8] = g[4 * c8 + 1] = g[4 * c8 + 2] = g[4 * c8 + 3] = make_float2(0.f, 0.f);
+                            if (valid) ldg256(in.p0 + r * in.ld0 + col0 + 8 * c8, g[4 * c8], g[4 * c8 + 1], g[4 * c8 + 2], g[4 * c8 + 3]);
+                        }
+                        load_y<CPT>(y, b, row_g, valid, col0);
+                        float ps, pm;
+                        bwd_transform<CPT>(g, y, b, in.w0, b.y != nullptr, scale, shift, sd, t_row + TC_XS_COL + 8, q, bar_id, ps, pm);
+                        if (norm && b.g_scale != nullptr) pool_scalar_grads(ps, pm, valid, dacc + 2 * TC_MAX_STAGES, lane);
+                        if (in.bwd_store != nullptr && valid) {
+                            float* o = in.bwd_store + (size_t)row_g * in.k_pad + col0;
+#pragma unroll
+                            for (int c8 = 0; c8 < CPT / 8; ++c8) stg256(o + 8 * c8, g[4 * c8], g[4 * c8 + 1], g[4 * c8 + 2], g[4 * c8 + 3]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; c += 8) {
+                            float2 hi[8], lo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) tc::split_tf32(g[c + j], hi[j], lo[j]);
+                            tc::tmem_st16(t_row + in.a_hi + col0 + 2 * c, hi);
+                            tc::tmem_st16(t_row + in.a_lo + col0 + 2 * c, lo);
+                        }
+                    };
+                    if (in.k_pad == 128) run(std::integral_constant<int, 64>{});
+                    else if (in.k_pad == 64) run(std::integral_constant<int, 32>{});
+                    else run(std::integral_constant<int, 16>{});
                 } else if (staged_in) {
                     cp_async_wait<0>();
                     group_sync(BAR_WORKERS, RM_NW);               // every thread's copies have landed
@@ -422,6 +589,9 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                             if (!valid) v[j] = 0.f;
                             tc::split_tf32(v[j], hi[j], lo[j]);
                         }
+                        if (in.in_store != nullptr && valid)
+                            stg256(in.in_store + (size_t)row_g * in.k_pad + c, make_float2(v[0], v[1]), make_float2(v[2], v[3]),
+                                   make_float2(v[4], v[5]), make_float2(v[6], v[7]));
                         tc::tmem_st8(t_row + in.a_hi + c, hi);
                         tc::tmem_st8(t_row + in.a_lo + c, lo);
                     }
@@ -431,6 +601,9 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                     for (int c = c0; c < c0 + cw; c += 8) {
                         float v[8], hi[8], lo[8];
                         load_input_block(in, row_g, valid, c, v);
+                        if (in.in_store != nullptr && valid)
+                            stg256(in.in_store + (size_t)row_g * in.k_pad + c, make_float2(v[0], v[1]), make_float2(v[2], v[3]),
+                                   make_float2(v[4], v[5]), make_float2(v[6], v[7]));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], hi[j], lo[j]);
                         tc::tmem_st8(t_row + in.a_hi + c, hi);
@@ -462,7 +635,31 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 tc::tc_fence_after();
                 tick(2 + 2 * s);
                 const float* cb = cst + s * RM_CST_LD;
-                if (e.scale != nullptr) {
+                if (e.is_bwd) {
+                    const int cpt = e.n_cols / RM_NQ;
+                    if (e.bwd.lin0) {           // mask of the first encoder layer: recomputed from the raw features
+                        float2 y[32];
+                        lin0_compute(fcur, e.bwd.lin0_off >> 7, y);
+                        if (e.bwd.y_store != nullptr && valid) {
+                            float* o = e.bwd.y_store + (size_t)row_g * e.bwd.y_ld + e.bwd.lin0_off + q * 64;
+#pragma unroll
+                            for (int c8 = 0; c8 < 8; ++c8) stg256(o + 8 * c8, y[4 * c8], y[4 * c8 + 1], y[4 * c8 + 2], y[4 * c8 + 3]);
+                        }
+                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                    } else if (cpt == 64) {
+                        float2 y[32];
+                        load_y<64>(y, e.bwd, row_g, valid, q * 64);
+                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                    } else if (cpt == 32) {
+                        float2 y[16];
+                        load_y<32>(y, e.bwd, row_g, valid, q * 32);
+                        epilogue_bwd<32>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                    } else {
+                        float2 y[8];
+                        load_y<16>(y, e.bwd, row_g, valid, q * 16);
+                        epilogue_bwd<16>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                    }
+                } else if (e.scale != nullptr) {
                     const int cpt = e.n_cols / RM_NQ;
                     if (cpt == 64) epilogue_norm<64>(e, row_g, valid, q, t_row, bar_id, cb);
                     else if (cpt == 32) epilogue_norm<32>(e, row_g, valid, q, t_row, bar_id, cb);
@@ -476,7 +673,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                 tick(3 + 2 * s);
             }
             group_sync(BAR_WORKERS, RM_NW);     // every worker is done with this tile's TMEM columns
-            if (lin0) {
+            if (lin0 || lin0_aux) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) fcur[k] = fnext[k];
             }
@@ -489,6 +686,20 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    // gradients of the channel_normalization scalars: one atomic per CTA, stage and scalar
+    if ((int)blockIdx.x < n_tiles && tid <= pg.n_stages) {
+        const TcBwd* b = nullptr;
+        int slot_i = 0;
+        if (tid < pg.n_stages) {
+            if (pg.st[tid].epi.is_bwd) { b = &pg.st[tid].epi.bwd; slot_i = tid; }
+        } else if (pg.in.mode == TC_IN_BWD) {
+            b = &pg.in.bwd; slot_i = TC_MAX_STAGES;
+        }
+        if (b != nullptr && b->scale != nullptr && b->g_scale != nullptr) {
+            atomicAdd(b->g_scale, (float)dacc[2 * slot_i]);
+            atomicAdd(b->g_shift, (float)dacc[2 * slot_i + 1]);
+        }
+    }
 }
 
 int g_rowmlp_profile = 0;
@@ -530,12 +741,12 @@ int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
 // per K chunk:  hi (kc/4, Np, 4)  |  lo (kc/4, Np, 4),   zero padded to Np rows / Kp columns
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_tc_kernel(const float* __restrict__ W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp,
-                               int kc, int n_loop, float* __restrict__ dst) {
+                               int kc, int n_loop, float* __restrict__ dst, int transpose) {
     const int tot = Kp * n_loop;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
         const int k = i / n_loop, n = i - k * n_loop;
         float w = 0.f;
-        if (k < Kt && n < Nt) w = W[(size_t)(n0 + n) * ldW + k0 + k];
+        if (k < Kt && n < Nt) w = transpose ? W[(size_t)(k0 + k) * ldW + n0 + n] : W[(size_t)(n0 + n) * ldW + k0 + k];
         float h, l;
         tc::split_tf32(w, h, l);
         const int chunk = k / kc, kk = k - chunk * kc;
@@ -546,11 +757,12 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, int ldW, int n0, int
     }
 }
 
+// transpose: the packed layer is W^T (element (n, k) = W[k0 + k][n0 + n])
 int pack_tc(const float* W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp, int kc, bool pad_rows, float* dst,
-            cudaStream_t stream) {
+            cudaStream_t stream, bool transpose) {
     const int n_loop = pad_rows ? Np - nd0 : Nt;
     const int blocks = (Kp * n_loop + 255) / 256;
-    pack_tc_kernel<<<blocks > 64 ? 64 : blocks, 256, 0, stream>>>(W, ldW, n0, Nt, nd0, Np, k0, Kt, Kp, kc, n_loop, dst);
+    pack_tc_kernel<<<blocks > 64 ? 64 : blocks, 256, 0, stream>>>(W, ldW, n0, Nt, nd0, Np, k0, Kt, Kp, kc, n_loop, dst, transpose ? 1 : 0);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }

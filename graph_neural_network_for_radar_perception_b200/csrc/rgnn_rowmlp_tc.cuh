@@ -20,7 +20,23 @@ constexpr int TC_SLOT_FLOATS = 16384;     // 64 KB weight ring slot: hi + lo cop
 constexpr int TC_SLOTS = 3;               // ring slots; the third one doubles as the input staging tile of programs that stage rows
 constexpr int TC_XS_COL = 496;            // 16 spare TMEM columns for the per-row statistics exchange
 
-enum TcInMode : int { TC_IN_ROWS = 0, TC_IN_PAIRSUM = 1, TC_IN_SEGMAX = 2, TC_IN_LIN0 = 3 };
+enum TcInMode : int { TC_IN_ROWS = 0, TC_IN_PAIRSUM = 1, TC_IN_SEGMAX = 2, TC_IN_LIN0 = 3, TC_IN_BWD = 4 };
+
+// Backward of (channel_normalization + LeakyReLU) of one layer applied to a gradient row: dz = norm'(act'(g)).  The
+// forward pass of a training step saved the layer's output rows y (post-activation) and the per-row sigma, so nothing is
+// recomputed; the normalised value is recovered from y like the FFMA backward does (rgnn_chain.cu, OP_ACTNORM_BWD).
+struct TcBwd {
+    const float* y;         // forward output rows of the layer (row stride y_ld); nullptr with lin0 = 0: plain Linear, dz = g
+    const float* sd;        // per-row sigma of the norm (nullptr: no norm)
+    const float* scale;     // channel_normalization scalars (nullptr: no norm)
+    const float* shift;
+    float* g_scale;         // gradients of the scalars (+=), nullable
+    float* g_shift;
+    float* y_store;         // lin0 only: the recomputed first-layer activation is written here (operand of a weight gradient)
+    int y_ld, act;
+    int lin0;               // 1: y = columns [lin0_off, lin0_off + n) of act(W0 f + b0), recomputed from the raw feature row
+    int lin0_off;
+};
 
 struct TcMma {
     int a_hi, a_lo;     // TMEM columns of the A operand (K columns each)
@@ -45,6 +61,13 @@ struct TcEpi {
     const float* resid; // optional residual row added to the result (identity residual of the conv block)
     int resid_ld;
     int refill;         // 1: no epilogue; once the stage's MMAs are done the workers write the second LIN0 half into the A operand
+    int is_bwd;         // 1: backward epilogue: z = norm'(act'(D)) described by `bwd` (no bias); store / y_hi / y_lo as usual
+    float* sd_store;    // forward of a training step: per-row sigma of this layer's norm (nullable)
+    int store_mode;     // 0 = overwrite, 1 = accumulate (+=), 2 = atomic pair scatter onto rows ia[row], ib[row] of `store`
+    int pad2;
+    const int* ia;      // store_mode 2
+    const int* ib;
+    TcBwd bwd;
 };
 
 struct TcStage {
@@ -66,12 +89,27 @@ struct TcInput {
     // feature row f (p0, <= 7 columns, optional row index i0); W0 = p1 (256 x w0, row-major), b0 = lin_b
     const float* lin_b;
     int lin_act, pad;
+    // BWD: p0 = gradient rows (ld0, w0 columns, optional row index i0); the A operand is norm'(act'(g)) described by `bwd`,
+    // also written to bwd_store (row stride k_pad) when that is set
+    TcBwd bwd;
+    float* bwd_store;
+    float* in_store;        // ROWS / PAIRSUM in a training step: the assembled input rows are written here (row stride k_pad)
+};
+
+// raw feature rows + first encoder Linear for epilogues with bwd.lin0 (the LIN0 input mode keeps its own copy in TcInput)
+struct TcLin0 {
+    const float* f;         // (rows, w) features, optional row index
+    const int* ridx;
+    const float* W;         // (256, w) row-major
+    const float* b;
+    int ld, w, act, pad;
 };
 
 struct TcProgram {
     int n_rows, n_stages;
     int n_slots, pad;       // 2 when the input rows are staged through shared memory (the staging tile aliases slot 2), else 3
     TcInput in;
+    TcLin0 lin0;
     TcStage st[TC_MAX_STAGES];
 };
 
@@ -89,6 +127,6 @@ inline size_t tc_pack_floats(int in_features, int out_features) { return (size_t
 int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream);
 // rows [n0, n0+Nt) x columns [k0, k0+Kt) of W -> chunked hi/lo pack at output rows [nd0, nd0+Nt) of a (Kp x Np) layer
 int pack_tc(const float* W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp, int kc, bool pad_rows, float* dst,
-            cudaStream_t stream);
+            cudaStream_t stream, bool transpose = false);
 
 }  // namespace rgnn

@@ -29,7 +29,8 @@ __device__ __forceinline__ float row_allreduce(float v, uint32_t t_cols, int q, 
 // register pairs for the packed f32x2 pipe).  Two-pass mean / unbiased std like the reference (common.py:215-220).
 template <int CP, int NQ>
 __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_norm, float scale, float shift,
-                                             bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id) {
+                                             bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id,
+                                             float* sd_out = nullptr /* receives the row's sigma */) {
     // scale / shift are passed BY VALUE: with ~226 KB of shared memory per CTA the L1 is a few KB, and a global load
     // inside this dependent chain costs an L2 round trip per row tile
     if (has_norm) {
@@ -46,6 +47,7 @@ __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_no
         }
         const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
         const float sd = sqrtf(ss / (float)(C - 1));
+        if (sd_out != nullptr) *sd_out = sd;
         const float k = scale / (sd + NORM_EPS);
         const float2 k2 = make_float2(k, k), sh2 = make_float2(shift, shift);
 #pragma unroll
@@ -60,6 +62,26 @@ __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_no
             z[c].y = fmaxf(z[c].y, t.y);
         }
     }
+}
+
+// two sums per row over the 2 threads that share it, exchanged through 4 spare TMEM columns
+__device__ __forceinline__ void row_allreduce2(float& u, float& v, uint32_t t_cols, int q, int bar_id) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t_cols + 2 * q), "f"(u), "f"(v) : "memory");
+    tc::tmem_wait_st();
+    tc::tc_fence_before();
+    group_sync(bar_id, 64);
+    tc::tc_fence_after();
+    float p0, p1, p2, p3;
+    tc::tmem_ld4(t_cols, p0, p1, p2, p3);
+    tc::tmem_wait_ld();
+    u = p0 + p2;
+    v = p1 + p3;
+}
+
+__device__ __forceinline__ void stg256(float* p, float2 a, float2 b, float2 c, float2 d) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y)
+                 : "memory");
 }
 
 // named barriers (0 = __syncthreads, 1..4 = the NQ warps sharing 32 rows)

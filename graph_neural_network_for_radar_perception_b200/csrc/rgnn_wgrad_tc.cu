@@ -41,6 +41,7 @@ struct WgradArgs {
     long long sm, sn;
     float* colsum_a;        // optional: += sum_r A[r][m]
     float* colsum_b;        // optional: += sum_r B[r][n]
+    const int* b_ridx;      // optional: row r of B is B[b_ridx[r]]
     int passes;
 };
 
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
                 const int col = (isa ? b : b - nba) * 32 + c4 * 4;
                 const int w = isa ? a.wa : a.wb;
                 if (col >= w) continue;
-                const float* p = (isa ? a.A + r * a.lda : a.B + r * a.ldb) + col;
+                const long long rb = (!isa && a.b_ridx != nullptr) ? (long long)__ldg(a.b_ridx + r) : r;
+                const float* p = (isa ? a.A + r * a.lda : a.B + rb * a.ldb) + col;
                 if (isa ? va : vb) {
                     pre[b] = __ldg(reinterpret_cast<const float4*>(p));
                 } else {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
 
 // D = A^T B added into dst (see WgradArgs); rows may be 0
 int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, int wb, long long rows, float* dst, long long sm,
-                    long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream) {
+                    long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream, const int* b_ridx) {
     if (rows <= 0 || (dst == nullptr && colsum_a == nullptr && colsum_b == nullptr)) return RGNN_OK;
     RGNN_REQUIRE(wa >= 1 && wa <= WG_MA && wb >= 1 && wb <= WG_NB_MAX, "wgrad: operand widths %d x %d outside 128 x 256", wa, wb);
     static bool configured = false;
@@ -225,7 +227,7 @@ int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, in
     WgradArgs a;
     a.A = A; a.B = B; a.lda = lda; a.ldb = ldb; a.wa = wa; a.wb = wb;
     a.wa_pad = WG_MA; a.wb_pad = round_up(wb, 16);
-    a.rows = rows; a.dst = dst; a.sm = sm; a.sn = sn; a.colsum_a = colsum_a; a.colsum_b = colsum_b;
+    a.rows = rows; a.dst = dst; a.sm = sm; a.sn = sn; a.colsum_a = colsum_a; a.colsum_b = colsum_b; a.b_ridx = b_ridx;
     a.passes = rgnn_get_option("tf32_passes");
     const long long n_chunks = (rows + WG_R - 1) / WG_R;
     // split-K: enough chunks per CTA to amortise the final 128 x wb reduction into the gradient buffer
@@ -242,5 +244,5 @@ int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, in
 // Test / integration hook: dst (wa x wb, row-major, leading dimension wb) += A^T B; colsum_* may be NULL.
 extern "C" int rgnn_wgrad(const float* A, int lda, int wa, const float* B, int ldb, int wb, long long rows, float* dst,
                           float* colsum_a, float* colsum_b, void* stream) {
-    return rgnn::launch_wgrad_tc(A, lda, wa, B, ldb, wb, rows, dst, wb, 1, colsum_a, colsum_b, static_cast<cudaStream_t>(stream));
+    return rgnn::launch_wgrad_tc(A, lda, wa, B, ldb, wb, rows, dst, wb, 1, colsum_a, colsum_b, static_cast<cudaStream_t>(stream), nullptr);
 }
