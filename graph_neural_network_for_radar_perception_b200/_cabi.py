@@ -85,6 +85,7 @@ SIGNATURES = {
     'rgnn_ffn_stack_bwd_workspace_bytes': (_SZ, [C.POINTER(rgnn_stack)]),
     'rgnn_ffn_stack_bwd': (_I, [C.POINTER(rgnn_stack), _V, _V, _I, _V, _V, _SZ, _V]),
     'rgnn_conv_block_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V]),
+    'rgnn_conv_edges_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V]),
     'rgnn_detector_workspace_bytes': (_SZ, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _I]),
     'rgnn_detector_fwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _I, _V]),
     'rgnn_detector_bwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),

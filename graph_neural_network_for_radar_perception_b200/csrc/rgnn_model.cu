@@ -406,6 +406,10 @@ extern "C" int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, co
     return run_conv_nodes(*blk, g->n_nodes, x, agg, out, nullptr, nullptr, s);
 }
 
+extern "C" int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, float* agg, void* stream) {
+    return run_conv_edges(*blk, *g, e, proj, agg, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" size_t rgnn_detector_workspace_bytes(const rgnn_detector* net, const rgnn_graph* g, int training) {
     DetPlan pl;
     if (plan_detector(*net, *g, training, nullptr, &pl) != RGNN_OK) return 0;

@@ -191,6 +191,11 @@ size_t rgnn_ffn_stack_bwd_workspace_bytes(const rgnn_stack* stack);
 int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* x, const float* e,
                         float* out, float* agg, float* proj, void* stream);
 
+/* The message + aggregation half of the block alone (MessagePassing.propagate, gnn_blocks.py:106-113):
+ * agg[t] = sum over edges s->t of msg(x_t, x_s, e); proj = the hoisted node projections written by
+ * rgnn_conv_block_fwd (or by the previous block).  This is the dominant kernel of the forward; bench.py times it. */
+int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, float* agg, void* stream);
+
 /* Model_Inference.forward with cluster_node_idx given (gnn_detector.py:141-162).
  * edge_features rows are in the caller's order (g->perm maps them).  Outputs: node_cls (N,7), node_off (N,2),
  * link_cls (n_und,2), obj_cls (n_clusters,7).  With training != 0 the node-level activations needed by
