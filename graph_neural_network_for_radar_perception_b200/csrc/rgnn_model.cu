@@ -137,9 +137,9 @@ struct FwdBuilder : ProgBuilder {
     }
 };
 
-int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream) {
+int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream, const TcSave* save) {
     RGNN_REQUIRE(s.n >= 1 && s.n <= RGNN_MAX_STACK, "stack with %d layers", s.n);
-    if (tc_stack_supported(s)) return tc_run_stack(s, x, nullptr, n_rows, y, stream);
+    if (tc_stack_supported(s)) return tc_run_stack(s, x, nullptr, n_rows, y, stream, save);
     FwdBuilder b(n_rows);
     b.load_rows(b.cur, x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
     b.stack(s);
@@ -197,7 +197,7 @@ int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, co
 
 // node update: out = x + upd(cat(x, agg)); optionally the next layer's projections
 int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float* agg, float* out,
-                   const rgnn_conv* next, float* P_next, cudaStream_t stream) {
+                   const rgnn_conv* next, float* P_next, cudaStream_t stream, float* u_save = nullptr, float* sd_save = nullptr) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
     if (tc_stack_supported(c.upd) && c.upd.n == 1 && (next == nullptr || tc_proj_supported(d))) {
@@ -206,7 +206,7 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
             if (!conv_dims(*next, &dn)) return RGNN_ERR_INVALID;
             RGNN_REQUIRE(dn.cn == d.cn && dn.h == d.h, "conv blocks with different channel plans");
         }
-        return tc_run_conv_nodes(c, d, n_nodes, x, agg, out, next, P_next, stream);
+        return tc_run_conv_nodes(c, d, n_nodes, x, agg, out, next, P_next, stream, u_save, sd_save);
     }
     FwdBuilder b(n_nodes);
     b.load_rows(b.cur, x, d.cn, d.cn, 0);
@@ -267,7 +267,9 @@ int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, v
     pl->emb = take(E * d.ce);
     pl->hlink = take(N * pl->link_w);
     pl->gcls = take(N * pl->cls_w);
-    pl->enc_tc_bwd = pl->link_tc_bwd = false;
+    pl->enc_tc_bwd = pl->link_tc_bwd = pl->conv_tc_bwd = false;
+    for (int i = 0; i < 5; ++i) { pl->node_tc_bwd[i] = false; memset(&pl->node_save[i], 0, sizeof(TcSave)); }
+    for (int l = 0; l < RGNN_MAX_CONV; ++l) pl->u_save[l] = pl->usd_save[l] = nullptr;
     memset(&pl->enc_save, 0, sizeof(TcSave));
     memset(&pl->link_save, 0, sizeof(TcSave));
     pl->cscr = nullptr;
@@ -283,7 +285,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
     int rc;
     if (tc_stack_supported(net.node_enc) && tc_proj_supported(d)) {
-        if ((rc = tc_run_node_encoder(net.node_enc, net.conv[0], d, node_features, N, pl.x[0], pl.P[0], stream))) return rc;
+        if ((rc = tc_run_node_encoder(net.node_enc, net.conv[0], d, node_features, N, pl.x[0], pl.P[0], stream,
+                                      pl.node_tc_bwd[0] ? &pl.node_save[0] : nullptr)))
+            return rc;
     } else {   // node encoder (+ first layer's projections)
         FwdBuilder b(N);
         const int in = stack_in(net.node_enc);
@@ -308,13 +312,15 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     for (int l = 0; l < L; ++l) {
         if ((rc = run_conv_edges(net.conv[l], g, pl.emb, pl.P[l], pl.agg[l], stream))) return rc;
         if ((rc = run_conv_nodes(net.conv[l], N, pl.x[l], pl.agg[l], pl.x[l + 1], l + 1 < L ? &net.conv[l + 1] : nullptr,
-                                 l + 1 < L ? pl.P[l + 1] : nullptr, stream)))
+                                 l + 1 < L ? pl.P[l + 1] : nullptr, stream, pl.conv_tc_bwd ? pl.u_save[l] : nullptr,
+                                 pl.conv_tc_bwd ? pl.usd_save[l] : nullptr)))
             return rc;
     }
     const float* xL = pl.x[L];
-    if ((rc = run_stack_fwd(net.head_node, xL, N, node_cls, stream))) return rc;
-    if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream))) return rc;
-    if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream))) return rc;
+    auto sv = [&](int i) { return pl.node_tc_bwd[i] ? &pl.node_save[i] : nullptr; };
+    if ((rc = run_stack_fwd(net.head_node, xL, N, node_cls, stream, sv(1)))) return rc;
+    if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream, sv(2)))) return rc;
+    if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream, sv(3)))) return rc;
     if (g.n_und > 0 && tc_stack_supported(net.head_link)) {
         if ((rc = tc_run_pairsum_stack(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream,
                                        pl.link_tc_bwd ? &pl.link_save : nullptr)))
@@ -328,7 +334,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if ((rc = run_stack_fwd(net.class_node, xL, N, pl.gcls, stream))) return rc;
+    if ((rc = run_stack_fwd(net.class_node, xL, N, pl.gcls, stream, sv(4)))) return rc;
     if (g.n_clusters > 0 && tc_stack_supported(net.head_class)) {
         if ((rc = tc_run_segmax_stack(net.head_class, pl.gcls, pl.cls_w, g.cl_ptr, g.cl_members, g.n_clusters, obj_cls, stream))) return rc;
     } else if (g.n_clusters > 0) {

@@ -36,6 +36,12 @@ struct DetPlan {
     // training with the tensor-core chain backward: saved layer outputs / sigmas of the edge encoder and the link head
     bool enc_tc_bwd, link_tc_bwd;
     TcSave enc_save, link_save;
+    // node-sized stacks with the chain backward: 0 node encoder, 1 head_node, 2 head_offset, 3 link_node, 4 class_node
+    bool node_tc_bwd[5];
+    TcSave node_save[5];
+    bool conv_tc_bwd;                  // node update of every conv block
+    float* u_save[RGNN_MAX_CONV];      // update output before the residual
+    float* usd_save[RGNN_MAX_CONV];    // its sigma
     float* cscr;     // scratch of tc_stack_bwd (dz per layer), shared by the two chains
     size_t bytes;
 };
@@ -46,7 +52,7 @@ void plan_detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const Take
 
 int stack_in(const rgnn_stack& s);
 int stack_out(const rgnn_stack& s);
-int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream);
+int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream, const TcSave* save = nullptr);
 void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* P,
                         int r_in, int r_mid, int r_out, int slot0, int slot1);
 
@@ -87,9 +93,13 @@ int tc_stack_bwd(const rgnn_stack& s, const TcSave& save, const float* x_rows, c
                  const float* g_top, int n_rows, float* scratch, float* dx, int dx_mode, const int* ia, const int* ib,
                  cudaStream_t stream);
 int tc_run_node_encoder(const rgnn_stack& enc, const rgnn_conv& first, const ConvDims& d, const float* node_features, int n_nodes,
-                        float* x0, float* P0, cudaStream_t stream);
+                        float* x0, float* P0, cudaStream_t stream, const TcSave* save = nullptr);
 int tc_run_conv_nodes(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
-                      const rgnn_conv* next, float* P_next, cudaStream_t stream);
+                      const rgnn_conv* next, float* P_next, cudaStream_t stream, float* u_save = nullptr, float* sd_save = nullptr);
+int tc_proj_bwd(const rgnn_conv& c, const ConvDims& d, const float* dP, const float* x, int n_nodes, float* dx, cudaStream_t stream);
+bool tc_conv_nodes_bwd_supported(const rgnn_conv& c, const ConvDims& d);
+int tc_conv_nodes_bwd(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, const float* u,
+                      const float* sd, float* dx, float* dagg, float* dz_scratch, cudaStream_t stream);
 int tc_run_pairsum_stack(const rgnn_stack& s, const float* h, int ld, const int* ia, const int* ib, int n_rows, float* y,
                          cudaStream_t stream, const TcSave* save = nullptr);
 int tc_run_segmax_stack(const rgnn_stack& s, const float* g, int ld, const int* ptr, const int* members, int n_rows, float* y,

@@ -210,6 +210,18 @@ void plan_detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const Take
     if (pl->enc_tc_bwd) plan_save(net.edge_enc, E, false, &pl->enc_save);
     pl->link_tc_bwd = g.n_und > 0 && tc_stack_bwd_supported(net.head_link);
     if (pl->link_tc_bwd) plan_save(net.head_link, (size_t)g.n_und, true, &pl->link_save);
+    // node-sized stacks and the node update of the conv blocks
+    const rgnn_stack* node_stacks[5] = {&net.node_enc, &net.head_node, &net.head_offset, &net.link_node, &net.class_node};
+    for (int i = 0; i < 5; ++i) {
+        pl->node_tc_bwd[i] = N > 0 && tc_stack_bwd_supported(*node_stacks[i]) && (i != 0 || tc_proj_supported(pl->d));
+        if (pl->node_tc_bwd[i]) plan_save(*node_stacks[i], N, false, &pl->node_save[i]);
+    }
+    pl->conv_tc_bwd = N > 0;
+    for (int l = 0; l < net.n_conv; ++l) pl->conv_tc_bwd = pl->conv_tc_bwd && tc_conv_nodes_bwd_supported(net.conv[l], pl->d);
+    if (pl->conv_tc_bwd) {
+        for (int l = 0; l < net.n_conv; ++l) { pl->u_save[l] = take(N * pl->d.cn); pl->usd_save[l] = take(N); }
+        cscr = cscr > N * pl->d.cn ? cscr : N * pl->d.cn;
+    }
     if (cscr > 0) pl->cscr = take(cscr);
 }
 
@@ -221,8 +233,14 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     const float* xL = pl.x[L];
     int rc;
     // ---- heads: accumulate dL/dx_L in pl.dx ----
-    if ((rc = stack_bwd(net.head_node, xL, nullptr, g_node_cls, N, pl.dx, false, stream))) return rc;
-    if ((rc = stack_bwd(net.head_offset, xL, nullptr, g_node_off, N, pl.dx, true, stream))) return rc;
+    // node-sized stack: tensor-core chain backward when the forward saved its activations, else the recompute tile program
+    auto node_bwd = [&](int i, const rgnn_stack& s, const float* y_out, const float* g_top, bool accumulate) -> int {
+        if (pl.node_tc_bwd[i])
+            return tc_stack_bwd(s, pl.node_save[i], xL, nullptr, y_out, g_top, N, pl.cscr, pl.dx, accumulate ? 1 : 0, nullptr, nullptr, stream);
+        return stack_bwd(s, xL, nullptr, g_top, N, pl.dx, accumulate, stream);
+    };
+    if ((rc = node_bwd(1, net.head_node, nullptr, g_node_cls, false))) return rc;
+    if ((rc = node_bwd(2, net.head_offset, nullptr, g_node_off, true))) return rc;
     RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dh, 0, (size_t)N * pl.link_w * sizeof(float), stream));
     if (g.n_und > 0 && pl.link_tc_bwd) {
         if ((rc = tc_stack_bwd(net.head_link, pl.link_save, nullptr, nullptr, nullptr, g_link, g.n_und, pl.cscr, pl.dh, 2, g.und_a,
@@ -247,7 +265,7 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if ((rc = stack_bwd(net.link_node, xL, nullptr, pl.dh, N, pl.dx, true, stream))) return rc;
+    if ((rc = node_bwd(3, net.link_node, pl.hlink, pl.dh, true))) return rc;
     RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dg, 0, (size_t)N * pl.cls_w * sizeof(float), stream));
     if (g.n_clusters > 0) {
         BwdBuilder b(g.n_clusters);
@@ -265,7 +283,7 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if ((rc = stack_bwd(net.class_node, xL, nullptr, pl.dg, N, pl.dx, true, stream))) return rc;
+    if ((rc = node_bwd(4, net.class_node, pl.gcls, pl.dg, true))) return rc;
 
     // ---- message-passing layers, last to first ----
     const bool tc_edges = pl.escr != nullptr && E > 0;
@@ -274,9 +292,14 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     if (tc_edges && (rc = build_src_index(g, pl.sidx, &sptr, &slist, stream))) return rc;
     for (int l = L - 1; l >= 0; --l) {
         const bool has_next = l + 1 < L;
-        if ((rc = conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], has_next ? &net.conv[l + 1] : nullptr,
-                                 has_next ? pl.x[l + 1] : nullptr, has_next ? pl.dP : nullptr, pl.dx, pl.dagg, stream)))
-            return rc;
+        if (pl.conv_tc_bwd) {
+            if (has_next && (rc = tc_proj_bwd(net.conv[l + 1], d, pl.dP, pl.x[l + 1], N, pl.dx, stream))) return rc;
+            rc = tc_conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], pl.u_save[l], pl.usd_save[l], pl.dx, pl.dagg, pl.cscr, stream);
+        } else {
+            rc = conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], has_next ? &net.conv[l + 1] : nullptr,
+                                has_next ? pl.x[l + 1] : nullptr, has_next ? pl.dP : nullptr, pl.dx, pl.dagg, stream);
+        }
+        if (rc) return rc;
         if (tc_edges && net.conv[l].msg.n == 2)
             rc = run_conv_edges_bwd_tc(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, pl.escr, sptr, slist, stream);
         else
@@ -284,7 +307,12 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
         if (rc) return rc;
     }
     // ---- node encoder (receives dL/dx_0 and the projection gradient of layer 0) ----
-    {
+    if (pl.node_tc_bwd[0]) {
+        if ((rc = tc_proj_bwd(net.conv[0], d, pl.dP, pl.x[0], N, pl.dx, stream))) return rc;
+        if ((rc = tc_stack_bwd(net.node_enc, pl.node_save[0], node_features, nullptr, pl.x[0], pl.dx, N, pl.cscr, nullptr, 0, nullptr,
+                               nullptr, stream)))
+            return rc;
+    } else {
         BwdBuilder b(N);
         const rgnn_stack& s = net.node_enc;
         const int in = stack_in(s);

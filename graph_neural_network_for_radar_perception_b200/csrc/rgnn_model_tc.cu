@@ -262,7 +262,12 @@ static void add_projection(TcBuilder& b, const rgnn_conv& c, const ConvDims& d, 
 }
 
 bool tc_proj_supported(const ConvDims& d) { return g_use_tensor_cores_flag() && d.cn == 64 && d.h == 128; }
-size_t tc_proj_pack_floats(const ConvDims& d) { return (d.cn == 64 && d.h == 128) ? tc_pack_floats(d.cn, 2 * d.h) : 0; }
+// forward image of the hoisted projection (cn -> 2h) followed by the two transposed images of its backward
+// (dx += dP_t W_t + dP_s W_s: K' = h, N' = cn each)
+static size_t tc_proj_fwd_floats(const ConvDims& d) { return tc_pack_floats(d.cn, 2 * d.h); }
+size_t tc_proj_pack_floats(const ConvDims& d) {
+    return (d.cn == 64 && d.h == 128) ? tc_proj_fwd_floats(d) + 2 * tc_pack_floats(d.h, d.cn) : 0;
+}
 
 size_t tc_linear_pack_floats(int in_features, int out_features) {
     return (in_features > 256 || out_features > 256) ? 0 : tc_pack_floats(in_features, out_features) + tc_t_pack_floats(in_features, out_features);
@@ -290,7 +295,74 @@ int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t strea
     const int Kp = tc_kp(d.cn), Np = 2 * d.h, kc = tc_chunk_k(Kp, Np);
     int rc = pack_tc(m0.weight, m0.in_features, 0, d.h, 0, Np, 0, d.cn, Kp, kc, false, dst, stream);          // target half
     if (rc) return rc;
-    return pack_tc(m0.weight, m0.in_features, 0, d.h, d.h, Np, d.cn, d.cn, Kp, kc, false, dst, stream);      // source half
+    rc = pack_tc(m0.weight, m0.in_features, 0, d.h, d.h, Np, d.cn, d.cn, Kp, kc, false, dst, stream);      // source half
+    if (rc) return rc;
+    // backward: element (n = node channel, k = projection column) = msg.0.weight[k][half * cn + n]
+    const int Kt = tc_kp(d.h), Nt = tc_np(d.cn);
+    for (int half = 0; half < 2; ++half) {
+        rc = pack_tc(m0.weight, m0.in_features, half * d.cn, d.cn, 0, Nt, 0, d.h, Kt, tc_chunk_k(Kt, Nt), true,
+                     dst + tc_proj_fwd_floats(d) + (size_t)half * tc_pack_floats(d.h, d.cn), stream, true);
+        if (rc) return rc;
+    }
+    return RGNN_OK;
+}
+
+// dx (N, cn) += dP_t W_t + dP_s W_s: the gradient of the hoisted projection P = [x W_t^T + b | x W_s^T] w.r.t. x, and the
+// weight gradient of the node columns of msg.0:  dW[:, 0:cn] += dP_t^T x,  dW[:, cn:2cn] += dP_s^T x
+int tc_proj_bwd(const rgnn_conv& c, const ConvDims& d, const float* dP, const float* x, int n_nodes, float* dx, cudaStream_t stream) {
+    const rgnn_linear& m0 = c.msg.layer[0];
+    const float* wt = m0.weight_t + conv_msg0_tc_offset(d) + mp_tc_pack_floats(d) + tc_proj_fwd_floats(d);
+    for (int half = 0; half < 2; ++half) {
+        TcBuilder b(n_nodes);
+        b.input(TC_IN_ROWS, dP + half * d.h, 2 * d.h, d.h, nullptr, 0, 0, nullptr, nullptr);
+        TcEpi* e = b.layer(wt + (size_t)half * tc_pack_floats(d.h, d.cn), d.h, d.cn, nullptr, nullptr, nullptr, 0, false);
+        set_store(*e, dx, d.cn, d.cn);
+        e->store_mode = 1;
+        int rc = b.run(stream);
+        if (rc) return rc;
+        if (m0.grad_weight != nullptr) {
+            rc = launch_wgrad_tc(dP + half * d.h, 2 * d.h, d.h, x, d.cn, d.cn, n_nodes, m0.grad_weight + half * d.cn, m0.in_features, 1,
+                                 nullptr, nullptr, stream);
+            if (rc) return rc;
+        }
+    }
+    return RGNN_OK;
+}
+
+// backward of the node update out = x + upd(cat(x, agg)) (one ffn_block): dx holds d out on entry and d x on exit
+// (residual + the x half of the update's input gradient), dagg receives the agg half.  u = the update's output before the
+// residual and its sigma were saved by the forward.
+int tc_conv_nodes_bwd(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, const float* u,
+                      const float* sd, float* dx, float* dagg, float* dz_scratch, cudaStream_t stream) {
+    const rgnn_linear& L = c.upd.layer[0];
+    TcBuilder b(n_nodes);
+    b.input(TC_IN_BWD, dx, d.cn, d.cn, nullptr, 0, 0, nullptr, nullptr);
+    TcBwd& bw = b.p.in.bwd;
+    memset(&bw, 0, sizeof(bw));
+    bw.y = u; bw.y_ld = d.cn; bw.sd = sd; bw.scale = L.norm_scale; bw.shift = L.norm_shift;
+    bw.g_scale = L.grad_norm_scale; bw.g_shift = L.grad_norm_shift; bw.act = L.activation;
+    b.p.in.bwd_store = dz_scratch;
+    // d cat = dz W_upd (cn -> 2cn): two stages of cn columns sharing the A operand
+    TcEpi* e0 = b.layer(tc_weights_t(L, 0), d.cn, 2 * d.cn, nullptr, nullptr, nullptr, 0, false, 0, d.cn);
+    set_store(*e0, dx, d.cn, d.cn);
+    e0->store_mode = 1;                       // identity residual: d x = d out + ...
+    TcEpi* e1 = b.layer(tc_weights_t(L, 0), d.cn, 2 * d.cn, nullptr, nullptr, nullptr, 0, false, d.cn, d.cn);
+    set_store(*e1, dagg, d.cn, d.cn);
+    int rc = b.run(stream);
+    if (rc) return rc;
+    if (L.grad_weight != nullptr || L.grad_bias != nullptr) {
+        rc = launch_wgrad_tc(dz_scratch, d.cn, d.cn, x, d.cn, d.cn, n_nodes, L.grad_weight, L.in_features, 1, L.grad_bias, nullptr, stream);
+        if (rc) return rc;
+        rc = launch_wgrad_tc(dz_scratch, d.cn, d.cn, agg, d.cn, d.cn, n_nodes, L.grad_weight ? L.grad_weight + d.cn : nullptr,
+                             L.in_features, 1, nullptr, nullptr, stream);
+    }
+    return rc;
+}
+
+bool tc_conv_nodes_bwd_supported(const rgnn_conv& c, const ConvDims& d) {
+    const rgnn_linear& L = c.upd.layer[0];
+    return rgnn_get_option("tensor_cores_bwd") != 0 && tc_proj_supported(d) && c.upd.n == 1 && tc_stack_supported(c.upd) &&
+           L.norm_scale != nullptr && L.in_features == 2 * d.cn && d.cn == 64 && tc_has_transposed(L.in_features, L.out_features);
 }
 
 // ---- the programs of the detector forward ----------------------------------------------------------------
@@ -304,10 +376,10 @@ int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_row
 }
 
 int tc_run_node_encoder(const rgnn_stack& enc, const rgnn_conv& first, const ConvDims& d, const float* node_features, int n_nodes,
-                        float* x0, float* P0, cudaStream_t stream) {
+                        float* x0, float* P0, cudaStream_t stream, const TcSave* save) {
     TcBuilder b(n_nodes);
     b.input(TC_IN_ROWS, node_features, stack_in(enc), stack_in(enc), nullptr, 0, 0, nullptr, nullptr);
-    add_stack(b, enc, true);
+    add_stack(b, enc, true, save);
     set_store(b.last_epi(), x0, d.cn, d.cn);
     add_projection(b, first, d, P0);
     return b.run(stream);
@@ -315,12 +387,13 @@ int tc_run_node_encoder(const rgnn_stack& enc, const rgnn_conv& first, const Con
 
 // out = x + upd(cat(x, agg)); optionally the next block's projection of `out`
 int tc_run_conv_nodes(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
-                      const rgnn_conv* next, float* P_next, cudaStream_t stream) {
+                      const rgnn_conv* next, float* P_next, cudaStream_t stream, float* u_save, float* sd_save) {
     TcBuilder b(n_nodes);
     b.input(TC_IN_ROWS, x, d.cn, d.cn, agg, d.cn, d.cn, nullptr, nullptr);
     add_stack(b, c.upd, next != nullptr);
     TcEpi& e = b.last_epi();
     e.resid = x; e.resid_ld = d.cn;
+    e.pre_store = u_save; e.sd_store = sd_save;
     set_store(e, out, d.cn, d.cn);
     if (next != nullptr) add_projection(b, *next, d, P_next);
     return b.run(stream);
@@ -449,7 +522,8 @@ int tc_stack_bwd(const rgnn_stack& s, const TcSave& save, const float* x_rows, c
         const float* xl;
         int x_ld;
         const int* xidx = nullptr;
-        if (l == 0) { xl = head ? x_rows : save.x_in; x_ld = head ? L.in_features : round_up(L.in_features, 8); xidx = head ? x_ridx : nullptr; }
+        if (l == 0 && (head || x_rows != nullptr)) { xl = x_rows; x_ld = L.in_features; xidx = x_ridx; }
+        else if (l == 0) { xl = save.x_in; x_ld = round_up(L.in_features, 8); }
         else if (l == 1 && head) { xl = a0; x_ld = 256; }
         else { xl = save.y[l - 1]; x_ld = s.layer[l - 1].out_features; }
         if (L.grad_weight == nullptr && L.grad_bias == nullptr) continue;

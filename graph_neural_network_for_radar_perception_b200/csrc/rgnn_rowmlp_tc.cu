@@ -100,6 +100,12 @@ __device__ __forceinline__ void load_input_block(const TcInput& in, int row_g, b
 template <int CP>
 __device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, int row_g, bool valid, int col0, uint32_t t_row,
                                                const float2 (&res)[CP] /* prefetched residual */, bool has_res) {
+    if (e.pre_store != nullptr && valid) {      // n_true is a multiple of 16 here (norm layers)
+        float* o = e.pre_store + (size_t)row_g * e.n_true + col0;
+#pragma unroll
+        for (int c = 0; c < CP; c += 4)
+            if (col0 + 2 * c < e.n_true) stg256(o + 2 * c, z[c], z[c + 1], z[c + 2], z[c + 3]);
+    }
     if (has_res) {
 #pragma unroll
         for (int c = 0; c < CP; ++c) z[c] = __fadd2_rn(z[c], res[c]);

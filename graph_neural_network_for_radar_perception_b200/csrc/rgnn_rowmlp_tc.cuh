@@ -63,6 +63,7 @@ struct TcEpi {
     int refill;         // 1: no epilogue; once the stage's MMAs are done the workers write the second LIN0 half into the A operand
     int is_bwd;         // 1: backward epilogue: z = norm'(act'(D)) described by `bwd` (no bias); store / y_hi / y_lo as usual
     float* sd_store;    // forward of a training step: per-row sigma of this layer's norm (nullable)
+    float* pre_store;   // forward of a training step: the result BEFORE the residual is added (row stride n_true), nullable
     int store_mode;     // 0 = overwrite, 1 = accumulate (+=), 2 = atomic pair scatter onto rows ia[row], ib[row] of `store`
     int pad2;
     const int* ia;      // store_mode 2
