@@ -527,6 +527,13 @@ int tc_stack_bwd(const rgnn_stack& s, const TcSave& save, const float* x_rows, c
         else if (l == 1 && head) { xl = a0; x_ld = 256; }
         else { xl = save.y[l - 1]; x_ld = s.layer[l - 1].out_features; }
         if (L.grad_weight == nullptr && L.grad_bias == nullptr) continue;
+        if (L.out_features <= 64 && L.in_features <= 128 && L.in_features > L.out_features && xidx == nullptr) {
+            // the narrower operand goes second (<= 64 columns: the two-CTA-per-SM variant): D[m = input][n = output] -> dW[n][m]
+            rc = launch_wgrad_tc(xl, x_ld, L.in_features, dzl, dz_ld, L.out_features, n_rows, L.grad_weight, 1, L.in_features,
+                                 nullptr, L.grad_bias, stream);
+            if (rc) return rc;
+            continue;
+        }
         for (int m0 = 0; m0 < L.out_features; m0 += 128) {
             const int wa = L.out_features - m0 < 128 ? L.out_features - m0 : 128;
             rc = launch_wgrad_tc(dzl + m0, dz_ld, wa, xl, x_ld, L.in_features, n_rows,

@@ -636,13 +636,17 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                     tick(2 + 2 * s);
                     continue;
                 }
-                tc::mbar_wait(d_ready, dphase);
-                dphase ^= 1u;
-                tc::tc_fence_after();
-                tick(2 + 2 * s);
                 const float* cb = cst + s * RM_CST_LD;
                 if (e.is_bwd) {
+                    // the saved forward rows are requested BEFORE waiting for the accumulator: their L2 / HBM round trip
+                    // overlaps the MMAs of this stage
                     const int cpt = e.n_cols / RM_NQ;
+                    auto wait_d = [&]() {
+                        tc::mbar_wait(d_ready, dphase);
+                        dphase ^= 1u;
+                        tc::tc_fence_after();
+                        tick(2 + 2 * s);
+                    };
                     if (e.bwd.lin0) {           // mask of the first encoder layer: recomputed from the raw features
                         float2 y[32];
                         lin0_compute(fcur, e.bwd.lin0_off >> 7, y);
@@ -651,21 +655,35 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
 #pragma unroll
                             for (int c8 = 0; c8 < 8; ++c8) stg256(o + 8 * c8, y[4 * c8], y[4 * c8 + 1], y[4 * c8 + 2], y[4 * c8 + 3]);
                         }
+                        wait_d();
                         epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
                     } else if (cpt == 64) {
                         float2 y[32];
                         load_y<64>(y, e.bwd, row_g, valid, q * 64);
+                        wait_d();
                         epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
                     } else if (cpt == 32) {
                         float2 y[16];
                         load_y<32>(y, e.bwd, row_g, valid, q * 32);
+                        wait_d();
                         epilogue_bwd<32>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
                     } else {
                         float2 y[8];
                         load_y<16>(y, e.bwd, row_g, valid, q * 16);
+                        wait_d();
                         epilogue_bwd<16>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
                     }
-                } else if (e.scale != nullptr) {
+                    tc::tmem_wait_st();
+                    tc::tc_fence_before();
+                    if (s + 1 < pg.n_stages) bar_arrive(BAR_Y_READY, RM_NW + 32);
+                    tick(3 + 2 * s);
+                    continue;
+                }
+                tc::mbar_wait(d_ready, dphase);
+                dphase ^= 1u;
+                tc::tc_fence_after();
+                tick(2 + 2 * s);
+                if (e.scale != nullptr) {
                     const int cpt = e.n_cols / RM_NQ;
                     if (cpt == 64) epilogue_norm<64>(e, row_g, valid, q, t_row, bar_id, cb);
                     else if (cpt == 32) epilogue_norm<32>(e, row_g, valid, q, t_row, bar_id, cb);

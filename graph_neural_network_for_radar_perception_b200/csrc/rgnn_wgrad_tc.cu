@@ -24,12 +24,19 @@ constexpr int WG_NB_MAX = 256;
 constexpr int WG_LOADERS = 256;
 constexpr int WG_NT = WG_LOADERS + 32;        // + the MMA warp
 constexpr int WG_BLK = WG_R * 32;             // floats of one (32 rows x 32 columns) block image
-constexpr int WG_NBLK = (WG_MA + WG_NB_MAX) / 32;                  // 32-column blocks per stage: 4 of A, up to 8 of B
-constexpr int WG_STAGE_FLOATS = 2 * WG_NBLK * WG_BLK;              // hi + lo images
-constexpr int WG_OFF_BAR = WG_STAGES * WG_STAGE_FLOATS;
-constexpr size_t WG_SMEM = (size_t)(WG_OFF_BAR + 16) * 4;
-static_assert(WG_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(WG_R / 4 == WG_LOADERS / 32, "one warp per group of 4 rows");
+// The kernel is instantiated for B operands of up to NBB blocks of 32 columns: NBB = 8 (wb <= 256, 192 KB of shared
+// memory, one CTA per SM) and NBB = 2 (wb <= 64, 96 KB, 128 TMEM columns: two CTAs per SM, whose load latencies overlap).
+template <int NBB>
+struct WgLayout {
+    static constexpr int NBLK = WG_MA / 32 + NBB;                 // 32-column blocks per stage: 4 of A, NBB of B
+    static constexpr int STAGE_FLOATS = 2 * NBLK * WG_BLK;        // hi + lo images
+    static constexpr int OFF_BAR = WG_STAGES * STAGE_FLOATS;
+    static constexpr size_t SMEM = (size_t)(OFF_BAR + 16) * 4;
+    static constexpr int TMEM_COLS = NBB <= 2 ? 64 : 256;
+    static constexpr int CTAS = NBB <= 2 ? 2 : 1;
+    static_assert(SMEM * CTAS <= 227 * 1024, "shared memory budget");
+};
 
 struct WgradArgs {
     const float* A; const float* B;
@@ -55,9 +62,12 @@ __device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr, uint32_t lbo_
 // instruction descriptor: kind::tf32, fp32 accumulate, A and B MN-major (bits 15 / 16)
 __host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) { return tc::idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
 
-__global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constant__ WgradArgs a) {
+template <int NBB>
+__global__ void __launch_bounds__(WG_NT, WgLayout<NBB>::CTAS) wgrad_tc_kernel(const __grid_constant__ WgradArgs a) {
+    using L = WgLayout<NBB>;
+    constexpr int WG_NBLK = L::NBLK, WG_STAGE_FLOATS = L::STAGE_FLOATS;
     extern __shared__ __align__(1024) float smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_OFF_BAR);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* full = bars;                   // [WG_STAGES] loaders -> MMA
     uint64_t* empty = bars + WG_STAGES;      // [WG_STAGES] MMA (tcgen05.commit) -> loaders
     uint64_t* done = bars + 2 * WG_STAGES;
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
         tc::mbar_init(done, 1);
         tc::mbar_init_fence();
     }
-    if (warp == 0) tc::tmem_alloc(slot, 256);
+    if (warp == 0) tc::tmem_alloc(slot, L::TMEM_COLS);
     // zero the operand images once: padded columns are never written again
     for (int i = tid; i < WG_STAGES * WG_STAGE_FLOATS / 4; i += WG_NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc::fence_async_smem();
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
 // D = A^T B added into dst (see WgradArgs); rows may be 0
@@ -221,7 +231,8 @@ int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, in
     RGNN_REQUIRE(wa >= 1 && wa <= WG_MA && wb >= 1 && wb <= WG_NB_MAX, "wgrad: operand widths %d x %d outside 128 x 256", wa, wb);
     static bool configured = false;
     if (!configured) {
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgLayout<2>::SMEM));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgLayout<8>::SMEM));
         configured = true;
     }
     WgradArgs a;
@@ -231,10 +242,13 @@ int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, in
     a.passes = rgnn_get_option("tf32_passes");
     const long long n_chunks = (rows + WG_R - 1) / WG_R;
     // split-K: enough chunks per CTA to amortise the final 128 x wb reduction into the gradient buffer
+    const bool narrow = wb <= 64;
+    const long long max_grid = (long long)sm_count() * (narrow ? 2 : 1);
     long long grid = n_chunks / 8;
     if (grid < 1) grid = 1;
-    if (grid > sm_count()) grid = sm_count();
-    wgrad_tc_kernel<<<(int)grid, WG_NT, WG_SMEM, stream>>>(a);
+    if (grid > max_grid) grid = max_grid;
+    if (narrow) wgrad_tc_kernel<2><<<(int)grid, WG_NT, WgLayout<2>::SMEM, stream>>>(a);
+    else wgrad_tc_kernel<8><<<(int)grid, WG_NT, WgLayout<8>::SMEM, stream>>>(a);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
