@@ -202,3 +202,46 @@ def test_trainer_step_equals_reference_sgd_step(golden_dir, ckpt_state_dict):
         if ref.size > 1:
             # lr * (gradient tolerance, see the module docstring) * (1 + momentum) over two steps
             assert_close(p.detach().cpu().numpy(), ref, 1e-5, 1e-4, n)
+
+
+def test_hidden_width_32_forward_matches_oracle_and_training_fails_loudly():
+    """BASELINE.json configs[4] (hidden width sweep).  Supported envelope of this library: forward for
+    node / edge widths that are multiples of 8 up to 128 with msg hidden <= 128; training additionally needs widths that are
+    multiples of 64.  Width 32: the forward (FFMA tile programs + the generic tensor-core row-MLP stages) is held to the
+    oracle; the training step must raise, not compute something else."""
+    from graph_neural_network_for_radar_perception_b200 import config, Model_Training, synth
+    from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
+    from oracle import graph_np, model_torch as mt
+    hidden = 32
+    cfg = config()
+    cfg.node_feat_enc_stem_channels = [256, 128, hidden]
+    cfg.edge_feat_enc_stem_channels = [256, 128, 128, hidden]
+    cfg.graph_convolution_stem_channels = [hidden] * 3
+    cfg.msg_mlp_hidden_dim = 2 * hidden
+    cfg.link_pred_stem_channels = [hidden] * 3
+    cfg.node_pred_stem_channels = [hidden] * 3
+    torch.manual_seed(1234)
+    m = Model_Training(cfg, 'cuda').to('cuda')
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
+    d, src = synth.make_frame(900, 150)
+    adj = graph_np.adjacency_information(d, 25, 10)
+    lab = synth.make_labels(d, src, adj['adj_list'])
+    nf = torch.from_numpy(graph_np.node_features(d, adj['degree'], True, 0, R, 0, np.pi * 0.5).astype(np.float32))
+    ef = torch.from_numpy(graph_np.edge_features(d, adj['adj_list']).astype(np.float32))
+    ei = torch.from_numpy(adj['adj_list'])
+    clusters = [torch.from_numpy(c) for c in lab['cluster_node_idx']]
+    want = mt.detector_forward(sd, nf, ef, ei, clusters)
+    with torch.no_grad():
+        got = m.pred.eval()(nf.cuda(), ef.cuda(), ei.cuda(), None, [c.cuda() for c in clusters])
+    for g, w, name in zip(got, want, ('node_cls', 'node_off', 'link_cls', 'obj_cls')):
+        w = w.detach().numpy()
+        assert_close(g.cpu().numpy(), w, 1e-4, 1e-5 * max(np.abs(w).max(), 1.0), name)
+    labels = {'cluster_node_idx': [[c.cuda() for c in clusters]],
+              'cluster_labels': [torch.from_numpy(lab['cluster_labels']).cuda()],
+              'edge_class': [torch.from_numpy(lab['edge_class']).cuda()],
+              'node_class': [torch.from_numpy(lab['node_class']).cuda()],
+              'node_offsets': [torch.from_numpy(lab['node_offsets']).cuda()]}
+    loss, _ = m.train()([nf.cuda()], [ef.cuda()], [ei.cuda()], [None], labels)
+    with pytest.raises(RgnnError):
+        sum(loss.values()).backward()
