@@ -278,6 +278,23 @@ int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, v
     return RGNN_OK;
 }
 
+// object_classification head on the per-node stem output pl.gcls: per-cluster max (gnn_blocks.py:384-386) -> FFN_TaskSpecificHead
+static int run_obj_head(const rgnn_detector& net, const rgnn_graph& g, const DetPlan& pl, float* obj_cls, cudaStream_t stream) {
+    int rc;
+    if (g.n_clusters > 0 && tc_stack_supported(net.head_class)) {
+        if ((rc = tc_run_segmax_stack(net.head_class, pl.gcls, pl.cls_w, g.cl_ptr, g.cl_members, g.n_clusters, obj_cls, stream))) return rc;
+    } else if (g.n_clusters > 0) {
+        FwdBuilder b(g.n_clusters);
+        Step* s = b.add(OP_LOAD_SEGMAX, b.cur);
+        s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
+        b.stack(net.head_class);
+        b.store_rows(b.cur, obj_cls, stack_out(net.head_class), stack_out(net.head_class));
+        if (!b.ok) return RGNN_ERR_INVALID;
+        if ((rc = launch_program(b.p, stream))) return rc;
+    }
+    return RGNN_OK;
+}
+
 int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* node_features,
                  const float* edge_features, float* node_cls, float* node_off, float* link_cls, float* obj_cls,
                  const DetPlan& pl, cudaStream_t stream) {
@@ -335,17 +352,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if ((rc = launch_program(b.p, stream))) return rc;
     }
     if ((rc = run_stack_fwd(net.class_node, xL, N, pl.gcls, stream, sv(4)))) return rc;
-    if (g.n_clusters > 0 && tc_stack_supported(net.head_class)) {
-        if ((rc = tc_run_segmax_stack(net.head_class, pl.gcls, pl.cls_w, g.cl_ptr, g.cl_members, g.n_clusters, obj_cls, stream))) return rc;
-    } else if (g.n_clusters > 0) {
-        FwdBuilder b(g.n_clusters);
-        Step* s = b.add(OP_LOAD_SEGMAX, b.cur);
-        s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
-        b.stack(net.head_class);
-        b.store_rows(b.cur, obj_cls, stack_out(net.head_class), stack_out(net.head_class));
-        if (!b.ok) return RGNN_ERR_INVALID;
-        if ((rc = launch_program(b.p, stream))) return rc;
-    }
+    if ((rc = run_obj_head(net, g, pl, obj_cls, stream))) return rc;
     return RGNN_OK;
 }
 
@@ -434,6 +441,18 @@ extern "C" int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, 
     }
     return detector_fwd(*net, *g, node_features, edge_features, node_cls, node_off, link_cls, obj_cls, pl,
                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rgnn_detector_obj_head(const rgnn_detector* net, const rgnn_graph* g, float* obj_cls, void* workspace,
+                                      size_t workspace_bytes, int training, void* stream) {
+    DetPlan pl;
+    int rc = plan_detector(*net, *g, training, workspace, &pl);
+    if (rc) return rc;
+    if (pl.bytes > workspace_bytes) {
+        set_error("detector workspace too small: need %zu bytes, got %zu", pl.bytes, workspace_bytes);
+        return RGNN_ERR_WORKSPACE;
+    }
+    return run_obj_head(*net, *g, pl, obj_cls, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {

@@ -98,8 +98,8 @@ class Model_Inference(nn.Module):
             gb.set_clusters([cluster_node_idx], [0], node_features.device)
             node_cls, node_off, link_cls, obj_cls = run_detector(self, gb, node_features, edge_features)
         else:
-            # proposal extraction (gnn_detector.py:164-187): offsets -> predicted centres -> host DBSCAN ->
-            # class head on the found clusters
+            # proposal extraction (gnn_detector.py:164-187): offsets -> predicted centres -> connected components of the
+            # predicted links / of the eps graph (on the device, csrc/rgnn_cluster.cu) -> class head on the found clusters
             if not hasattr(self, 'clustering_obj'):
                 raise AttributeError("call set_param_for_proposal_extraction(eps, ...) before forward without "
                                      "cluster_node_idx (the reference fails here too: gnn_detector.py:170)")
@@ -107,17 +107,11 @@ class Model_Inference(nn.Module):
             with torch.no_grad():
                 _, off0, link0, _ = run_detector(self, gb, node_features, edge_features, training=False)
             reg = unnormalize_gt_offsets(off0.clone(), self.reg_mu, self.reg_sigma)
-            centres = (other_features[:, :2] + reg).detach().cpu().numpy()
-            if self.compute_adj_mat_from_links:
-                und = torch.stack((gb.und_a[:gb.n_und], gb.und_b[:gb.n_und])).cpu().numpy()
-                self.clustering_obj.cluster_nodes(centres, link0.argmax(dim=-1).cpu().numpy(), und_pairs=und)
-            else:
-                self.clustering_obj.cluster_nodes(centres)
-            ids = self.clustering_obj.meas_to_cluster_id
-            cluster_members_list = [
-                torch.from_numpy(np.nonzero(ids == i)[0]).to(node_features.device).to(torch.int64)
-                for i in range(self.clustering_obj.num_clusters)]
-            gb.set_clusters([cluster_members_list], [0], node_features.device)
+            centres = other_features[:, :2].to(torch.float32) + reg
+            res = self.clustering_obj.cluster_nodes_device(centres, gb, link0)
+            cluster_members_list = res.member_lists()
+            gb.cl_ptr, gb.cl_members, gb.n_clusters = res.cl_ptr, res.cl_members, res.n_clusters
+            gb.frame_cluster_ptr = [0, res.n_clusters]
             node_cls, node_off, link_cls, obj_cls = run_detector(self, gb, node_features, edge_features)
         if self.extract_proposals:
             return node_cls, node_off, link_cls, obj_cls, cluster_members_list

@@ -205,6 +205,29 @@ int rgnn_detector_fwd(const rgnn_detector* net, const rgnn_graph* g, const float
                       const float* edge_features, float* node_cls, float* node_off, float* link_cls, float* obj_cls,
                       void* workspace, size_t workspace_bytes, int training, void* stream);
 
+/* Proposal extraction (gnn_detector.py:164-187; Simple_DBSCAN, modules/inference/clustering.py:8-92) on the device.
+ * The reference grows clusters by breadth-first search over a dense adjacency: that labels the connected components of the
+ * graph, numbered by their smallest member, members in ascending order.  Two ways to get the graph, as in the reference:
+ *   rgnn_cluster_links:  undirected pair k = (und_a[k], und_b[k]) is kept iff its predicted class is 1 (link_logits
+ *                        (n_und,2), arg-max with ties to class 0) and NOT sqrt(dx^2+dy^2) >= eps between the predicted
+ *                        centres xy (n_nodes,2)                                                (clustering.py:9-24)
+ *   rgnn_cluster_radius: all pairs of one frame with dx^2+dy^2 <= eps (eps compares with the SQUARED distance, :27-41);
+ *                        frame_ptr_dev (n_frames+1), max_frame_nodes = largest frame (grid sizing)
+ * Outputs: cluster_id (n_nodes) = meas_to_cluster_id, n_clusters_out (device scalar), cl_ptr (n_nodes+1; entries past
+ * n_clusters repeat n_nodes) and cl_members (n_nodes) = the cluster_node_idx lists flattened, ready for rgnn_graph. */
+size_t rgnn_cluster_workspace_bytes(int n_nodes);
+int rgnn_cluster_links(const float* xy, const int32_t* und_a, const int32_t* und_b, const float* link_logits, int n_nodes,
+                       int n_und, float eps, int32_t* cluster_id, int32_t* n_clusters_out, int32_t* cl_ptr,
+                       int32_t* cl_members, void* workspace, size_t workspace_bytes, void* stream);
+int rgnn_cluster_radius(const float* xy, const int32_t* frame_ptr_dev, int n_frames, int n_nodes, int max_frame_nodes,
+                        float eps, int32_t* cluster_id, int32_t* n_clusters_out, int32_t* cl_ptr, int32_t* cl_members,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* predict_class on clusters found after the forward pass: the per-node stem output of predict_class is still in the
+ * workspace of the preceding rgnn_detector_fwd call on the same graph (same `training` flag); g carries the new
+ * cl_ptr / cl_members / n_clusters.  obj_cls (n_clusters, n_classes). */
+int rgnn_detector_obj_head(const rgnn_detector* net, const rgnn_graph* g, float* obj_cls, void* workspace,
+                           size_t workspace_bytes, int training, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (5) backward and training -- replaces torch autograd over the above (gnn/training.py:81) and
  *     Loss_Graph (gnn/loss.py:37-76)

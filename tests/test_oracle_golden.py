@@ -91,3 +91,19 @@ def test_init_loss_anchors():
     gt = torch.zeros(100, dtype=torch.int64)
     l = model_torch.sigmoid_focal(logits, torch.nn.functional.one_hot(gt, 2).float()).sum(-1).mean() * 2.0
     assert abs(float(l) - 2 * (0.25 * 0.99 ** 2 * np.log(100.0) + 0.75 * 0.01 ** 2 * -np.log(0.99))) < 1e-4
+
+
+def test_cluster_oracle_matches_reference_dbscan(golden_dir):
+    """oracle/clustering_np.py against outputs of the reference's own Simple_DBSCAN (tests/golden/clusters.npz)."""
+    from oracle.clustering_np import Simple_DBSCAN
+    g = np.load(os.path.join(golden_dir, 'clusters.npz'))
+    for c in range(int(g['n_cases'])):
+        p = f'c{c}_'
+        o = Simple_DBSCAN(float(g[p + 'eps_links']), True)
+        o.cluster_nodes(g[p + 'centres'], g[p + 'pred'], g[p + 'adj_matrix'])
+        assert o.num_clusters == int(g[p + 'n_links'])
+        assert np.array_equal(o.meas_to_cluster_id.astype(np.int64), g[p + 'ids_links'])
+        o = Simple_DBSCAN(float(g[p + 'eps_radius']), False)
+        o.cluster_nodes(g[p + 'centres'])
+        assert o.num_clusters == int(g[p + 'n_radius'])
+        assert np.array_equal(o.meas_to_cluster_id.astype(np.int64), g[p + 'ids_radius'])
