@@ -17,12 +17,16 @@
 // kernel writes y1, dz1 and dz2 to a scratch buffer and rgnn_wgrad_tc.cu contracts them over all edges; the per-node
 // gradient of the hoisted projection, dP = [sum_{e: tgt=n} dz1_e | sum_{e: src=n} dz1_e], is a gather over the same scratch
 // (deterministic: no floating-point atomics anywhere in the message backward).
+#include <vector>
+
 #include "rgnn_model.h"
 #include "rgnn_tc.cuh"
 #include "rgnn_tile.cuh"
 #include "rgnn_tc_rows.cuh"
 
 namespace rgnn {
+
+extern int g_rowmlp_profile;
 
 struct MpBwdArgs {
     const float* emb;       // (E, CE) target-major
@@ -42,6 +46,7 @@ struct MpBwdArgs {
     int act1, act2;
     int demb_accumulate;
     int passes;
+    long long* prof;        // developer aid (rgnn_set_option("debug", 8)): [grid][10] cycle counters of worker thread 0
 };
 
 namespace tc {
@@ -211,6 +216,12 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             stage_ps(s_my);
         }
         uint32_t phase = 0;
+        long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+        const bool profiling = a.prof != nullptr && tid == 0;
+        auto tick = [&](int i) {
+            if (profiling) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
+        };
+        if (profiling) tlast = clock64();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
             const int e_my = tile * TM + row;
             const bool valid = e_my < a.n_edges;
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             tc::tmem_wait_st();
             tc::tc_fence_before();
             bar_arrive(BAR_Y_READY, NMMA);          // -> G1
+            tick(0);
 
             // while G1 runs: the hoisted target projection of this row, the next tile's indices and emb rows
             float2 z[H / 4];                        // this thread's half row: H/2 floats
@@ -258,8 +270,10 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             if (has_next) stage_emb(next);
 
             // ---- epilogue 1: z1 = D1 + P_t + P_s -> norm -> act -> y1 (TMEM hi | lo, and the scratch buffer) ----
+            tick(1);
             tc::mbar_wait(&bars[0], phase);
             tc::tc_fence_after();
+            tick(2);
 #pragma unroll
             for (int c = 0; c < H / 2; c += 16) {
                 float2 d[8];
@@ -333,8 +347,10 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             if (has_next) stage_ps(n_s);
 
             // ---- epilogue 2: recompute z2's statistics and activation mask; dz2 = norm'(act'(d message)) ----
+            tick(3);
             tc::mbar_wait(&bars[1], phase);
             tc::tc_fence_after();
+            tick(4);
             {
                 float2 c2[CN / 4];
 #pragma unroll
@@ -419,8 +435,10 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             }
 
             // ---- epilogue 3: d(y1) = D3 -> act' -> norm' -> dz1 (TMEM hi | lo over y1, and the scratch buffer) ----
+            tick(5);
             tc::mbar_wait(&bars[2], phase);
             tc::tc_fence_after();
+            tick(6);
             {
                 // one 16-column block: g := d(pre-activation) (times the norm scale when there is a norm), nv := normalised value
                 auto block = [&](int c, float2 (&g)[8], float2 (&nv)[8]) {
@@ -488,8 +506,10 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             bar_arrive(BAR_Y_READY, NMMA);          // -> G4
 
             // ---- epilogue 4: d(emb) (+)= D4 ----
+            tick(7);
             tc::mbar_wait(&bars[3], phase);
             tc::tc_fence_after();
+            tick(8);
             {
                 float2 d[CE / 4];
 #pragma unroll
@@ -505,7 +525,10 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             }
             tc::tc_fence_before();
             t_my = n_t; s_my = n_s;
+            tick(9);
         }
+        if (profiling)
+            for (int i = 0; i < 10; ++i) a.prof[blockIdx.x * 10 + i] = pt[i];
         // ---- gradients of the channel_normalization scalars: one double per CTA and scalar, published once ----
         {
             double v[4] = {acc_s1, acc_m1, acc_s2, acc_m2};
@@ -648,7 +671,25 @@ int run_conv_edges_bwd_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_grap
     a.passes = rgnn_get_option("tf32_passes");
     const int n_tiles = (g.n_edges + MB_TM - 1) / MB_TM;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    mp_edge_bwd_tc_kernel<<<grid, MB_NW + 128, MB_SMEM, stream>>>(a);
+    a.prof = nullptr;
+    if (g_rowmlp_profile) {     // developer aid: per-phase cycles of worker thread 0, printed to stderr (synchronises!)
+        long long* prof = nullptr;
+        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 10 * grid));
+        a.prof = prof;
+        mp_edge_bwd_tc_kernel<<<grid, MB_NW + 128, MB_SMEM, stream>>>(a);
+        RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
+        std::vector<long long> h(10 * grid);
+        RGNN_CHECK_CUDA(cudaMemcpy(h.data(), prof, sizeof(long long) * 10 * grid, cudaMemcpyDeviceToHost));
+        double tot[10] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 10; ++i) tot[i] += (double)h[b * 10 + i];
+        static const char* nm[10] = {"in->A", "preG1", "waitG1", "epi1", "waitG2", "epi2", "waitG3", "epi3", "waitG4", "epi4"};
+        fprintf(stderr, "[mp_edge_bwd_tc profile] cycles per tile (thread 0):");
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], tot[i] / (double)n_tiles);
+        fprintf(stderr, "\n");
+        cudaFree(prof);
+    } else {
+        mp_edge_bwd_tc_kernel<<<grid, MB_NW + 128, MB_SMEM, stream>>>(a);
+    }
     RGNN_CHECK_CUDA(cudaGetLastError());
     int rc;
     // dW_2 (cn x h) = dz2^T y1:  D[m = input channel of msg.1][n = output channel] -> dst[n * h + m];  db_2 = column sums of dz2
