@@ -209,26 +209,14 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             cp_async_commit();
         };
 
-        int t_my = -1, s_my = -1;
-        if ((int)blockIdx.x < n_tiles) {
-            load_idx(blockIdx.x, t_my, s_my);
-            stage_emb(blockIdx.x);
-            stage_ps(s_my);
-        }
-        uint32_t phase = 0;
-        long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-        const bool profiling = a.prof != nullptr && tid == 0;
-        auto tick = [&](int i) {
-            if (profiling) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
-        };
-        if (profiling) tlast = clock64();
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-            const int e_my = tile * TM + row;
-            const bool valid = e_my < a.n_edges;
-            const int next = tile + (int)gridDim.x;
-            const bool has_next = next < n_tiles;
-
-            // ---- phase 0: emb rows -> TMEM (hi | lo) as the A operand of G1 ----
+        int t_my = -1, s_my = -1;       // target of this thread's edge row / source of the row it stages, for the tile in `prepare`
+        int n_s = -1;                   // source ids of the tile after that (P_s rows are staged after epilogue 1)
+        float2 z[H / 4];                // this thread's half of the hoisted target projection P_t[tgt] (H/2 floats)
+        // Everything a tile needs before G1 can be issued.  It runs while G4 of the PREVIOUS tile executes: the emb operand
+        // goes to TMEM columns [384, 512), which no MMA touches between G3 and the next G1.
+        auto prepare = [&](int tile) {
+            const int e = tile * TM + row;
+            const bool v_ok = e < a.n_edges;
             cp_async_wait<0>();
             group_sync(BAR_WORKERS, NW);            // this tile's emb and P_s rows have landed (every thread's copies)
 #pragma unroll
@@ -239,7 +227,7 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
                 float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}, hi[8], lo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (!valid) v[j] = 0.f;
+                    if (!v_ok) v[j] = 0.f;
                     tc::split_tf32(v[j], hi[j], lo[j]);
                 }
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -249,28 +237,49 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
                              ::"r"(t_row + MB_COL_ELO + q * (CE / 2) + 8 * c8), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]), "f"(lo[4]),
                                "f"(lo[5]), "f"(lo[6]), "f"(lo[7]) : "memory");
             }
-            tc::tmem_wait_st();
-            tc::tc_fence_before();
-            bar_arrive(BAR_Y_READY, NMMA);          // -> G1
-            tick(0);
-
-            // while G1 runs: the hoisted target projection of this row, the next tile's indices and emb rows
-            float2 z[H / 4];                        // this thread's half row: H/2 floats
             {
-                const float* Pt = a.P + (size_t)(valid ? t_my : 0) * (2 * H) + q * (H / 2);
+                const float* Pt = a.P + (size_t)(v_ok ? t_my : 0) * (2 * H) + q * (H / 2);
 #pragma unroll
                 for (int c8 = 0; c8 < H / 2 / 8; ++c8) {
                     z[4 * c8] = z[4 * c8 + 1] = z[4 * c8 + 2] = z[4 * c8 + 3] = make_float2(0.f, 0.f);
-                    if (valid) ldg256(Pt + 8 * c8, z[4 * c8], z[4 * c8 + 1], z[4 * c8 + 2], z[4 * c8 + 3]);
+                    if (v_ok) ldg256(Pt + 8 * c8, z[4 * c8], z[4 * c8 + 1], z[4 * c8 + 2], z[4 * c8 + 3]);
                 }
             }
-            int n_t = -1, n_s = -1;
-            if (has_next) load_idx(next, n_t, n_s);
+            const int nx = tile + (int)gridDim.x;
+            int n_t = -1;
+            n_s = -1;
+            if (nx < n_tiles) load_idx(nx, n_t, n_s);
             group_sync(BAR_WORKERS, NW);            // everyone has read its emb row: the staging tile may be refilled
-            if (has_next) stage_emb(next);
+            if (nx < n_tiles) stage_emb(nx);
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            return n_t;
+        };
+        uint32_t phase = 0;
+        long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+        const bool profiling = a.prof != nullptr && tid == 0;
+        auto tick = [&](int i) {
+            if (profiling) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
+        };
+        if (profiling) tlast = clock64();
+        int t_next = -1;
+        if ((int)blockIdx.x < n_tiles) {
+            load_idx(blockIdx.x, t_my, s_my);
+            stage_emb(blockIdx.x);
+            stage_ps(s_my);
+            t_next = prepare(blockIdx.x);
+        }
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
+            const int e_my = tile * TM + row;
+            const bool valid = e_my < a.n_edges;
+            const int next = tile + (int)gridDim.x;
+            const bool has_next = next < n_tiles;
+            const int t_cur = t_my;                 // dagg[target] is gathered in epilogue 2
+            bar_arrive(BAR_Y_READY, NMMA);          // -> G1 (operand written by prepare())
+            tick(0);
+            tick(1);
 
             // ---- epilogue 1: z1 = D1 + P_t + P_s -> norm -> act -> y1 (TMEM hi | lo, and the scratch buffer) ----
-            tick(1);
             tc::mbar_wait(&bars[0], phase);
             tc::tc_fence_after();
             tick(2);
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             // while G2 runs: d(message) = dagg[target] for this thread's half row; next tile's P_s rows
             float2 g2[CN / 4];
             {
-                const float* dg = a.dagg + (size_t)(valid ? t_my : 0) * CN + q * (CN / 2);
+                const float* dg = a.dagg + (size_t)(valid ? t_cur : 0) * CN + q * (CN / 2);
 #pragma unroll
                 for (int c8 = 0; c8 < CN / 2 / 8; ++c8) {
                     g2[4 * c8] = g2[4 * c8 + 1] = g2[4 * c8 + 2] = g2[4 * c8 + 3] = make_float2(0.f, 0.f);
@@ -379,32 +388,32 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
                     inv_den = 1.f / (sd2 + NORM_EPS);
                     k = s2v / (sd2 + NORM_EPS);
                 }
-                // g2 := d(pre-activation); with a norm: dn = s * g, nv = c * inv_den
-                float ps = 0.f, pm = 0.f, sum_dn = 0.f, dot = 0.f;
+                // g2 := d(pre-activation); with a norm: dn = s * g, nv = c * inv_den   (packed f32x2: instruction-bound)
+                const float2 k2 = make_float2(k, k), m22 = make_float2(m2v, m2v), id2 = make_float2(inv_den, inv_den);
+                const float2 s22 = make_float2(s2v, s2v);
+                float2 ps2 = make_float2(0.f, 0.f), pm2 = ps2, sum2 = ps2, dot2 = ps2;
 #pragma unroll
                 for (int c = 0; c < CN / 4; ++c) {
-                    const float yx = norm2 ? fmaf(c2[c].x, k, m2v) : c2[c].x, yy = norm2 ? fmaf(c2[c].y, k, m2v) : c2[c].y;
-                    if (act2 && !(yx > 0.f)) g2[c].x *= LEAKY;
-                    if (act2 && !(yy > 0.f)) g2[c].y *= LEAKY;
+                    const float2 y = norm2 ? __ffma2_rn(c2[c], k2, m22) : c2[c];
+                    g2[c] = __fmul2_rn(g2[c], make_float2((!act2 || y.x > 0.f) ? 1.f : LEAKY, (!act2 || y.y > 0.f) ? 1.f : LEAKY));
                     if (norm2) {
-                        c2[c].x *= inv_den; c2[c].y *= inv_den;      // nv
-                        ps = fmaf(g2[c].x, c2[c].x, ps); ps = fmaf(g2[c].y, c2[c].y, ps);
-                        pm += g2[c].x + g2[c].y;
-                        g2[c].x *= s2v; g2[c].y *= s2v;              // dn
-                        sum_dn += g2[c].x + g2[c].y;
-                        dot = fmaf(g2[c].x, c2[c].x, dot); dot = fmaf(g2[c].y, c2[c].y, dot);
+                        c2[c] = __fmul2_rn(c2[c], id2);              // nv
+                        ps2 = __ffma2_rn(g2[c], c2[c], ps2);
+                        pm2 = __fadd2_rn(pm2, g2[c]);
+                        g2[c] = __fmul2_rn(g2[c], s22);              // dn
+                        sum2 = __fadd2_rn(sum2, g2[c]);
+                        dot2 = __ffma2_rn(g2[c], c2[c], dot2);
                     }
                 }
                 if (norm2) {
-                    if (valid) { acc_s2 += (double)ps; acc_m2 += (double)pm; }
+                    if (valid) { acc_s2 += (double)(ps2.x + ps2.y); acc_m2 += (double)(pm2.x + pm2.y); }
+                    float sum_dn = sum2.x + sum2.y, dot = dot2.x + dot2.y;
                     row_allreduce2(sum_dn, dot, t_row + MB_COL_D3 + 8, q, bar_id);
                     const float mean_dn = sum_dn / (float)CN;
                     const float coef = sd2 > 0.f ? dot / ((float)(CN - 1) * sd2) : 0.f;
+                    const float2 nm2 = make_float2(-mean_dn, -mean_dn), nc2 = make_float2(-coef, -coef);
 #pragma unroll
-                    for (int c = 0; c < CN / 4; ++c) {
-                        g2[c].x = (g2[c].x - mean_dn) * inv_den - c2[c].x * coef;
-                        g2[c].y = (g2[c].y - mean_dn) * inv_den - c2[c].y * coef;
-                    }
+                    for (int c = 0; c < CN / 4; ++c) g2[c] = __ffma2_rn(c2[c], nc2, __fmul2_rn(__fadd2_rn(g2[c], nm2), id2));
                 }
             }
 #pragma unroll
@@ -440,71 +449,68 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
             tc::tc_fence_after();
             tick(6);
             {
-                // one 16-column block: g := d(pre-activation) (times the norm scale when there is a norm), nv := normalised value
-                auto block = [&](int c, float2 (&g)[8], float2 (&nv)[8]) {
+                // single pass: dn (= d pre-activation, times the norm scale) and nv (= normalised value recovered from y1) of this
+                // thread's half row stay in registers between the row reduction and the final formula (packed f32x2 math)
+                float2 dn[H / 4], nv[H / 4];
+                const float2 is2 = make_float2(inv_s1, inv_s1), nsh2 = make_float2(-m1v * inv_s1, -m1v * inv_s1);
+                const float2 s12 = make_float2(s1v, s1v);
+                float2 ps2 = make_float2(0.f, 0.f), pm2 = ps2, sum2 = ps2, dot2 = ps2;
+#pragma unroll
+                for (int c = 0; c < H / 2; c += 16) {
                     float2 yh[8], yl[8];
-                    tc::tmem_ld16(t_row + MB_COL_D3 + q * (H / 2) + c, g);
+                    tc::tmem_ld16(t_row + MB_COL_D3 + q * (H / 2) + c, dn + c / 2);
                     tc::tmem_ld16(t_row + MB_COL_Y + q * (H / 2) + c, yh);
                     tc::tmem_ld16(t_row + MB_COL_YLO + q * (H / 2) + c, yl);
                     tc::tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float2 y = __fadd2_rn(yh[j], yl[j]);
-                        const bool px = !act1 || y.x > 0.f, py = !act1 || y.y > 0.f;
-                        if (!px) g[j].x *= LEAKY;
-                        if (!py) g[j].y *= LEAKY;
-                        nv[j].x = ((px ? y.x : y.x / LEAKY) - m1v) * inv_s1;
-                        nv[j].y = ((py ? y.y : y.y / LEAKY) - m1v) * inv_s1;
-                    }
-                };
-                float sum_dn = 0.f, dot = 0.f, mean_dn = 0.f, coef = 0.f;
-                const float inv_den = 1.f / (sd1 + NORM_EPS);
-                if (norm1) {
-                    float ps = 0.f, pm = 0.f;
-#pragma unroll 1
-                    for (int c = 0; c < H / 2; c += 16) {
-                        float2 g[8], nv[8];
-                        block(c, g, nv);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            ps = fmaf(g[j].x, nv[j].x, ps); ps = fmaf(g[j].y, nv[j].y, ps);
-                            pm += g[j].x + g[j].y;
-                            const float dx = g[j].x * s1v, dy = g[j].y * s1v;
-                            sum_dn += dx + dy;
-                            dot = fmaf(dx, nv[j].x, dot); dot = fmaf(dy, nv[j].y, dot);
+                        float2& g = dn[c / 2 + j];
+                        act_bwd_pair(g, nv[c / 2 + j], __fadd2_rn(yh[j], yl[j]), act1, is2, nsh2);
+                        if (norm1) {
+                            ps2 = __ffma2_rn(g, nv[c / 2 + j], ps2);
+                            pm2 = __fadd2_rn(pm2, g);
+                            g = __fmul2_rn(g, s12);
+                            sum2 = __fadd2_rn(sum2, g);
+                            dot2 = __ffma2_rn(g, nv[c / 2 + j], dot2);
                         }
                     }
-                    if (valid) { acc_s1 += (double)ps; acc_m1 += (double)pm; }
-                    row_allreduce2(sum_dn, dot, t_row + MB_COL_Z2LO, q, bar_id);
-                    mean_dn = sum_dn / (float)H;
-                    coef = sd1 > 0.f ? dot / ((float)(H - 1) * sd1) : 0.f;
                 }
-#pragma unroll 1
+                if (norm1) {
+                    if (valid) { acc_s1 += (double)(ps2.x + ps2.y); acc_m1 += (double)(pm2.x + pm2.y); }
+                    float sum_dn = sum2.x + sum2.y, dot = dot2.x + dot2.y;
+                    row_allreduce2(sum_dn, dot, t_row + MB_COL_Z2LO, q, bar_id);
+                    const float inv_den = 1.f / (sd1 + NORM_EPS);
+                    const float mean_dn = sum_dn / (float)H;
+                    const float coef = sd1 > 0.f ? dot / ((float)(H - 1) * sd1) : 0.f;
+                    const float2 nm2 = make_float2(-mean_dn, -mean_dn), id2 = make_float2(inv_den, inv_den), nc2 = make_float2(-coef, -coef);
+#pragma unroll
+                    for (int c = 0; c < H / 4; ++c) dn[c] = __ffma2_rn(nv[c], nc2, __fmul2_rn(__fadd2_rn(dn[c], nm2), id2));
+                }
+#pragma unroll
                 for (int c = 0; c < H / 2; c += 16) {
-                    float2 g[8], nv[8], hi[8], lo[8];
-                    block(c, g, nv);
-                    if (norm1) {
+                    float2 hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            g[j].x = (g[j].x * s1v - mean_dn) * inv_den - nv[j].x * coef;
-                            g[j].y = (g[j].y * s1v - mean_dn) * inv_den - nv[j].y * coef;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) tc::split_tf32(g[j], hi[j], lo[j]);
+                    for (int j = 0; j < 8; ++j) tc::split_tf32(dn[c / 2 + j], hi[j], lo[j]);
                     tc::tmem_st16(t_row + MB_COL_Y + q * (H / 2) + c, hi);
                     tc::tmem_st16(t_row + MB_COL_YLO + q * (H / 2) + c, lo);
-                    if (valid) {
-                        float* o = a.dz1_out + (size_t)e_my * H + q * (H / 2) + c;
-                        stg256(o, g[0], g[1], g[2], g[3]);
-                        stg256(o + 8, g[4], g[5], g[6], g[7]);
-                    }
+                }
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                bar_arrive(BAR_Y_READY, NMMA);          // -> G4
+                if (valid) {
+                    float* o = a.dz1_out + (size_t)e_my * H + q * (H / 2);
+#pragma unroll
+                    for (int c8 = 0; c8 < H / 2 / 8; ++c8) stg256(o + 8 * c8, dn[4 * c8], dn[4 * c8 + 1], dn[4 * c8 + 2], dn[4 * c8 + 3]);
                 }
             }
-            tc::tmem_wait_st();
-            tc::tc_fence_before();
-            bar_arrive(BAR_Y_READY, NMMA);          // -> G4
 
+
+            // ---- while G4 runs: the next tile's operand, projection rows, indices (see prepare) ----
+            if (has_next) {
+                if (!norm1) group_sync(bar_id, 64);     // the row partner has finished reading D3 (with a norm: row_allreduce2 did that)
+                t_my = t_next;
+                t_next = prepare(next);
+            }
             // ---- epilogue 4: d(emb) (+)= D4 ----
             tick(7);
             tc::mbar_wait(&bars[3], phase);
@@ -524,7 +530,6 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
                 }
             }
             tc::tc_fence_before();
-            t_my = n_t; s_my = n_s;
             tick(9);
         }
         if (profiling)

@@ -127,7 +127,11 @@ __device__ __forceinline__ void finish_columns(float2 (&z)[CP], const TcEpi& e, 
         }
     } else if (e.store != nullptr && valid) {
         float* o = e.store + (size_t)row_g * e.store_ld + col0;
-        if (((e.store_ld | e.store_w) & 3) == 0) {
+        if (CP % 4 == 0 && ((e.store_ld | e.store_w) & 7) == 0 && (reinterpret_cast<uintptr_t>(e.store) & 31) == 0) {
+#pragma unroll
+            for (int c = 0; c + 3 < CP; c += 4)      // full 32-byte sectors per lane
+                if (col0 + 2 * c < e.store_w) stg256(o + 2 * c, z[c], z[c + 1], z[c + 2], z[c + 3]);
+        } else if (((e.store_ld | e.store_w) & 3) == 0) {
 #pragma unroll
             for (int c = 0; c < CP; c += 2)
                 if (col0 + 2 * c < e.store_w) *reinterpret_cast<float4*>(o + 2 * c) = make_float4(z[c].x, z[c].y, z[c + 1].x, z[c + 1].y);
@@ -203,30 +207,29 @@ __device__ __forceinline__ void bwd_transform(float2 (&g)[CPT / 2], const float2
         return;
     }
     const float inv_scale = scale != 0.f ? 1.f / scale : 0.f;
-    float sum_dn = 0.f, dot = 0.f;
+    const float2 is2 = make_float2(inv_scale, inv_scale), nsh2 = make_float2(-shift * inv_scale, -shift * inv_scale);
+    const float2 sc2 = make_float2(scale, scale);
+    float2 ps2 = make_float2(0.f, 0.f), pm2 = ps2, sum2 = ps2, dot2 = ps2;
     float2 nv[CPT / 2];
 #pragma unroll
-    for (int c = 0; c < CPT / 2; ++c) {
-        const bool px = !act || y[c].x > 0.f, py = !act || y[c].y > 0.f;
-        if (!px) g[c].x *= LEAKY;
-        if (!py) g[c].y *= LEAKY;
-        nv[c].x = ((px ? y[c].x : y[c].x / LEAKY) - shift) * inv_scale;
-        nv[c].y = ((py ? y[c].y : y[c].y / LEAKY) - shift) * inv_scale;
-        ps = fmaf(g[c].x, nv[c].x, ps); ps = fmaf(g[c].y, nv[c].y, ps);
-        pm += g[c].x + g[c].y;
-        g[c].x *= scale; g[c].y *= scale;
-        sum_dn += g[c].x + g[c].y;
-        dot = fmaf(g[c].x, nv[c].x, dot); dot = fmaf(g[c].y, nv[c].y, dot);
+    for (int c = 0; c < CPT / 2; ++c) {       // packed f32x2 throughout: the epilogue is instruction-bound (8 worker warps per SM)
+        act_bwd_pair(g[c], nv[c], y[c], act, is2, nsh2);
+        ps2 = __ffma2_rn(g[c], nv[c], ps2);
+        pm2 = __fadd2_rn(pm2, g[c]);
+        g[c] = __fmul2_rn(g[c], sc2);
+        sum2 = __fadd2_rn(sum2, g[c]);
+        dot2 = __ffma2_rn(g[c], nv[c], dot2);
     }
+    ps = ps2.x + ps2.y;
+    pm = pm2.x + pm2.y;
+    float sum_dn = sum2.x + sum2.y, dot = dot2.x + dot2.y;
     row_allreduce2(sum_dn, dot, t_xs, q, bar_id);
     const float inv_den = 1.f / (sd + NORM_EPS);
     const float mean_dn = sum_dn / (float)n_true;
     const float coef = sd > 0.f ? dot / ((float)(n_true - 1) * sd) : 0.f;
+    const float2 nm2 = make_float2(-mean_dn, -mean_dn), id2 = make_float2(inv_den, inv_den), nc2 = make_float2(-coef, -coef);
 #pragma unroll
-    for (int c = 0; c < CPT / 2; ++c) {
-        g[c].x = (g[c].x - mean_dn) * inv_den - nv[c].x * coef;
-        g[c].y = (g[c].y - mean_dn) * inv_den - nv[c].y * coef;
-    }
+    for (int c = 0; c < CPT / 2; ++c) g[c] = __ffma2_rn(nv[c], nc2, __fmul2_rn(__fadd2_rn(g[c], nm2), id2));
 }
 
 // forward output columns of this thread's row (32-byte loads: y_ld and col0 are multiples of 8)
@@ -255,9 +258,19 @@ __device__ __forceinline__ void pool_scalar_grads(float ps, float pm, bool valid
 }
 
 // backward epilogue of a stage: D = d(layer output) -> dz = norm'(act'(D)) -> store / next A operand
+struct BwdScalars { float scale, shift, sd; };
+__device__ __forceinline__ BwdScalars load_bwd_scalars(const TcBwd& b, int row_g, bool valid) {
+    BwdScalars r;
+    const bool norm = b.scale != nullptr;
+    r.scale = norm ? __ldg(b.scale) : 1.f;
+    r.shift = norm ? __ldg(b.shift) : 0.f;
+    r.sd = (norm && valid) ? __ldg(b.sd + row_g) : 0.f;
+    return r;
+}
+
 template <int CPT>
 __device__ __forceinline__ void epilogue_bwd(const TcEpi& e, int row_g, bool valid, int q, uint32_t t_row, int bar_id,
-                                             const float2 (&y)[CPT / 2], double* dacc, int lane) {
+                                             const float2 (&y)[CPT / 2], const BwdScalars& bs, double* dacc, int lane) {
     float2 z[CPT / 2];
     const int col0 = q * CPT;
 #pragma unroll
@@ -265,8 +278,7 @@ __device__ __forceinline__ void epilogue_bwd(const TcEpi& e, int row_g, bool val
     tc::tmem_wait_ld();
     const TcBwd& b = e.bwd;
     const bool norm = b.scale != nullptr;
-    const float scale = norm ? __ldg(b.scale) : 1.f, shift = norm ? __ldg(b.shift) : 0.f;
-    const float sd = (norm && valid) ? __ldg(b.sd + row_g) : 0.f;
+    const float scale = bs.scale, shift = bs.shift, sd = bs.sd;
     float ps, pm;
     bwd_transform<CPT>(z, y, b, e.n_true, b.y != nullptr || b.lin0 != 0, scale, shift, sd, t_row + TC_XS_COL + 4, q, bar_id, ps, pm);
     if (norm && b.g_scale != nullptr) pool_scalar_grads(ps, pm, valid, dacc, lane);
@@ -641,6 +653,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                     // the saved forward rows are requested BEFORE waiting for the accumulator: their L2 / HBM round trip
                     // overlaps the MMAs of this stage
                     const int cpt = e.n_cols / RM_NQ;
+                    const BwdScalars bs = load_bwd_scalars(e.bwd, row_g, valid);
                     auto wait_d = [&]() {
                         tc::mbar_wait(d_ready, dphase);
                         dphase ^= 1u;
@@ -656,22 +669,22 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
                             for (int c8 = 0; c8 < 8; ++c8) stg256(o + 8 * c8, y[4 * c8], y[4 * c8 + 1], y[4 * c8 + 2], y[4 * c8 + 3]);
                         }
                         wait_d();
-                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, bs, dacc + 2 * s, lane);
                     } else if (cpt == 64) {
                         float2 y[32];
                         load_y<64>(y, e.bwd, row_g, valid, q * 64);
                         wait_d();
-                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                        epilogue_bwd<64>(e, row_g, valid, q, t_row, bar_id, y, bs, dacc + 2 * s, lane);
                     } else if (cpt == 32) {
                         float2 y[16];
                         load_y<32>(y, e.bwd, row_g, valid, q * 32);
                         wait_d();
-                        epilogue_bwd<32>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                        epilogue_bwd<32>(e, row_g, valid, q, t_row, bar_id, y, bs, dacc + 2 * s, lane);
                     } else {
                         float2 y[8];
                         load_y<16>(y, e.bwd, row_g, valid, q * 16);
                         wait_d();
-                        epilogue_bwd<16>(e, row_g, valid, q, t_row, bar_id, y, dacc + 2 * s, lane);
+                        epilogue_bwd<16>(e, row_g, valid, q, t_row, bar_id, y, bs, dacc + 2 * s, lane);
                     }
                     tc::tmem_wait_st();
                     tc::tc_fence_before();

@@ -78,6 +78,14 @@ __device__ __forceinline__ void row_allreduce2(float& u, float& v, uint32_t t_co
     v = p1 + p3;
 }
 
+// Backward of LeakyReLU + the inverse of the scalar affine for one register pair (packed f32x2):
+//   g <- g * act'(y),   nv <- (act^-1(y) - shift) / scale     with y the layer output, neg_shift_is = -shift / scale
+__device__ __forceinline__ void act_bwd_pair(float2& g, float2& nv, float2 y, bool act, float2 inv_scale2, float2 neg_shift_is) {
+    const bool px = !act || y.x > 0.f, py = !act || y.y > 0.f;
+    g = __fmul2_rn(g, make_float2(px ? 1.f : LEAKY, py ? 1.f : LEAKY));
+    nv = __ffma2_rn(__fmul2_rn(y, make_float2(px ? 1.f : 1.f / LEAKY, py ? 1.f : 1.f / LEAKY)), inv_scale2, neg_shift_is);
+}
+
 __device__ __forceinline__ void stg256(float* p, float2 a, float2 b, float2 c, float2 d) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y)
