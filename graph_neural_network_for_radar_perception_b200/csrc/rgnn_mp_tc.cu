@@ -47,6 +47,7 @@ extern int g_rowmlp_profile;
 static int g_tf32_passes = 3;
 static int g_use_tensor_cores = 1;
 static int g_use_tensor_cores_bwd = 1;
+static int g_wgrad_tma = 1;
 static int g_debug = 0;
 
 template <int CE, int H, int CN, int NQ>
@@ -545,6 +546,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     if (name != nullptr && strcmp(name, "tf32_passes") == 0 && (value == 1 || value == 3)) { g_tf32_passes = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores_bwd = value; return RGNN_OK; }
+    if (name != nullptr && strcmp(name, "wgrad_tma") == 0 && (value == 0 || value == 1)) { g_wgrad_tma = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; g_rowmlp_profile = (value & 8) != 0; return RGNN_OK; }
     set_error("rgnn_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
     return RGNN_ERR_INVALID;
@@ -555,5 +557,6 @@ extern "C" int rgnn_get_option(const char* name) {
     if (name != nullptr && strcmp(name, "tf32_passes") == 0) return g_tf32_passes;
     if (name != nullptr && strcmp(name, "tensor_cores") == 0) return g_use_tensor_cores;
     if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0) return g_use_tensor_cores_bwd;
+    if (name != nullptr && strcmp(name, "wgrad_tma") == 0) return g_wgrad_tma;
     return -1;
 }
