@@ -97,6 +97,7 @@ SIGNATURES = {
     'rgnn_losses_fwdbwd': (_I, [C.POINTER(rgnn_loss_cfg), _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I,
                                 C.c_double, C.c_double, C.c_double, _V, _V, _V, _V, _V, _V, _V]),
     'rgnn_sgd_step': (_I, [_V, _V, _V, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, _I, _V]),
+    'rgnn_sgd_step_guarded': (_I, [_V, _V, _V, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, _I, _V, _V]),
 }
 
 _lib = None

@@ -124,7 +124,13 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
 }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, size_t n, float lr,
-                           float mu, float wd, float gscale, int first) {
+                           float mu, float wd, float gscale, int first, const float* __restrict__ skip) {
+    // device-side version of the reference's skip_batch (gnn/training.py:40-45): a non-zero or NaN flag leaves parameters
+    // and momentum untouched, without the host ever reading the loss
+    if (skip != nullptr) {
+        const float f = __ldg(skip);
+        if (f != 0.f || f != f) return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float pi = p[i];
         const float gi = fmaf(wd, pi, g[i] * gscale);
@@ -174,7 +180,18 @@ extern "C" int rgnn_sgd_step(float* params, const float* grads, float* momentum_
     if (n == 0) return RGNN_OK;
     size_t grid = (n + 255) / 256;
     if (grid > (size_t)4 * sm_count()) grid = (size_t)4 * sm_count();
-    sgd_kernel<<<(unsigned)grid, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step);
+    sgd_kernel<<<(unsigned)grid, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, nullptr);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+extern "C" int rgnn_sgd_step_guarded(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
+                                     float weight_decay, float grad_scale, int first_step, const float* skip_flag, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return RGNN_OK;
+    size_t grid = (n + 255) / 256;
+    if (grid > (size_t)4 * sm_count()) grid = (size_t)4 * sm_count();
+    sgd_kernel<<<(unsigned)grid, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, skip_flag);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }

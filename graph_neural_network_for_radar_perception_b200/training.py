@@ -80,7 +80,9 @@ class FlatBuffers:
             total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.params = params
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # one extra slot behind the gradients: the "skip this batch" flag (NaN loss on any rank), all-reduced with them
+        self.flat_grad = torch.zeros(total + self.ALIGN, dtype=torch.float32, device=dev)
+        self.skip_flag = self.flat_grad[total:total + 1]
         self.momentum = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, off in zip(params, self.offsets):
             n = p.numel()
@@ -135,10 +137,184 @@ class DataParallelTrainer:
         loss, acc = self.model.forward_packed(gb, node_features, edge_features, labels)
         total = loss['loss_node_cls'] + loss['loss_node_reg'] + loss['loss_edge_cls'] + loss['loss_obj_cls']
         total.backward()
-        allreduce_flat_(self.buffers.flat_grad, self.group)
         b = self.buffers
-        check(lib().rgnn_sgd_step(ptr(b.flat_param), ptr(b.flat_grad), ptr(b.momentum), b.numel,
-                                  self.lr if lr is None else float(lr), self.mu, self.wd, 1.0,
-                                  1 if self.steps == 0 else 0, stream_ptr()), 'rgnn_sgd_step')
+        # reference skip_batch (gnn/training.py:40-45,79-84): a NaN loss on ANY rank skips the update on every rank; the flag
+        # rides behind the gradients through the all-reduce, nothing is read back to the host
+        b.skip_flag.copy_(torch.isnan(total.detach()).to(torch.float32).reshape(1))
+        allreduce_flat_(b.flat_grad, self.group)
+        check(lib().rgnn_sgd_step_guarded(ptr(b.flat_param), ptr(b.flat_grad), ptr(b.momentum), b.numel,
+                                          self.lr if lr is None else float(lr), self.mu, self.wd, 1.0,
+                                          1 if self.steps == 0 else 0, ptr(b.skip_flag), stream_ptr()), 'rgnn_sgd_step_guarded')
         self.steps += 1
         return loss, acc
+
+    # ---- optimizer-state checkpointing (the reference saves only detector.state_dict(), training.py:16-18) ----
+    def state_dict(self) -> Dict[str, object]:
+        return {'momentum': self.buffers.momentum.detach().cpu().clone(), 'steps': self.steps, 'lr': self.lr,
+                'momentum_coef': self.mu, 'weight_decay': self.wd, 'numel': self.buffers.numel}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        if int(sd['numel']) != self.buffers.numel:
+            raise ValueError(f"optimizer state for {sd['numel']} flat parameters, model has {self.buffers.numel}")
+        self.buffers.momentum.copy_(sd['momentum'].to(self.buffers.momentum.device))
+        self.steps, self.lr = int(sd['steps']), float(sd['lr'])
+        self.mu, self.wd = float(sd['momentum_coef']), float(sd['weight_decay'])
+
+
+# -------------------------------------------------------------------------------------------------
+# loss / accuracy tracking without per-step host syncs, and the reference's training loop on top of the trainer
+# -------------------------------------------------------------------------------------------------
+class _DeviceSeries:
+    """Append-only list of 0-dim device tensors; the mean over the entries whose weight is non-zero is taken in ONE
+    device-to-host read (the reference calls .item() on every value of every step, training.py:353-365)."""
+
+    def __init__(self):
+        self.values: List[torch.Tensor] = []
+        self.weights: List[torch.Tensor] = []
+
+    def append(self, value: torch.Tensor, weight: Optional[torch.Tensor] = None) -> None:
+        v = value.detach().to(torch.float64).reshape(())
+        self.values.append(v)
+        self.weights.append(torch.ones_like(v) if weight is None else weight.detach().to(torch.float64).reshape(()))
+
+    def mean(self) -> float:
+        if not self.values:
+            return float('nan')
+        v, w = torch.stack(self.values), torch.stack(self.weights)
+        ws = w.sum()
+        m = torch.where(ws > 0, torch.where(w > 0, v, torch.zeros_like(v)).sum() / ws.clamp_min(1e-30), torch.full_like(ws, float('nan')))
+        return float(m.item())          # the one device-to-host read
+
+    def reset(self) -> None:
+        self.values, self.weights = [], []
+
+    def tolist(self) -> List[float]:
+        return torch.stack(self.values).cpu().tolist() if self.values else []
+
+
+_LOSS_KEYS = ('loss_node_cls', 'loss_node_reg', 'loss_edge_cls', 'loss_obj_cls')
+
+
+class LossTracker:
+    """Reference interface (gnn/training.py:336-400); entries are kept on the device.  The reference only records steps
+    with `total_loss > 0` (training.py:89): here that test is a device-side weight."""
+
+    def __init__(self):
+        self._history = _DeviceSeries()
+        self._train = {k: _DeviceSeries() for k in ('total',) + _LOSS_KEYS}
+        self._val = {k: _DeviceSeries() for k in ('total',) + _LOSS_KEYS}
+
+    @property
+    def loss_history(self) -> List[float]:
+        return self._history.tolist()
+
+    @staticmethod
+    def _append(series, total_loss, losses):
+        w = (total_loss.detach() > 0).to(torch.float64)
+        series['total'].append(total_loss, w)
+        for k in _LOSS_KEYS:
+            series[k].append(losses[k], w)
+
+    def append_training_loss_for_tb(self, total_loss, losses):
+        self._append(self._train, total_loss, losses)
+        self._history.append(total_loss)
+
+    def append_validation_loss_for_tb(self, total_loss, losses):
+        self._append(self._val, total_loss, losses)
+
+    def reset_training_loss_for_tb(self):
+        for s in self._train.values():
+            s.reset()
+
+    def reset_validation_loss_for_tb(self):
+        for s in self._val.values():
+            s.reset()
+
+    def compute_avg_training_loss(self):
+        return tuple(self._train[k].mean() for k in ('total',) + _LOSS_KEYS)
+
+    def compute_avg_val_loss(self):
+        return tuple(self._val[k].mean() for k in ('total',) + _LOSS_KEYS)
+
+
+_ACC_KEYS = ('segment_accuracy', 'edge_accuracy', 'object_accuracy')
+
+
+class AccuracyTracker:
+    """Reference interface (gnn/training.py:403-450), device-side like LossTracker."""
+
+    def __init__(self):
+        self._train = {k: _DeviceSeries() for k in _ACC_KEYS}
+        self._val = {k: _DeviceSeries() for k in _ACC_KEYS}
+
+    def append_training_acc_for_tb(self, accuracy):
+        for k in _ACC_KEYS:
+            self._train[k].append(accuracy[k])
+
+    def append_validation_acc_for_tb(self, accuracy):
+        for k in _ACC_KEYS:
+            self._val[k].append(accuracy[k])
+
+    def reset_training_acc_for_tb(self):
+        for s in self._train.values():
+            s.reset()
+
+    def reset_validation_acc_for_tb(self):
+        for s in self._val.values():
+            s.reset()
+
+    def compute_avg_training_acc(self):
+        return tuple(self._train[k].mean() for k in _ACC_KEYS)
+
+    def compute_avg_val_acc(self):
+        return tuple(self._val[k].mean() for k in _ACC_KEYS)
+
+
+def train_model(detector, trainer: DataParallelTrainer, lr_milestones: Sequence[int], dataloader_train, dataloader_val, tb_writer,
+                max_iters: int, log_period: int, val_period: int, iter_start_offset: int = 0, save_fn=None, base_lr: Optional[float] = None):
+    """The reference's `train_model` (gnn/training.py:48-186) on top of DataParallelTrainer: same iteration structure, logging
+    and validation cadence, but no host synchronisation inside a training step (no loss.item(), no isnan() on the host).
+    dataloader_*: iterables of (graph_features, labels) in the reference's collate format (datagen_gnn.py:143-190:
+    dict with 'node_features_dyn', 'edge_features_dyn', 'edge_index_dyn', 'adj_matrix_dyn').  tb_writer may be None;
+    save_fn(detector, trainer, iteration) is called where the reference saves weights."""
+    loss_tracker, acc_tracker = LossTracker(), AccuracyTracker()
+    base_lr = trainer.lr if base_lr is None else base_lr
+    it_train = iter(dataloader_train)
+    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    for it in range(iter_start_offset, max_iters):
+        graph_features, labels = next(it_train)
+        if graph_features is not None:
+            detector.train()
+            gb, nf, ef = detector.pack_batch(graph_features['node_features_dyn'], graph_features['edge_features_dyn'],
+                                             graph_features['edge_index_dyn'], labels['cluster_node_idx'])
+            loss, accuracy = trainer.step(gb, nf, ef, labels, lr=multistep_lr(base_lr, it, lr_milestones))
+            total = sum(loss.values())
+            loss_tracker.append_training_loss_for_tb(total, loss)
+            acc_tracker.append_training_acc_for_tb(accuracy)
+            if it % log_period == 0 and rank0:
+                print(f'[Iter {it}][loss: {float(total.detach()):.5f}]' + ''.join(f'[{k}: {float(v.detach()):.5f}]' for k, v in loss.items()))
+        if (it % val_period == 0) or (it == max_iters - 1):
+            if save_fn is not None and rank0:
+                save_fn(detector, trainer, it)
+            detector.eval()
+            with torch.no_grad():
+                for graph_features, labels in dataloader_val:
+                    if graph_features is None:
+                        continue
+                    loss, accuracy = detector(node_features=graph_features['node_features_dyn'],
+                                              edge_features=graph_features['edge_features_dyn'],
+                                              edge_index=graph_features['edge_index_dyn'],
+                                              adj_matrix=graph_features['adj_matrix_dyn'], labels=labels)
+                    loss_tracker.append_validation_loss_for_tb(sum(loss.values()), loss)
+                    acc_tracker.append_validation_acc_for_tb(accuracy)
+            tr, va = loss_tracker.compute_avg_training_loss(), loss_tracker.compute_avg_val_loss()
+            tra, vaa = acc_tracker.compute_avg_training_acc(), acc_tracker.compute_avg_val_acc()
+            if tb_writer is not None and rank0:
+                for name, i in (('Total_Loss', 0), ('Loss_Node_Segmentation', 1), ('Loss_Node_Offset', 2),
+                                ('Loss_Edge_Classification', 3), ('Loss_Object_Classification', 4)):
+                    tb_writer.add_scalars(name, {'train': tr[i], 'val': va[i]}, it)
+                for name, i in (('Acc_Node_Segmentation', 0), ('Acc_Edge_Classification', 1), ('Acc_Object_Classification', 2)):
+                    tb_writer.add_scalars(name, {'train': tra[i], 'val': vaa[i]}, it)
+            loss_tracker.reset_training_loss_for_tb(); loss_tracker.reset_validation_loss_for_tb()
+            acc_tracker.reset_training_acc_for_tb(); acc_tracker.reset_validation_acc_for_tb()
+    return loss_tracker

@@ -269,6 +269,11 @@ int rgnn_losses_fwdbwd(const rgnn_loss_cfg* cfg, const float* node_cls, const fl
  * grad_scale multiplies the (all-reduced) gradient first. */
 int rgnn_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, void* stream);
+/* Same, guarded by a device flag: when *skip_flag is non-zero or NaN nothing is written.  Replaces the host-side
+ * `skip_batch(total_loss)` / `torch.isnan(loss)` of the reference loop (gnn/training.py:40-45,79-84) without a
+ * device-to-host read per step; under data parallelism the flag travels inside the gradient all-reduce. */
+int rgnn_sgd_step_guarded(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
+                          float weight_decay, float grad_scale, int first_step, const float* skip_flag, void* stream);
 
 #ifdef __cplusplus
 }

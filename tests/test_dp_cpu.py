@@ -142,3 +142,22 @@ def test_two_rank_losses_and_gradients_add_up_to_the_single_process_batch(tmp_pa
             checked += 1
         off += k
     assert checked >= 8
+
+
+def test_device_side_trackers_match_reference_semantics():
+    """LossTracker / AccuracyTracker (reference gnn/training.py:336-450): means over the recorded steps, steps with
+    total_loss <= 0 are not recorded (training.py:89) -- here a device-side weight instead of a host-side `if`."""
+    lt, at = tr.LossTracker(), tr.AccuracyTracker()
+    steps = [(2.0, (0.5, 0.5, 0.5, 0.5)), (0.0, (0.0, 0.0, 0.0, 0.0)), (4.0, (1.0, 1.0, 1.0, 1.0))]
+    for total, parts in steps:
+        losses = {k: torch.tensor(v) for k, v in zip(('loss_node_cls', 'loss_node_reg', 'loss_edge_cls', 'loss_obj_cls'), parts)}
+        lt.append_training_loss_for_tb(torch.tensor(total), losses)
+        at.append_training_acc_for_tb({'segment_accuracy': torch.tensor(0.5), 'edge_accuracy': torch.tensor(1.0),
+                                       'object_accuracy': torch.tensor(total / 4)})
+    avg = lt.compute_avg_training_loss()
+    assert avg[0] == pytest.approx(3.0) and avg[1] == pytest.approx(0.75)        # the zero-loss step is excluded
+    assert lt.loss_history == [2.0, 0.0, 4.0]
+    assert at.compute_avg_training_acc() == pytest.approx((0.5, 1.0, 0.5))
+    lt.reset_training_loss_for_tb()
+    assert np.isnan(lt.compute_avg_training_loss()[0])
+    assert tr.multistep_lr(0.005, 10, [5, 20]) == pytest.approx(0.0005)

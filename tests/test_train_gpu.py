@@ -245,3 +245,80 @@ def test_hidden_width_32_forward_matches_oracle_and_training_fails_loudly():
     loss, _ = m.train()([nf.cuda()], [ef.cuda()], [ei.cuda()], [None], labels)
     with pytest.raises(RgnnError):
         sum(loss.values()).backward()
+
+
+def _tiny_loader(n_batches, seed0):
+    """Batches in the reference's collate format (datagen_gnn.py:143-190): dict of per-frame lists + labels dict."""
+    from graph_neural_network_for_radar_perception_b200 import synth
+    from oracle import graph_np
+    R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
+    out = []
+    for b in range(n_batches):
+        gfeat = {k: [] for k in ('node_features_dyn', 'edge_features_dyn', 'edge_index_dyn', 'adj_matrix_dyn')}
+        labels = {k: [] for k in ('cluster_node_idx', 'cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
+        for f in range(2):
+            d, src = synth.make_frame(seed0 + 10 * b + f, 80 + 20 * f)
+            adj = graph_np.adjacency_information(d, 25, 10)
+            lab = synth.make_labels(d, src, adj['adj_list'])
+            gfeat['node_features_dyn'].append(torch.from_numpy(graph_np.node_features(d, adj['degree'], True, 0, R, 0, np.pi * 0.5).astype(np.float32)).cuda())
+            gfeat['edge_features_dyn'].append(torch.from_numpy(graph_np.edge_features(d, adj['adj_list']).astype(np.float32)).cuda())
+            gfeat['edge_index_dyn'].append(torch.from_numpy(adj['adj_list']).cuda())
+            gfeat['adj_matrix_dyn'].append(None)
+            labels['cluster_node_idx'].append([torch.from_numpy(c).cuda() for c in lab['cluster_node_idx']])
+            for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets'):
+                labels[k].append(torch.from_numpy(lab[k]).cuda())
+        out.append((gfeat, labels))
+    return out
+
+
+def test_nan_batch_is_skipped_on_the_device_and_optimizer_state_round_trips(ckpt_state_dict):
+    """Row f1: the reference's skip_batch (training.py:40-45) as a device flag of the fused SGD kernel; trainer.state_dict()."""
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
+    m = load_model(ckpt_state_dict).train()
+    t = DataParallelTrainer(m)
+    (gf0, lab0), (gf1, lab1) = _tiny_loader(2, 300)
+
+    def step(trainer, model, gfeat, labels):
+        lb = {k: ([x.clone() for x in v] if k == 'node_offsets' else v) for k, v in labels.items()}
+        gb, nf, ef = model.pack_batch(gfeat['node_features_dyn'], gfeat['edge_features_dyn'], gfeat['edge_index_dyn'], lb['cluster_node_idx'])
+        return trainer.step(gb, nf, ef, lb)
+    step(t, m, gf0, lab0)
+    before = t.buffers.flat_param.clone()
+    mom_before = t.buffers.momentum.clone()
+    bad = dict(lab1)
+    bad['node_offsets'] = [x.clone() for x in lab1['node_offsets']]
+    bad['node_offsets'][0][3, 0] = float('nan')
+    loss, _ = step(t, m, gf1, bad)
+    assert bool(torch.isnan(sum(loss.values())))
+    assert torch.equal(t.buffers.flat_param, before) and torch.equal(t.buffers.momentum, mom_before)     # nothing was written
+    # checkpoint: a fresh trainer restored from (model, optimizer) state continues identically up to the summation order of
+    # the split-K weight-gradient reductions (red.global.add across CTAs; the reference's GPU scatter-add is unordered too)
+    sd_model = {k: v.clone() for k, v in m.state_dict().items()}
+    sd_opt = t.state_dict()
+    m2 = load_model(sd_model).train()
+    t2 = DataParallelTrainer(m2)
+    t2.load_state_dict(sd_opt)
+    step(t, m, gf1, lab1)
+    step(t2, m2, gf1, lab1)
+    assert torch.allclose(t.buffers.flat_param, t2.buffers.flat_param, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(t.buffers.momentum, t2.buffers.momentum, rtol=1e-4, atol=1e-7)
+    assert not torch.equal(t.buffers.flat_param, before)
+
+
+def test_train_model_loop_runs_without_per_step_host_reads(ckpt_state_dict):
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer, train_model
+    m = load_model(ckpt_state_dict).train()
+    t = DataParallelTrainer(m, lr=1e-3)
+    batches = _tiny_loader(3, 500)
+
+    def endless():
+        while True:
+            for b in batches:
+                yield (b[0], {k: ([x.clone() for x in v] if k == 'node_offsets' else v) for k, v in b[1].items()})
+    val = [(b[0], {k: ([x.clone() for x in v] if k == 'node_offsets' else v) for k, v in b[1].items()}) for b in batches[:1]]
+    saved = []
+    tracker = train_model(m, t, lr_milestones=[4], dataloader_train=endless(), dataloader_val=val, tb_writer=None, max_iters=6,
+                          log_period=100, val_period=5, save_fn=lambda det, trn, it: saved.append(it))
+    hist = tracker.loss_history
+    assert len(hist) == 6 and all(np.isfinite(hist)) and hist[-1] < hist[0]       # it optimises
+    assert saved == [0, 5] and t.steps == 6
