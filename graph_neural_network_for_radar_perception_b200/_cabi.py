@@ -91,6 +91,7 @@ SIGNATURES = {
     'rgnn_cluster_workspace_bytes': (_SZ, [_I]),
     'rgnn_cluster_links': (_I, [_V, _V, _V, _V, _I, _I, C.c_float, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_cluster_radius': (_I, [_V, _V, _I, _I, _I, C.c_float, _V, _V, _V, _V, _V, _SZ, _V]),
+    'rgnn_cluster_proposals': (_I, [_V, _V, _V, _I, _V, _V, _I, _V, _V, _V, _V, _V, _V]),
     'rgnn_detector_obj_head': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _SZ, _I, _V]),
     'rgnn_detector_bwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_wgrad': (_I, [_V, _I, _I, _V, _I, _I, C.c_longlong, _V, _V, _V, _V]),

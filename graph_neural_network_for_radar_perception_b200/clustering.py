@@ -95,3 +95,37 @@ class Simple_DBSCAN:
         else:
             self._finish(cluster_radius(centres, self.eps, gb.frame_node_ptr if gb is not None else None))
         return self.result
+
+
+def compute_proposals_device(res: ClusterResult, px: torch.Tensor, py: torch.Tensor, meas_noise_cov, node_cls: Optional[torch.Tensor] = None):
+    """Reference `compute_proposals` (modules/inference/inference.py:36-47) + the majority-vote object class of
+    inference/output.py:111-118 for every cluster of `res`, on the device.  Returns (mean (C,2), cov (C,2,2), size (C,),
+    vote (C,) or None) as tensors."""
+    import ctypes as C
+    dev = px.device
+    px, py = px.to(torch.float32).contiguous(), py.to(torch.float32).contiguous()
+    c = res.n_clusters
+    mean = torch.empty((c, 2), dtype=torch.float32, device=dev)
+    cov = torch.empty((c, 2, 2), dtype=torch.float32, device=dev)
+    size = torch.empty(c, dtype=torch.int32, device=dev)
+    vote = torch.empty(c, dtype=torch.int32, device=dev) if node_cls is not None else None
+    noise = (C.c_float * 4)(*[float(v) for v in np.asarray(meas_noise_cov, dtype=np.float32).reshape(-1)])
+    ncls = node_cls.to(torch.float32).contiguous() if node_cls is not None else None
+    check(lib().rgnn_cluster_proposals(ptr(px), ptr(py), ptr(ncls), int(ncls.shape[1]) if ncls is not None else 0, ptr(res.cl_ptr),
+                                       ptr(res.cl_members), c, noise, ptr(mean), ptr(cov), ptr(size), ptr(vote), stream_ptr()),
+          'rgnn_cluster_proposals')
+    return mean, cov, size, vote
+
+
+def compute_proposals(cluster_members_list, px, py, meas_noise_cov):
+    """Reference signature (inference.py:36-47): list of member tensors + NumPy / tensor coordinates -> lists of means,
+    covariances and sizes (NumPy, like the reference)."""
+    dev = torch.device('cuda', torch.cuda.current_device())
+    sizes = [int(m.shape[0]) for m in cluster_members_list]
+    cl_ptr = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    cl_ptr[1:] = torch.tensor(sizes, dtype=torch.int32).cumsum(0)
+    members = torch.cat([torch.as_tensor(m).to(dev) for m in cluster_members_list]).to(torch.int32) if sizes else torch.zeros(1, dtype=torch.int32, device=dev)
+    res = ClusterResult(None, cl_ptr.to(dev), members, len(sizes))
+    mean, cov, size, _ = compute_proposals_device(res, torch.as_tensor(np.asarray(px)).to(dev), torch.as_tensor(np.asarray(py)).to(dev), meas_noise_cov)
+    mean, cov = mean.cpu().numpy(), cov.cpu().numpy()
+    return [mean[i] for i in range(len(sizes))], [cov[i] for i in range(len(sizes))], sizes

@@ -174,3 +174,76 @@ extern "C" int rgnn_cluster_radius(const float* xy, const int32_t* frame_ptr_dev
     uf_radius_kernel<<<dim3(gx, n_frames), 256, 0, stream>>>(xy, frame_ptr_dev, n_frames, eps, parent);
     return finish_clusters(parent, n_nodes, workspace_bytes, cluster_id, n_clusters_out, cl_ptr, cl_members, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Proposals from clusters (reference modules/inference/inference.py:23-47 and output.py:111-118): per cluster the sample
+// mean of the member positions, the sample covariance of (mean - x) plus the measurement-noise covariance (noise only for
+// a single member), the size, and the majority vote over the members' arg-max segmentation class (torch.bincount +
+// argmax: ties go to the lowest class).  One thread per cluster, members visited in list order with separately rounded
+// float32 operations: NumPy's axis-0 reductions over (n,2) / (n,2,2) arrays add row by row in that order.
+// ---------------------------------------------------------------------------------------------
+namespace rgnn {
+__global__ void proposals_kernel(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ node_cls,
+                                 int n_classes, const int* __restrict__ cl_ptr, const int* __restrict__ cl_members, int n_clusters,
+                                 float noise_xx, float noise_xy, float noise_yy, float* __restrict__ mean, float* __restrict__ cov,
+                                 int* __restrict__ size, int* __restrict__ vote) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_clusters; c += gridDim.x * blockDim.x) {
+        const int m0 = cl_ptr[c], m1 = cl_ptr[c + 1], n = m1 - m0;
+        float sx = 0.f, sy = 0.f;
+        int cnt[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cnt[k] = 0;
+        for (int m = m0; m < m1; ++m) {
+            const int i = cl_members[m];
+            sx = __fadd_rn(sx, px[i]);
+            sy = __fadd_rn(sy, py[i]);
+            if (node_cls != nullptr) {
+                const float* l = node_cls + (size_t)i * n_classes;
+                int best = 0;
+                for (int k = 1; k < n_classes; ++k) if (l[k] > l[best]) best = k;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) cnt[k] += (k == best);
+            }
+        }
+        const float mx = __fdiv_rn(sx, (float)n), my = __fdiv_rn(sy, (float)n);
+        float cxx = 0.f, cxy = 0.f, cyy = 0.f;
+        if (n > 1) {
+            for (int m = m0; m < m1; ++m) {
+                const int i = cl_members[m];
+                const float ex = __fsub_rn(mx, px[i]), ey = __fsub_rn(my, py[i]);
+                cxx = __fadd_rn(cxx, __fmul_rn(ex, ex));
+                cxy = __fadd_rn(cxy, __fmul_rn(ex, ey));
+                cyy = __fadd_rn(cyy, __fmul_rn(ey, ey));
+            }
+            const float d = (float)(n - 1);
+            cxx = __fadd_rn(__fdiv_rn(cxx, d), noise_xx);
+            cxy = __fadd_rn(__fdiv_rn(cxy, d), noise_xy);
+            cyy = __fadd_rn(__fdiv_rn(cyy, d), noise_yy);
+        } else {
+            cxx = noise_xx; cxy = noise_xy; cyy = noise_yy;
+        }
+        mean[2 * c] = mx; mean[2 * c + 1] = my;
+        cov[4 * c] = cxx; cov[4 * c + 1] = cxy; cov[4 * c + 2] = cxy; cov[4 * c + 3] = cyy;
+        size[c] = n;
+        if (vote != nullptr) {
+            int best = 0;
+#pragma unroll
+            for (int k = 1; k < 16; ++k) if (k < n_classes && cnt[k] > cnt[best]) best = k;
+            vote[c] = best;
+        }
+    }
+}
+}  // namespace rgnn
+
+extern "C" int rgnn_cluster_proposals(const float* px, const float* py, const float* node_cls, int n_classes, const int32_t* cl_ptr,
+                                      const int32_t* cl_members, int n_clusters, const float* noise_cov_host, float* mean, float* cov,
+                                      int32_t* size, int32_t* vote, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_clusters <= 0) return RGNN_OK;
+    RGNN_REQUIRE(node_cls == nullptr || (n_classes >= 1 && n_classes <= 16), "proposals: %d classes", n_classes);
+    const int blocks = (n_clusters + 255) / 256 > 1184 ? 1184 : (n_clusters + 255) / 256;
+    proposals_kernel<<<blocks, 256, 0, stream>>>(px, py, node_cls, n_classes, cl_ptr, cl_members, n_clusters, noise_cov_host[0],
+                                                 noise_cov_host[1], noise_cov_host[3], mean, cov, size, vote);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}

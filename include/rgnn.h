@@ -222,6 +222,15 @@ int rgnn_cluster_links(const float* xy, const int32_t* und_a, const int32_t* und
 int rgnn_cluster_radius(const float* xy, const int32_t* frame_ptr_dev, int n_frames, int n_nodes, int max_frame_nodes,
                         float eps, int32_t* cluster_id, int32_t* n_clusters_out, int32_t* cl_ptr, int32_t* cl_members,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Proposals from the clusters (modules/inference/inference.py:23-47, output.py:111-118): per cluster the sample mean of
+ * the member positions (px, py), covariance = sum (mean - x)(mean - x)^T / (n - 1) + noise_cov (noise_cov alone for a
+ * single member), the size, and -- when node_cls (n_nodes, n_classes) is given -- the majority vote over the members'
+ * arg-max class (ties to the lowest class, like torch.bincount + argmax).  noise_cov_host: 4 floats on the HOST
+ * (Model_Inference.meas_noise_cov).  Outputs: mean (C,2), cov (C,2,2), size (C) int32, vote (C) int32 or NULL. */
+int rgnn_cluster_proposals(const float* px, const float* py, const float* node_cls, int n_classes, const int32_t* cl_ptr,
+                           const int32_t* cl_members, int n_clusters, const float* noise_cov_host, float* mean, float* cov,
+                           int32_t* size, int32_t* vote, void* stream);
+
 /* predict_class on clusters found after the forward pass: the per-node stem output of predict_class is still in the
  * workspace of the preceding rgnn_detector_fwd call on the same graph (same `training` flag); g carries the new
  * cl_ptr / cl_members / n_clusters.  obj_cls (n_clusters, n_classes). */

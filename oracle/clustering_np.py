@@ -60,3 +60,30 @@ class Simple_DBSCAN:
         remap[order] = np.arange(ncomp)
         self.meas_to_cluster_id = remap[lab].astype(np.int16 if n < 32768 else np.int64)
         self.num_clusters = int(ncomp)
+
+
+def proposals_np(cluster_id, px, py, meas_noise_cov, node_logits=None):
+    """Restatement of the reference's compute_proposals / compute_cluster_sample_mean_and_cov
+    (modules/inference/inference.py:23-47) and of the majority-vote object class (inference/output.py:111-118) for the
+    clusters encoded by `cluster_id` (meas_to_cluster_id).  float32 like the reference's arrays; rows are added in member
+    order (NumPy's axis-0 reduction of an (n,2) array)."""
+    cluster_id = np.asarray(cluster_id)
+    xy = np.stack((np.asarray(px, dtype=np.float32), np.asarray(py, dtype=np.float32)), axis=-1)
+    noise = np.asarray(meas_noise_cov, dtype=np.float32)
+    n_c = int(cluster_id.max()) + 1 if cluster_id.size else 0
+    mean, cov, size, vote = [], [], [], []
+    pred = np.argmax(node_logits, axis=-1) if node_logits is not None else None
+    for c in range(n_c):
+        mem = np.nonzero(cluster_id == c)[0]
+        v = xy[mem]
+        mu = np.sum(v, axis=0) / v.shape[0]
+        if v.shape[0] > 1:
+            err = np.expand_dims(mu[:2] - v[:, :2], axis=-1)
+            sig = np.sum(err @ err.transpose(0, 2, 1), axis=0) / (v.shape[0] - 1) + noise
+        else:
+            sig = noise
+        mean.append(mu); cov.append(sig); size.append(v.shape[0])
+        if pred is not None:
+            vote.append(int(np.argmax(np.bincount(pred[mem]))))
+    return (np.stack(mean).astype(np.float32), np.stack(cov).astype(np.float32), np.array(size, dtype=np.int64),
+            np.array(vote, dtype=np.int64) if pred is not None else None)

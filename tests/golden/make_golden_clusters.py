@@ -29,6 +29,8 @@ def load(path, name):
 def main():
     clus = load(os.path.join(REF, 'modules/inference/clustering.py'), 'ref_clustering')
     gfeat = load(os.path.join(REF, 'modules/compute_features/graph_features.py'), 'ref_graph_features')
+    sys.path.insert(0, REF)
+    import modules.inference.inference as infer          # the reference package itself (NumPy / torch only)
     from graph_neural_network_for_radar_perception_b200 import synth
     out = {}
     for case, (seed, n, eps_l, eps_r) in enumerate([(11, 60, 1.4, 1.4), (12, 300, 2.0, 0.6), (13, 7, 1.4, 1.4), (14, 500, 0.8, 3.0)]):
@@ -53,6 +55,18 @@ def main():
                     p + 'adj_matrix': adj['adj_matrix'], p + 'eps_links': np.float64(eps_l), p + 'eps_radius': np.float64(eps_r),
                     p + 'ids_links': ids_l, p + 'n_links': np.int64(n_l), p + 'ids_radius': ids_r, p + 'n_radius': np.int64(n_r)})
         print(f'case {case}: n={n} pairs={r.shape[0]} clusters links={n_l} radius={n_r}')
+        # proposals of the links-mode clusters: the reference's compute_proposals (modules/inference/inference.py:36-47) and
+        # the majority vote of output.py:111-118 over random segmentation logits
+        import torch
+        members = [torch.from_numpy(np.nonzero(ids_l == i)[0]) for i in range(n_l)]
+        noise = 0.5 * np.eye(2, dtype=np.float32)
+        mu, sig, size = infer.compute_proposals(members, centres[:, 0].copy(), centres[:, 1].copy(), noise)
+        node_logits = rng.normal(size=(n, 7)).astype(np.float32)
+        pred = torch.from_numpy(node_logits).argmax(dim=-1)
+        vote = np.array([int(torch.argmax(torch.bincount(pred[m]))) for m in members], dtype=np.int64)
+        out.update({p + 'prop_mean': np.stack(mu).astype(np.float32), p + 'prop_cov': np.stack(sig).astype(np.float32),
+                    p + 'prop_size': np.array(size, dtype=np.int64), p + 'node_logits': node_logits, p + 'prop_vote': vote,
+                    p + 'prop_dtypes': np.array([str(np.stack(mu).dtype), str(np.stack(sig).dtype)])})
     out['n_cases'] = np.int64(4)
     np.savez_compressed(os.path.join(HERE, 'clusters.npz'), **out)
 

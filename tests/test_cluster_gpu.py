@@ -26,6 +26,16 @@ def test_reference_interface_matches_reference_outputs(golden_dir):
         ids = g[p + 'ids_links']
         for i, m in enumerate(_lists(o.result)):                  # cluster_members_list of gnn_detector.py:176-181
             assert np.array_equal(m, np.nonzero(ids == i)[0])
+        # proposals of those clusters (row f4): float32 bit-exact against the reference's compute_proposals
+        xy = torch.from_numpy(g[p + 'centres']).cuda()
+        mean, cov, size, vote = cl.compute_proposals_device(o.result, xy[:, 0], xy[:, 1], 0.5 * np.eye(2, dtype=np.float32),
+                                                            torch.from_numpy(g[p + 'node_logits']).cuda())
+        assert np.array_equal(mean.cpu().numpy(), g[p + 'prop_mean']) and np.array_equal(cov.cpu().numpy(), g[p + 'prop_cov'])
+        assert np.array_equal(size.cpu().numpy().astype(np.int64), g[p + 'prop_size'])
+        assert np.array_equal(vote.cpu().numpy().astype(np.int64), g[p + 'prop_vote'])
+        mu_l, sig_l, size_l = cl.compute_proposals(o.result.member_lists(), g[p + 'centres'][:, 0], g[p + 'centres'][:, 1],
+                                                   0.5 * np.eye(2, dtype=np.float32))          # reference signature
+        assert np.array_equal(np.stack(mu_l), g[p + 'prop_mean']) and size_l == g[p + 'prop_size'].tolist()
         o = cl.Simple_DBSCAN(float(g[p + 'eps_radius']), False)
         o.cluster_nodes(g[p + 'centres'])
         assert o.num_clusters == int(g[p + 'n_radius'])

@@ -107,3 +107,9 @@ def test_cluster_oracle_matches_reference_dbscan(golden_dir):
         o.cluster_nodes(g[p + 'centres'])
         assert o.num_clusters == int(g[p + 'n_radius'])
         assert np.array_equal(o.meas_to_cluster_id.astype(np.int64), g[p + 'ids_radius'])
+        # proposals (row f4): bit-exact float32 against the reference's compute_proposals, votes against torch.bincount
+        from oracle.clustering_np import proposals_np
+        mean, cov, size, vote = proposals_np(g[p + 'ids_links'], g[p + 'centres'][:, 0], g[p + 'centres'][:, 1],
+                                             0.5 * np.eye(2, dtype=np.float32), g[p + 'node_logits'])
+        assert np.array_equal(mean, g[p + 'prop_mean']) and np.array_equal(cov, g[p + 'prop_cov'])
+        assert np.array_equal(size, g[p + 'prop_size']) and np.array_equal(vote, g[p + 'prop_vote'])
