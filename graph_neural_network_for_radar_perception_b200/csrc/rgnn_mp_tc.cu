@@ -7,7 +7,7 @@
 // produced by the node kernel), so per edge
 //   z1 = emb_e W_e^T + P_t[tgt] + P_s[src]                  (msg.0's bias rides on P_t)
 // A CTA owns tiles of 128 target-major edges (UMMA M = 128, thread = TMEM lane = edge row):
-//   GEMM1  D1[128 x H]  = A(emb tile, smem) * W_e^T (smem)          tcgen05.mma kind::tf32, SS
+//   GEMM1  D1[128 x H]  = A(emb tile, TMEM) * W_e^T (smem)          tcgen05.mma kind::tf32, TS (ATM) / SS (legacy)
 //   epi 1  z1 -> mean / unbiased std / scalar affine / LeakyReLU -> y1, written back to TMEM (hi and lo parts)
 //   GEMM2  D2[128 x Cn] = y1 (TMEM) * W_2^T (smem)                  tcgen05.mma kind::tf32, TS
 //   epi 2  + b2 -> norm -> act -> staged in smem -> segmented sum over equal consecutive targets -> agg
@@ -62,16 +62,17 @@ struct MpTcLayout {
     static constexpr int OFF_W2 = OFF_W1 + 2 * W1;
     static constexpr int OFF_A = OFF_W2 + 2 * W2;           // A operand (hi | lo); between GEMM1 and the next fill: P_s row staging
     static constexpr int OFF_STAGE = OFF_A + 2 * A;         // messages of one tile, XOR-swizzled 16-byte chunks
-    static constexpr int OFF_TGT = OFF_STAGE + TM * CN;     // [2][TM] target ids (double buffered: deferred segsum)
-    static constexpr int OFF_SEG = OFF_TGT + 2 * TM;        // [2][SEG] first row of every target segment
-    static constexpr int OFF_MASK = OFF_SEG + 2 * SEG;      // [2][4] segment-head ballots, [2] segment counts, 3 x [2] boundary flags
+    static constexpr int OFF_SEG = OFF_STAGE + TM * CN;     // [2][SEG] int2 {first row, target node} of every target segment (double buffered: deferred segsum)
+    static constexpr int OFF_MASK = OFF_SEG + 4 * SEG;      // [2][4] segment-head ballots, [2] segment counts, 3 x [2] boundary flags
     static constexpr int OFF_BAR = OFF_MASK + 16;           // 2 x uint64
     static constexpr int OFF_SLOT = OFF_BAR + 4;
     static constexpr int FLOATS = OFF_SLOT + 2;
     static constexpr size_t BYTES = (size_t)FLOATS * 4;
-    static constexpr int TMEM_COLS = 512;                   // D1/y1_hi [0,H) | y1_lo [H,2H) | D2 [2H, 2H+CN) | row statistics (16)
+    static constexpr int TMEM_COLS = 512;                   // D1/y1_hi [0,H) | y1_lo [H,2H) | D2 [2H, 2H+CN) | row statistics (16) | emb hi, lo [512-2CE, 512)
+    static constexpr int COL_EHI = 512 - 2 * CE, COL_ELO = 512 - CE;
     static_assert(CE % 16 == 0 && H % 16 == 0 && CN % 16 == 0, "UMMA shape constraints");
-    static_assert(2 * H + CN + 16 <= 512, "TMEM budget");
+    static_assert(2 * H + CN + 16 + 2 * CE <= 512, "TMEM budget");
+    static_assert((CE / NQ) % 16 == 0, "emb column split must keep 16-column TMEM accesses");
     static_assert((H / NQ) % 16 == 0 && (CN / NQ) % 16 == 0, "column split must keep 16-column TMEM accesses");
     static_assert(NT % CN == 0 && CN % 4 == 0 && CN / 4 >= 8, "segmented sum thread mapping / stage swizzle");
     static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
@@ -83,10 +84,14 @@ struct MpTcLayout {
 // Thread roles: 128*NQ worker threads (thread = edge row x column quarter; loads, both epilogues, segmented sum)
 // + one extra warp whose lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy,
 // so it must not sit on a worker's critical path).
-template <int CE, int H, int CN, int NQ, bool PROFILE>
+// ATM: the A operand of GEMM1 (emb tile, hi | lo) lives in TMEM like GEMM2's (TS MMA).  An SS tf32 MMA with N = 128 reads
+// 8 KB of shared memory per 64 cycles = the whole 128 B/clk of the SM, which starves the workers' own LDS traffic (deferred
+// segmented sum) for the duration of GEMM1; with A in TMEM the tensor core reads only W_e, the fill is a tcgen05.st (no
+// proxy fence), and the shared-memory A region holds nothing but the staged P_s rows, so those can be copied during GEMM1.
+template <int CE, int H, int CN, int NQ, bool PROFILE, bool ATM>
 __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
     using L = MpTcLayout<CE, H, CN, NQ>;
-    constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 128, HQ = H / NQ, CQ = CN / NQ;
+    constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 128, HQ = H / NQ, CQ = CN / NQ, EQ = CE / NQ;
     constexpr int NMMA = NW + 32;            // threads that take part in the worker <-> MMA-warp barriers
     // register budget: the issue warpgroup keeps 24 registers, the workers take the rest (setmaxnreg)
     constexpr int WORKER_REGS = NQ == 4 ? 112 : 232;
@@ -96,8 +101,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     float* As = smem + L::OFF_A;
     float* Gs = As;                          // P_s rows of the NEXT tile, staged while no GEMM1 reads A
     float* stage = smem + L::OFF_STAGE;
-    int* tgt_s = reinterpret_cast<int*>(smem + L::OFF_TGT);
-    int* seg_s = reinterpret_cast<int*>(smem + L::OFF_SEG);
+    int2* seg_s = reinterpret_cast<int2*>(smem + L::OFF_SEG);
     unsigned* mask_s = reinterpret_cast<unsigned*>(smem + L::OFF_MASK);
     int* nseg_s = reinterpret_cast<int*>(smem + L::OFF_MASK + 8);
     int* cut_s = nseg_s + 2;
@@ -140,10 +144,13 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
         constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
         const uint32_t sA = tc::smem_u32(As), sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long g1 = 0, g2 = 0, tm0 = 0;
+        uint32_t mph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, mph ^= 1) {
             // GEMM1: D1 = A * W1e^T.  3xTF32: small terms first (lo*hi, hi*lo), then hi*hi
             group_sync(BAR_A_READY, NMMA);
             tc::tc_fence_after();
+            if (PROFILE) tm0 = clock64();
             if (lane == 0) {
                 bool acc = false;
                 for (int p = 0; p < np; ++p) {
@@ -151,18 +158,22 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                     const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
                     const uint64_t ad0 = tc::smem_desc(sA + pa * (L::A * 4), LBO_A, SBO);
                     const uint64_t bd0 = tc::smem_desc(sW1 + pb * (L::W1 * 4), LBO_W1, SBO);
+                    const uint32_t ecol = tmem + (pa ? L::COL_ELO : L::COL_EHI);
 #pragma unroll
                     for (int ks = 0; ks < CE / 8; ++ks) {
-                        tc::mma_tf32_ss(tmem, ad0 + (uint64_t)((ks * 2 * LBO_A) >> 4), bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
+                        if (ATM) tc::mma_tf32_ts(tmem, ecol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
+                        else tc::mma_tf32_ss(tmem, ad0 + (uint64_t)((ks * 2 * LBO_A) >> 4), bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
                         acc = true;
                     }
                 }
                 tc::mma_commit(&bars[0]);
+                if (PROFILE) { tc::mbar_wait(&bars[0], mph); g1 += clock64() - tm0; }   // issue -> completion as the tensor pipe sees it
             }
             __syncwarp();
             // GEMM2: D2 = y1 * W2^T, A operand from TMEM
             group_sync(BAR_Y_READY, NMMA);
             tc::tc_fence_after();
+            if (PROFILE) tm0 = clock64();
             if (lane == 0) {
                 bool acc = false;
                 for (int p = 0; p < np; ++p) {
@@ -177,9 +188,11 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                     }
                 }
                 tc::mma_commit(&bars[1]);
+                if (PROFILE) { tc::mbar_wait(&bars[1], mph); g2 += clock64() - tm0; }
             }
             __syncwarp();
         }
+        if (PROFILE && lane == 0 && a.prof != nullptr) { a.prof[blockIdx.x * 12 + 10] = g1; a.prof[blockIdx.x * 12 + 11] = g2; }
     } else {
         // =========================== worker warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
@@ -193,12 +206,25 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         float4 pre[UNITS];
         auto prefetch = [&](int tile) {
             const int row0 = tile * TM;
+            if constexpr (ATM) {   // thread = (edge row, column part): EQ contiguous floats of its own row, 32 bytes per request
+                static_assert(EQ / 4 == UNITS, "both prefetch mappings hold the same number of registers");
+                const bool v = row0 + row < a.n_edges;
+                const float* p = a.emb + (size_t)(v ? row0 + row : 0) * CE + q * EQ;
 #pragma unroll
-            for (int u = 0; u < UNITS; ++u) {
-                const int unit = warp * UNITS + u;
-                const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
-                pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < a.n_edges) pre[u] = __ldg(reinterpret_cast<const float4*>(a.emb + (size_t)(row0 + r) * CE) + kc);
+                for (int c8 = 0; c8 < EQ / 8; ++c8) {
+                    float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
+                    if (v) ldg256(p + 8 * c8, x0, x1, x2, x3);
+                    pre[2 * c8] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                    pre[2 * c8 + 1] = make_float4(x2.x, x2.y, x3.x, x3.y);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNITS; ++u) {
+                    const int unit = warp * UNITS + u;
+                    const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
+                    pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row0 + r < a.n_edges) pre[u] = __ldg(reinterpret_cast<const float4*>(a.emb + (size_t)(row0 + r) * CE) + kc);
+                }
             }
         };
 
@@ -206,12 +232,15 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         //   t_my / s_my : target / source node of this thread's edge row;  e_first (lane 0 of the first four warps):
         //   target of the edge just before this warp's rows;  e_last (thread TM-1): target of the edge after the tile
         constexpr int RPW = TM / (NW / 32);     // P_s rows staged per warp
+        auto load_src = [&](int tile) {   // source of the (lane % RPW)-th row this warp stages
+            const int es = tile * TM + warp * RPW + (lane % RPW);
+            return (tile < n_tiles && es < a.n_edges) ? __ldg(a.src + es) : -1;
+        };
         auto load_idx = [&](int tile, int& t_my, int& s_my, int& e_first, int& e_last) {
             const int e = tile * TM + row;
             const bool v = e < a.n_edges;
             t_my = v ? __ldg(a.tgt + e) : -1;
-            const int es = tile * TM + warp * RPW + (lane % RPW);   // source of the (lane % RPW)-th row this warp stages
-            s_my = es < a.n_edges ? __ldg(a.src + es) : -1;
+            if (!ATM) s_my = load_src(tile);
             e_first = (tid < TM && lane == 0 && v && e > 0) ? __ldg(a.tgt + e - 1) : -2;
             e_last = (tid == TM - 1 && e + 1 < a.n_edges) ? __ldg(a.tgt + e + 1) : -3;
         };
@@ -254,23 +283,33 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         // construction (edges are target-major), only the first / last segment of a tile can be cut by its boundary.
         auto segsum = [&](int buf) {
             static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
-            const int* tg = tgt_s + buf * TM;
-            const int* sg = seg_s + buf * L::SEG;
+            // Every shared-memory round trip costs a few hundred cycles while the tensor core streams its operands, so the
+            // dependent chain is kept to: {count, bounds + target of my segment} -> {up to RB rows at once} -> store.
+            constexpr int RB = 8;
+            const int2* sg = seg_s + buf * L::SEG;
+            const int s0 = tid >> 4, c4 = tid & 15;
+            const int2 h0 = sg[s0], h1 = sg[s0 + 1];          // speculative: entries beyond the count are never used
             const int nseg = nseg_s[buf];
             const int cut = cut_s[buf];            // bit 0: first segment continues from the previous tile; bit 1: last one continues
-            const int c4 = tid & 15;
-            for (int s = tid >> 4; s < nseg; s += NW / 16) {
-                const int rs = sg[s], re = sg[s + 1];
+            for (int s = s0; s < nseg; s += NW / 16) {
+                const int2 a0 = s == s0 ? h0 : sg[s], a1 = s == s0 ? h1 : sg[s + 1];
+                const int rs = a0.x, re = a1.x;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                for (int r = rs; r < re; ++r) {
-                    const float4 v = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                for (int r0 = rs; r0 < re; r0 += RB) {
+                    float4 v[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int r = r0 + j;
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < re) v[j] = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
                 }
                 // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
                 // boundary is completed with atomicAdd onto the zero-initialised output
                 const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
-                float* o = a.agg + (size_t)tg[rs] * CN + 4 * c4;
+                float* o = a.agg + (size_t)a0.y * CN + 4 * c4;
                 if (whole) {
                     *reinterpret_cast<float4*>(o) = acc;
                 } else {
@@ -296,10 +335,13 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         int buf = 0;
         bool have_prev = false;
         int t_my = -1, s_my = 0, e_first = -2, e_last = -3;
+        int s_ahead = -1;   // ATM: source ids of the NEXT tile, loaded one tile earlier than the other indices (their consumer, the
+                            // P_s staging, is issued right after the segmented sum and must not wait for a DRAM round trip)
         float2 z[HQ / 2];
         if ((int)blockIdx.x < n_tiles) {
             prefetch(blockIdx.x);
             load_idx(blockIdx.x, t_my, s_my, e_first, e_last);
+            if (ATM) { s_my = load_src(blockIdx.x); s_ahead = load_src(blockIdx.x + gridDim.x); }
             stage_ps(s_my);
             cp_async_wait<0>();
             group_sync(BAR_WORKERS, NW);
@@ -316,8 +358,23 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             {
                 float4* Ahi = reinterpret_cast<float4*>(As);
                 float4* Alo = reinterpret_cast<float4*>(As + L::A);
+                if (ATM) {
 #pragma unroll
-                for (int u = 0; u < UNITS; ++u) {
+                    for (int c = 0; c < EQ; c += 16) {
+                        float2 hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 v = pre[c / 4 + j];
+                            tc::split_tf32(make_float2(v.x, v.y), hi[2 * j], lo[2 * j]);
+                            tc::split_tf32(make_float2(v.z, v.w), hi[2 * j + 1], lo[2 * j + 1]);
+                        }
+                        tc::tmem_st16(t_row + L::COL_EHI + q * EQ + c, hi);
+                        if (np != 1) tc::tmem_st16(t_row + L::COL_ELO + q * EQ + c, lo);
+                    }
+                    tc::tmem_wait_st();
+                }
+#pragma unroll
+                for (int u = 0; u < (ATM ? 0 : UNITS); ++u) {
                     const int unit = warp * UNITS + u;
                     const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
                     float4 hi, lo;
@@ -333,13 +390,12 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                     int prev = __shfl_up_sync(0xffffffffu, t_my, 1);
                     if (lane == 0) prev = e_first;
                     const unsigned m = __ballot_sync(0xffffffffu, v && (tid == 0 || t_my != prev));
-                    tgt_s[buf * TM + tid] = t_my;
                     if (lane == 0) mask_s[buf * 4 + warp] = m;
                     if (tid == 0) cut_first_s[buf] = (e_first == t_my) ? 1 : 0;
                     if (tid == nvalid - 1) cut_last_s[buf] = (tid == TM - 1 && e_last == t_my) ? 2 : 0;
                 }
             }
-            tc::fence_async_smem();
+            if (!ATM) tc::fence_async_smem();
             tc::tc_fence_before();
             bar_arrive(BAR_A_READY, NMMA);          // -> MMA warp issues GEMM1
             tick(1);
@@ -352,15 +408,18 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 prefetch(next);
                 load_idx(next, n_t, n_s, n_first, n_last);
             }
+            int s_ahead2 = -1;
+            if (ATM) { n_s = s_ahead; s_ahead2 = load_src(next + (int)gridDim.x); }
             tick(2);
             if (have_prev && !(a.debug & 4)) segsum(buf ^ 1);
+            if (ATM && has_next && !(a.debug & 64)) stage_ps(n_s);     // the staging region is no operand: the copies overlap GEMM1
             tick(3);
 
             // ---- (c) epilogue 1: z1 = D1 + (P_t + P_s) -> norm -> act -> y1 (hi | lo) back into TMEM ----
             tc::mbar_wait(&bars[0], phase);
             tc::tc_fence_after();
             tick(4);
-            if (has_next) stage_ps(n_s);            // GEMM1 is done with the A region: next tile's P_s rows land there
+            if (!ATM && has_next) stage_ps(n_s);    // GEMM1 is done with the A region: next tile's P_s rows land there
             {
                 float2 d[HQ / 2];
 #pragma unroll
@@ -397,16 +456,16 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 const unsigned m = mk[warp];
                 int base = 0;
                 for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
-                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = tid;
+                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = make_int2(tid, t_my);
                 if (tid == TM - 1) {
                     const int n = base + __popc(m);
-                    seg_s[buf * L::SEG + n] = nvalid;
+                    seg_s[buf * L::SEG + n] = make_int2(nvalid, -1);
                     nseg_s[buf] = n;
                     cut_s[buf] = cut_first_s[buf] | cut_last_s[buf];
                 }
             }
             if (has_next) add_ps(z);
-            t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last;
+            t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last; s_ahead = s_ahead2;
             tick(6);
 
             // ---- (e) epilogue 2: message = act(norm(D2 + b2)) -> stage ----
@@ -436,7 +495,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         if (have_prev) segsum(buf ^ 1);
         tick(9);
         if (PROFILE && tid == 0 && a.prof != nullptr)
-            for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];
+            for (int i = 0; i < 10; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];   // 10, 11: GEMM1 / GEMM2 durations (MMA warp)
     }
 
 teardown:
@@ -488,13 +547,13 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
     return RGNN_OK;
 }
 
-template <int NQ>
+template <int NQ, bool ATM>
 static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
     using L = MpTcLayout<64, 128, 64, NQ>;
     static bool configured = false;
     if (!configured) {
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
         configured = true;
     }
     const int n_tiles = (n_edges + L::TM - 1) / L::TM;
@@ -503,7 +562,7 @@ static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
         long long* prof = nullptr;
         RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid));
         a.prof = prof;
-        mp_edge_tc_kernel<64, 128, 64, NQ, true><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
+        mp_edge_tc_kernel<64, 128, 64, NQ, true, ATM><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
         long long* h = new long long[12 * grid];
         RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost));
@@ -516,7 +575,7 @@ static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
         cudaFree(prof);
         return RGNN_OK;
     }
-    mp_edge_tc_kernel<64, 128, 64, NQ, false><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
+    mp_edge_tc_kernel<64, 128, 64, NQ, false, ATM><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
@@ -536,7 +595,8 @@ int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g
     a.debug = g_debug;
     a.prof = nullptr;
     (void)d;
-    return (g_debug & 16) ? launch_mp_tc<4>(a, g.n_edges, stream) : launch_mp_tc<2>(a, g.n_edges, stream);
+    if (g_debug & 32) return launch_mp_tc<2, false>(a, g.n_edges, stream);   // legacy: A operand of GEMM1 in shared memory
+    return (g_debug & 16) ? launch_mp_tc<4, true>(a, g.n_edges, stream) : launch_mp_tc<2, true>(a, g.n_edges, stream);
 }
 
 }  // namespace rgnn
