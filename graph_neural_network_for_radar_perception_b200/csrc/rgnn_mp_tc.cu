@@ -93,8 +93,25 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     using L = MpTcLayout<CE, H, CN, NQ>;
     constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 128, HQ = H / NQ, CQ = CN / NQ, EQ = CE / NQ;
     constexpr int NMMA = NW + 32;            // threads that take part in the worker <-> MMA-warp barriers
-    // register budget: the issue warpgroup keeps 24 registers, the workers take the rest (setmaxnreg)
-    constexpr int WORKER_REGS = NQ == 4 ? 112 : 232;
+    // register budget (setmaxnreg): the auxiliary warpgroup (MMA issue warp + three helper warps) keeps AUX_REGS,
+    // the workers take the rest
+    constexpr int WORKER_REGS = NQ == 4 ? 104 : 208, AUX_REGS = NQ == 4 ? 64 : 80;
+    constexpr int LAUNCH_REGS = (65536 / NALL) / 8 * 8;     // what __launch_bounds__(NALL, 1) compiles to (168 / 96)
+    static_assert(128 * AUX_REGS + NW * WORKER_REGS <= 65536, "register file");
+    // setmaxnreg.inc only draws from what setmaxnreg.dec released (measured: asking for the never-allocated remainder
+    // of the register file as well blocks forever)
+    static_assert(128 * (LAUNCH_REGS - AUX_REGS) >= NW * (WORKER_REGS - LAUNCH_REGS), "setmaxnreg pool");
+    // Helper warps (ATM only): the three warps next to the MMA issue warp take the two jobs that used to sit between
+    // the workers' fill and epilogue 1 -- the segmented sum of the previous tile and the P_s row staging of the next
+    // one (4 100 of 12 400 cycles per tile, profiles/README.md) -- so the workers' chain per tile is fill -> epi 1 ->
+    // epi 2 only.  Hand-over by four named barriers (workers + helpers):
+    //   PS_READY   helpers -> workers : staged P_s rows of the next tile are in shared memory
+    //   PS_FREE    workers -> helpers : they have been consumed (added into z), the region may be refilled
+    //   STAGE_FULL workers -> helpers : messages + segment table of this tile are in shared memory
+    //   STAGE_FREE helpers -> workers : the segmented sum has read them, epilogue 2 may overwrite the stage
+    constexpr int NHELP = 96, NWH = NW + NHELP;
+    constexpr int BAR_PS_READY = 8, BAR_PS_FREE = 9, BAR_STAGE_FULL = 10, BAR_STAGE_FREE = 11;
+    const bool helpers = ATM && !(a.debug & 128);
     extern __shared__ __align__(1024) float smem[];
     float* w1s = smem + L::OFF_W1;
     float* w2s = smem + L::OFF_W2;
@@ -136,10 +153,96 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     const int n_tiles = (a.n_edges + TM - 1) / TM;
     const int np = a.passes == 1 ? 1 : 3;
 
+    // deferred segmented sum of the tile whose messages sit in `stage`.  16 threads (one float4 of columns each) per
+    // target segment, `ngroups` such groups; interior segments are whole CSR rows by construction (edges are
+    // target-major), only the first / last segment of a tile can be cut by its boundary.
+    auto segsum = [&](int buf, int s0, int ngroups, int c4) {
+        static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
+        // Every shared-memory round trip costs a few hundred cycles while the tensor core streams its operands, so the
+        // dependent chain is kept to: {count, bounds + target of my segment} -> {up to RB rows at once} -> store.
+        constexpr int RB = NQ == 4 ? 4 : 8;
+        const int2* sg = seg_s + buf * L::SEG;
+        const int2 h0 = sg[s0], h1 = sg[s0 + 1];          // speculative: entries beyond the count are never used
+        const int nseg = nseg_s[buf];
+        const int cut = cut_s[buf];            // bit 0: first segment continues from the previous tile; bit 1: last one continues
+        for (int s = s0; s < nseg; s += ngroups) {
+            const int2 a0 = s == s0 ? h0 : sg[s], a1 = s == s0 ? h1 : sg[s + 1];
+            const int rs = a0.x, re = a1.x;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r0 = rs; r0 < re; r0 += RB) {
+                float4 v[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int r = r0 + j;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < re) v[j] = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+            }
+            // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
+            // boundary is completed with atomicAdd onto the zero-initialised output
+            const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
+            float* o = a.agg + (size_t)a0.y * CN + 4 * c4;
+            if (whole) {
+                *reinterpret_cast<float4*>(o) = acc;
+            } else {
+                atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+            }
+        }
+    };
+
     if (tid >= NW) {
         // =========================== MMA issue warpgroup (only its first warp works) ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (tid >= NW + 32) goto teardown;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+        if (tid >= NW + 32) {
+            // =========================== helper warps ===========================
+            if (!helpers || (int)blockIdx.x >= n_tiles) goto teardown;
+            static_assert(H == 128, "one warp instruction copies one H-float row");
+            const int ht = tid - (NW + 32), hw = ht >> 5;        // helper warp hw stages rows hw, hw + 3, hw + 6, ...
+            constexpr int JMAX = (TM + 2) / 3;
+            int sa, sb;                                          // source ids of rows hw + 3 * lane and hw + 3 * (lane + 32)
+            auto load_ids = [&](int tile) {
+                const int ra = hw + 3 * lane, rb = ra + 96;
+                const int ea = tile * TM + ra, eb = tile * TM + rb;
+                sa = (tile < n_tiles && ea < a.n_edges) ? __ldg(a.src + ea) : -1;
+                sb = (tile < n_tiles && rb < TM && eb < a.n_edges) ? __ldg(a.src + eb) : -1;
+            };
+            auto hstage = [&]() {
+#pragma unroll 4
+                for (int j = 0; j < JMAX; ++j) {
+                    const int r = hw + 3 * j;
+                    const int sn = __shfl_sync(0xffffffffu, j < 32 ? sa : sb, j & 31);
+                    if (r < TM && sn >= 0)
+                        cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+                }
+                cp_async_commit();
+            };
+            const int G = (int)gridDim.x;
+            load_ids(blockIdx.x + G);
+            group_sync(BAR_PS_FREE, NWH);                        // the workers' prologue is done with the staging region
+            hstage();
+            load_ids(blockIdx.x + 2 * G);
+            cp_async_wait<0>();
+            bar_arrive(BAR_PS_READY, NWH);
+            bar_arrive(BAR_STAGE_FREE, NWH);
+            int hbuf = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G, hbuf ^= 1) {
+                const bool last = tile + G >= n_tiles;
+                group_sync(BAR_PS_FREE, NWH);                    // rows of tile + G consumed -> stage those of tile + 2G
+                hstage();
+                load_ids(tile + 3 * G);
+                group_sync(BAR_STAGE_FULL, NWH);                 // messages of `tile` are staged
+                segsum(hbuf, ht >> 4, NHELP / 16, ht & 15);
+                __syncwarp();
+                cp_async_wait<0>();
+                if (!last) {
+                    bar_arrive(BAR_STAGE_FREE, NWH);
+                    bar_arrive(BAR_PS_READY, NWH);
+                }
+            }
+            goto teardown;
+        }
         constexpr uint32_t IDESC1 = tc::idesc_tf32(TM, H);
         constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
         constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
@@ -278,46 +381,6 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             }
         };
 
-        // deferred segmented sum of the tile whose messages sit in `stage` (runs while the next GEMM1 executes).
-        // 16 threads (one float4 of columns each) per target segment; interior segments are whole CSR rows by
-        // construction (edges are target-major), only the first / last segment of a tile can be cut by its boundary.
-        auto segsum = [&](int buf) {
-            static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
-            // Every shared-memory round trip costs a few hundred cycles while the tensor core streams its operands, so the
-            // dependent chain is kept to: {count, bounds + target of my segment} -> {up to RB rows at once} -> store.
-            constexpr int RB = 8;
-            const int2* sg = seg_s + buf * L::SEG;
-            const int s0 = tid >> 4, c4 = tid & 15;
-            const int2 h0 = sg[s0], h1 = sg[s0 + 1];          // speculative: entries beyond the count are never used
-            const int nseg = nseg_s[buf];
-            const int cut = cut_s[buf];            // bit 0: first segment continues from the previous tile; bit 1: last one continues
-            for (int s = s0; s < nseg; s += NW / 16) {
-                const int2 a0 = s == s0 ? h0 : sg[s], a1 = s == s0 ? h1 : sg[s + 1];
-                const int rs = a0.x, re = a1.x;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int r0 = rs; r0 < re; r0 += RB) {
-                    float4 v[RB];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        const int r = r0 + j;
-                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < re) v[j] = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-                }
-                // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
-                // boundary is completed with atomicAdd onto the zero-initialised output
-                const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
-                float* o = a.agg + (size_t)a0.y * CN + 4 * c4;
-                if (whole) {
-                    *reinterpret_cast<float4*>(o) = acc;
-                } else {
-                    atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
-                }
-            }
-        };
-
         long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
         auto tick = [&](int i) {
             if (PROFILE && tid == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
@@ -341,13 +404,14 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
         if ((int)blockIdx.x < n_tiles) {
             prefetch(blockIdx.x);
             load_idx(blockIdx.x, t_my, s_my, e_first, e_last);
-            if (ATM) { s_my = load_src(blockIdx.x); s_ahead = load_src(blockIdx.x + gridDim.x); }
+            if (ATM) { s_my = load_src(blockIdx.x); if (!helpers) s_ahead = load_src(blockIdx.x + gridDim.x); }
             stage_ps(s_my);
             cp_async_wait<0>();
             group_sync(BAR_WORKERS, NW);
             load_pt(z, t_my);
             add_ps(z);
             group_sync(BAR_WORKERS, NW);     // the A region is about to be overwritten by the first tile's operand
+            if (helpers) bar_arrive(BAR_PS_FREE, NWH);
         }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1, buf ^= 1) {
             const int row0 = tile * TM;
@@ -409,10 +473,12 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 load_idx(next, n_t, n_s, n_first, n_last);
             }
             int s_ahead2 = -1;
-            if (ATM) { n_s = s_ahead; s_ahead2 = load_src(next + (int)gridDim.x); }
+            if (ATM && !helpers) { n_s = s_ahead; s_ahead2 = load_src(next + (int)gridDim.x); }
             tick(2);
-            if (have_prev && !(a.debug & 4)) segsum(buf ^ 1);
-            if (ATM && has_next && !(a.debug & 64)) stage_ps(n_s);     // the staging region is no operand: the copies overlap GEMM1
+            if (!helpers) {
+                if (have_prev && !(a.debug & 4)) segsum(buf ^ 1, tid >> 4, NW / 16, tid & 15);
+                if (ATM && has_next && !(a.debug & 64)) stage_ps(n_s);     // the staging region is no operand: the copies overlap GEMM1
+            }
             tick(3);
 
             // ---- (c) epilogue 1: z1 = D1 + (P_t + P_s) -> norm -> act -> y1 (hi | lo) back into TMEM ----
@@ -449,8 +515,12 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
 
             // ---- while GEMM2 runs: the next tile's projection gathers (consumed by its epilogue 1) ----
             if (has_next) load_pt(z, n_t);          // issue first: their latency overlaps the barrier below
-            cp_async_wait<0>();
-            group_sync(BAR_WORKERS, NW);            // every warp's staged rows (and this tile's ballots) are visible
+            if (helpers) {
+                group_sync(BAR_PS_READY, NWH);      // the helpers' staged rows (and this tile's ballots) are visible
+            } else {
+                cp_async_wait<0>();
+                group_sync(BAR_WORKERS, NW);        // every warp's staged rows (and this tile's ballots) are visible
+            }
             if (tid < TM) {   // segment start rows of this tile (consumed by the deferred segsum)
                 const unsigned* mk = mask_s + buf * 4;
                 const unsigned m = mk[warp];
@@ -465,6 +535,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 }
             }
             if (has_next) add_ps(z);
+            if (helpers) bar_arrive(BAR_PS_FREE, NWH);
             t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last; s_ahead = s_ahead2;
             tick(6);
 
@@ -482,17 +553,19 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(b2v[c], d[c]);
             }
             row_norm_act<CQ / 2, NQ>(m, CN, norm2, s2v, m2v, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
+            if (helpers) group_sync(BAR_STAGE_FREE, NWH);   // the previous tile's segmented sum has read the stage
 #pragma unroll
             for (int c4 = 0; c4 < CQ / 4; ++c4) {
                 const int chunk = (q * (CQ / 4) + c4) ^ (row & 7);
                 *reinterpret_cast<float4*>(stage + row * CN + chunk * 4) = make_float4(m[2 * c4].x, m[2 * c4].y, m[2 * c4 + 1].x, m[2 * c4 + 1].y);
             }
             tc::tc_fence_before();
-            group_sync(BAR_WORKERS, NW);
+            if (helpers) bar_arrive(BAR_STAGE_FULL, NWH);
+            else group_sync(BAR_WORKERS, NW);
             tick(8);
             have_prev = true;
         }
-        if (have_prev) segsum(buf ^ 1);
+        if (have_prev && !helpers) segsum(buf ^ 1, tid >> 4, NW / 16, tid & 15);
         tick(9);
         if (PROFILE && tid == 0 && a.prof != nullptr)
             for (int i = 0; i < 10; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];   // 10, 11: GEMM1 / GEMM2 durations (MMA warp)

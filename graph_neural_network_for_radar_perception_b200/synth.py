@@ -120,3 +120,83 @@ def make_labels(data: dict, labels_src: dict, adj_list: np.ndarray):
     return dict(edge_class=same.astype(np.int64), node_class=node_class,
                 node_offsets=offsets, cluster_node_idx=clusters,
                 cluster_labels=np.asarray(cluster_labels, dtype=np.int64))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Raw sliding-window input: what the reference's extract_and_sync_radar_data
+# (modules/data_utils/read_data.py:227-303) reads -- RadarScenes-shaped structured arrays `radar_data`, `odometry`,
+# the sensors.json mount dict and one window of create_dataset_sliding_window (read_data.py:202-224).
+# ---------------------------------------------------------------------------------------------------------------
+RADAR_DTYPE = np.dtype([('timestamp', '<i8'), ('sensor_id', 'u1'), ('range_sc', '<f4'), ('azimuth_sc', '<f4'),
+                        ('rcs', '<f4'), ('vr', '<f4'), ('vr_compensated', '<f4'), ('x_cc', '<f4'), ('y_cc', '<f4'),
+                        ('x_seq', '<f4'), ('y_seq', '<f4'), ('uuid', 'S32'), ('track_id', 'S32'), ('label_id', 'u1')])
+ODOMETRY_DTYPE = np.dtype([('timestamp', '<i8'), ('x_seq', '<f4'), ('y_seq', '<f4'), ('yaw_seq', '<f4'),
+                           ('vx', '<f4'), ('yaw_rate', '<f4')])
+RADAR_MOUNTS = {'radar_1': {'id': 1, 'x': 3.663, 'y': -0.873, 'yaw': -1.48418552},
+                'radar_2': {'id': 2, 'x': 3.86, 'y': -0.7, 'yaw': -0.436185662},
+                'radar_3': {'id': 3, 'x': 3.86, 'y': 0.7, 'yaw': 0.436},
+                'radar_4': {'id': 4, 'x': 3.663, 'y': 0.873, 'yaw': 1.484}}
+
+
+def make_raw_window(window_idx: int, n_scans: int = 10, points_per_scan: int = 300, seed: int = 1234,
+                    dynamic_fraction: float = 0.35):
+    """One synthetic sliding window: (radar_mount_data, radar_data_all_scenes, odometry_data_all_scenes,
+    windowed_data), the four arguments of the reference's extract_and_sync_radar_data.
+
+    The ego vehicle drives a gentle arc (vx ~ 8..15 m/s, |yaw rate| < 0.15 rad/s); scans cycle through the four
+    radars every ~16.5 ms; stationary detections carry the range rate the ego motion predicts plus N(0, 0.3^2)
+    noise, moving ones (tracked objects of random old-label class, or clutter without a track) an arbitrary one;
+    detections are spread over x_cc in [-20, 120) and y_cc in [-70, 70) so that the 100 m x 100 m region-of-interest
+    filter has something to drop."""
+    rng = np.random.default_rng([seed, 7919, window_idx])
+    vx0, w0 = rng.uniform(8.0, 15.0), rng.uniform(-0.15, 0.15)
+    odo = np.zeros(n_scans, dtype=ODOMETRY_DTYPE)
+    t = T0_US + np.arange(n_scans, dtype=np.int64) * SCAN_US + rng.integers(0, 400, n_scans)
+    dt = (t - t[0]) * 1e-6
+    yaw = 0.3 + w0 * dt
+    odo['timestamp'] = t
+    odo['yaw_seq'] = yaw
+    odo['x_seq'] = 120.0 + vx0 * dt * np.cos(yaw)
+    odo['y_seq'] = -40.0 + vx0 * dt * np.sin(yaw)
+    odo['vx'] = vx0 + 0.05 * rng.standard_normal(n_scans)
+    odo['yaw_rate'] = w0 + 0.005 * rng.standard_normal(n_scans)
+    counts = rng.integers(max(points_per_scan // 2, 1), points_per_scan * 3 // 2 + 1, n_scans)
+    bounds = np.concatenate([[0], np.cumsum(counts)])
+    rad = np.zeros(int(bounds[-1]), dtype=RADAR_DTYPE)
+    radar_ids = [int(1 + (window_idx + s) % 4) for s in range(n_scans)]
+    n_tracks = max(2, points_per_scan // 40)
+    track_names = np.array([('trk%03d_%05d' % (k, window_idx)).encode() for k in range(n_tracks)], dtype='S32')
+    track_class = rng.integers(0, 11, n_tracks)
+    for s in range(n_scans):
+        a, b = int(bounds[s]), int(bounds[s + 1])
+        n = b - a
+        m = RADAR_MOUNTS['radar_%d' % radar_ids[s]]
+        x = rng.uniform(-20.0, 120.0, n).astype(np.float32)
+        y = rng.uniform(-70.0, 70.0, n).astype(np.float32)
+        # sensor-frame azimuth of the detection
+        xs, ys = x - m['x'], y - m['y']
+        az = (np.arctan2(ys, xs) - m['yaw']).astype(np.float32)
+        vxs = float(odo['vx'][s]) - float(odo['yaw_rate'][s]) * m['y']
+        vys = float(odo['yaw_rate'][s]) * m['x']
+        c, sn = np.cos(-m['yaw']), np.sin(-m['yaw'])
+        vxs, vys = vxs * c - vys * sn, vxs * sn + vys * c
+        pred = -(vxs * np.cos(az.astype(np.float64)) + vys * np.sin(az.astype(np.float64)))
+        moving = rng.random(n) < dynamic_fraction
+        vr = np.where(moving, pred + rng.uniform(-12.0, 12.0, n), pred + 0.3 * rng.standard_normal(n))
+        has_track = moving & (rng.random(n) < 0.7)
+        which = rng.integers(0, n_tracks, n)
+        r = rad[a:b]
+        r['timestamp'] = t[s] + rng.integers(0, 200, n)
+        r['sensor_id'] = radar_ids[s]
+        r['range_sc'] = np.hypot(xs, ys)
+        r['azimuth_sc'] = az
+        r['rcs'] = -5.0 + 10.0 * rng.standard_normal(n)
+        r['vr'] = vr
+        r['vr_compensated'] = vr - pred
+        r['x_cc'], r['y_cc'] = x, y
+        r['track_id'] = np.where(has_track, track_names[which], np.array(b'', dtype='S32'))
+        r['label_id'] = np.where(has_track, track_class[which], 11)
+    windowed = {'current_timestamps': [int(v) for v in t], 'radar_id': radar_ids,
+                'odometry_timestamp': [int(v) for v in t], 'odometry_index': list(range(n_scans)),
+                'radar_data_indices': [[int(bounds[s]), int(bounds[s + 1])] for s in range(n_scans)]}
+    return RADAR_MOUNTS, rad, odo, windowed
