@@ -40,7 +40,7 @@ struct MpTcArgs {
     int act1, act2;
     int passes;             // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
     int debug;              // experiment switches (0 in production)
-    long long* prof;        // PROFILE builds: [grid][12] cycle counters of thread 0
+    long long* prof;        // PROFILE builds: [grid][worker warps][12] cycle counters of each worker warp's lane 0
 };
 
 extern int g_rowmlp_profile;
@@ -81,14 +81,23 @@ struct MpTcLayout {
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 
-// Thread roles: 128*NQ worker threads (thread = edge row x column quarter; loads, both epilogues, segmented sum)
-// + one extra warp whose lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy,
-// so it must not sit on a worker's critical path).
-// ATM: the A operand of GEMM1 (emb tile, hi | lo) lives in TMEM like GEMM2's (TS MMA).  An SS tf32 MMA with N = 128 reads
-// 8 KB of shared memory per 64 cycles = the whole 128 B/clk of the SM, which starves the workers' own LDS traffic (deferred
-// segmented sum) for the duration of GEMM1; with A in TMEM the tensor core reads only W_e, the fill is a tcgen05.st (no
-// proxy fence), and the shared-memory A region holds nothing but the staged P_s rows, so those can be copied during GEMM1.
-template <int CE, int H, int CN, int NQ, bool PROFILE, bool ATM>
+// Thread roles (128*NQ + 128 threads, one CTA per SM):
+//   workers   128*NQ threads, thread = edge row x column part: emb fill, both epilogues
+//   MMA warp  lane 0 issues every tcgen05.mma (the issue loop blocks while the tensor pipe is busy, so it must not sit
+//             on a worker's critical path)
+//   helpers   the three warps next to the MMA warp: P_s row staging of the next tile, segmented sum of the finished one
+// Both A operands live in TMEM (TS MMAs).  An SS tf32 MMA with N = 128 reads 8 KB of shared memory per 64 cycles = the
+// whole 128 B/clk of the SM, which starves every other shared-memory user for the duration of GEMM1; with the emb tile
+// in TMEM the tensor core reads only W_e, the fill is a tcgen05.st (no proxy fence), and the staging region is no
+// operand, so P_s rows can be copied at any time.
+// Order of work (default, `debug & 256` = 0): GEMM1 of tile i+1 is issued right behind GEMM2 of tile i and runs under
+// the workers' epilogue 2 of tile i:
+//     workers   epi1(i)  fill(i+1)  gathers(i+1)  | wait G2(i) |  epi2(i)      epi1(i+1) ...
+//     tensor             G2(i) ................................  G1(i+1) ....
+// TMEM: D1/y1 of tile i [0, 2H) is dead once G2(i) has completed, which the in-order tensor pipe guarantees before
+// G1(i+1) overwrites it; emb(i+1) [512-2CE, 512) is filled while G2(i) runs; D2(i) [2H, 2H+CN) is read while G1(i+1) runs.
+// `debug & 256` keeps the serial order fill -> G1 -> epi1 -> G2 -> epi2 per tile (A/B measurements).
+template <int CE, int H, int CN, int NQ, bool PROFILE>
 __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __grid_constant__ MpTcArgs a) {
     using L = MpTcLayout<CE, H, CN, NQ>;
     constexpr int TM = L::TM, NW = L::NT, NALL = L::NT + 128, HQ = H / NQ, CQ = CN / NQ, EQ = CE / NQ;
@@ -101,22 +110,19 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     // setmaxnreg.inc only draws from what setmaxnreg.dec released (measured: asking for the never-allocated remainder
     // of the register file as well blocks forever)
     static_assert(128 * (LAUNCH_REGS - AUX_REGS) >= NW * (WORKER_REGS - LAUNCH_REGS), "setmaxnreg pool");
-    // Helper warps (ATM only): the three warps next to the MMA issue warp take the two jobs that used to sit between
-    // the workers' fill and epilogue 1 -- the segmented sum of the previous tile and the P_s row staging of the next
-    // one (4 100 of 12 400 cycles per tile, profiles/README.md) -- so the workers' chain per tile is fill -> epi 1 ->
-    // epi 2 only.  Hand-over by four named barriers (workers + helpers):
+    // Hand-over between workers and helpers by four named barriers (workers + helpers):
     //   PS_READY   helpers -> workers : staged P_s rows of the next tile are in shared memory
     //   PS_FREE    workers -> helpers : they have been consumed (added into z), the region may be refilled
     //   STAGE_FULL workers -> helpers : messages + segment table of this tile are in shared memory
-    //   STAGE_FREE helpers -> workers : the segmented sum has read them, epilogue 2 may overwrite the stage
-    constexpr int NHELP = 96, NWH = NW + NHELP;
+    //   STAGE_FREE helpers -> workers : the segmented sum has read them (stage and segment table may be rewritten)
+    // (one helper warp stages, the other two sum: the two jobs must not wait for each other)
+    constexpr int NSTAGER = 32, NSUMMER = 64, NWS = NW + NSTAGER, NWG = NW + NSUMMER;
     constexpr int BAR_PS_READY = 8, BAR_PS_FREE = 9, BAR_STAGE_FULL = 10, BAR_STAGE_FREE = 11;
-    const bool helpers = ATM && !(a.debug & 128);
+    const bool pipelined = !(a.debug & 256);
     extern __shared__ __align__(1024) float smem[];
     float* w1s = smem + L::OFF_W1;
     float* w2s = smem + L::OFF_W2;
-    float* As = smem + L::OFF_A;
-    float* Gs = As;                          // P_s rows of the NEXT tile, staged while no GEMM1 reads A
+    float* Gs = smem + L::OFF_A;             // staged P_s rows of the next tile
     float* stage = smem + L::OFF_STAGE;
     int2* seg_s = reinterpret_cast<int2*>(smem + L::OFF_SEG);
     unsigned* mask_s = reinterpret_cast<unsigned*>(smem + L::OFF_MASK);
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid & 127, q = tid >> 7;
     const int bar_id = 1 + (row >> 5);       // the NQ warps that share rows [32k, 32k+32)
+    const int G = (int)gridDim.x;
 
     // ---- one-time setup: weights -> smem (already hi/lo split and chunk-major), barriers, TMEM ----
     {
@@ -152,131 +159,139 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     constexpr uint32_t COL_Y1LO = H, COL_D2 = 2 * H, COL_XS = 2 * H + CN;
     const int n_tiles = (a.n_edges + TM - 1) / TM;
     const int np = a.passes == 1 ? 1 : 3;
+    if ((int)blockIdx.x >= n_tiles) goto teardown;
 
-    // deferred segmented sum of the tile whose messages sit in `stage`.  16 threads (one float4 of columns each) per
-    // target segment, `ngroups` such groups; interior segments are whole CSR rows by construction (edges are
-    // target-major), only the first / last segment of a tile can be cut by its boundary.
-    auto segsum = [&](int buf, int s0, int ngroups, int c4) {
-        static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
-        // Every shared-memory round trip costs a few hundred cycles while the tensor core streams its operands, so the
-        // dependent chain is kept to: {count, bounds + target of my segment} -> {up to RB rows at once} -> store.
-        constexpr int RB = NQ == 4 ? 4 : 8;
-        const int2* sg = seg_s + buf * L::SEG;
-        const int2 h0 = sg[s0], h1 = sg[s0 + 1];          // speculative: entries beyond the count are never used
-        const int nseg = nseg_s[buf];
-        const int cut = cut_s[buf];            // bit 0: first segment continues from the previous tile; bit 1: last one continues
-        for (int s = s0; s < nseg; s += ngroups) {
-            const int2 a0 = s == s0 ? h0 : sg[s], a1 = s == s0 ? h1 : sg[s + 1];
-            const int rs = a0.x, re = a1.x;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r0 = rs; r0 < re; r0 += RB) {
-                float4 v[RB];
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    const int r = r0 + j;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < re) v[j] = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
-                }
-#pragma unroll
-                for (int j = 0; j < RB; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-            }
-            // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
-            // boundary is completed with atomicAdd onto the zero-initialised output
-            const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
-            float* o = a.agg + (size_t)a0.y * CN + 4 * c4;
-            if (whole) {
-                *reinterpret_cast<float4*>(o) = acc;
-            } else {
-                atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
-            }
-        }
-    };
-
-    if (tid >= NW) {
-        // =========================== MMA issue warpgroup (only its first warp works) ===========================
+    if (tid >= NW + 32) {
+        // =========================== helper warps ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
-        if (tid >= NW + 32) {
-            // =========================== helper warps ===========================
-            if (!helpers || (int)blockIdx.x >= n_tiles) goto teardown;
-            static_assert(H == 128, "one warp instruction copies one H-float row");
-            const int ht = tid - (NW + 32), hw = ht >> 5;        // helper warp hw stages rows hw, hw + 3, hw + 6, ...
-            constexpr int JMAX = (TM + 2) / 3;
-            int sa, sb;                                          // source ids of rows hw + 3 * lane and hw + 3 * (lane + 32)
+        static_assert(H == 128, "one warp instruction copies one H-float row");
+        static_assert(CN == 64, "segsum thread mapping assumes 16 float4 per message row");
+        const int ht = tid - (NW + 32);
+        if (ht < NSTAGER) {
+            // ---- staging warp: P_s[source] rows of the tile after next -> shared memory, whole 512-byte rows per warp
+            // instruction (cp.async, 16 B per lane; sector-granular per-thread gathers run ~2.5x slower,
+            // tools/micro/bench_gather.cu).  Row r is stored with its 16-byte chunks XOR-swizzled by (r & 7) so that the
+            // row-owning threads read it conflict-free.  The copies come from DRAM (P does not fit the L2): issue + landing
+            // take a few thousand cycles per tile, which is why this warp does nothing else.
+            int id[TM / 32];                                     // source ids of rows lane, lane + 32, ...
             auto load_ids = [&](int tile) {
-                const int ra = hw + 3 * lane, rb = ra + 96;
-                const int ea = tile * TM + ra, eb = tile * TM + rb;
-                sa = (tile < n_tiles && ea < a.n_edges) ? __ldg(a.src + ea) : -1;
-                sb = (tile < n_tiles && rb < TM && eb < a.n_edges) ? __ldg(a.src + eb) : -1;
+#pragma unroll
+                for (int k = 0; k < TM / 32; ++k) {
+                    const int e = tile * TM + k * 32 + lane;
+                    id[k] = (tile < n_tiles && e < a.n_edges) ? __ldg(a.src + e) : -1;
+                }
             };
             auto hstage = [&]() {
-#pragma unroll 4
-                for (int j = 0; j < JMAX; ++j) {
-                    const int r = hw + 3 * j;
-                    const int sn = __shfl_sync(0xffffffffu, j < 32 ? sa : sb, j & 31);
-                    if (r < TM && sn >= 0)
-                        cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+#pragma unroll
+                for (int k = 0; k < TM / 32; ++k) {
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        const int r = k * 32 + j;
+                        const int sn = __shfl_sync(0xffffffffu, id[k], j);
+                        if (sn >= 0) cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+                    }
                 }
                 cp_async_commit();
             };
-            const int G = (int)gridDim.x;
             load_ids(blockIdx.x + G);
-            group_sync(BAR_PS_FREE, NWH);                        // the workers' prologue is done with the staging region
+            group_sync(BAR_PS_FREE, NWS);                        // the workers' prologue is done with the staging region
             hstage();
             load_ids(blockIdx.x + 2 * G);
             cp_async_wait<0>();
-            bar_arrive(BAR_PS_READY, NWH);
-            bar_arrive(BAR_STAGE_FREE, NWH);
-            int hbuf = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += G, hbuf ^= 1) {
-                const bool last = tile + G >= n_tiles;
-                group_sync(BAR_PS_FREE, NWH);                    // rows of tile + G consumed -> stage those of tile + 2G
+            bar_arrive(BAR_PS_READY, NWS);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G) {
+                group_sync(BAR_PS_FREE, NWS);                    // rows of tile + G consumed -> stage those of tile + 2G
                 hstage();
                 load_ids(tile + 3 * G);
-                group_sync(BAR_STAGE_FULL, NWH);                 // messages of `tile` are staged
-                segsum(hbuf, ht >> 4, NHELP / 16, ht & 15);
-                __syncwarp();
                 cp_async_wait<0>();
-                if (!last) {
-                    bar_arrive(BAR_STAGE_FREE, NWH);
-                    bar_arrive(BAR_PS_READY, NWH);
-                }
+                if (tile + G < n_tiles) bar_arrive(BAR_PS_READY, NWS);
             }
-            goto teardown;
+        } else {
+            // ---- segmented-sum warps: the tile whose messages sit in `stage`.  16 threads (one float4 of columns each)
+            // per target segment; interior segments are whole CSR rows by construction (edges are target-major), only the
+            // first / last segment of a tile can be cut by its boundary.  Every shared-memory round trip costs several
+            // hundred cycles while the tensor core streams its operands, so the dependent chain is kept to: {count,
+            // bounds + target of my first three segments} -> {up to RB rows at once} -> store.
+            constexpr int RB = 8, NGRP = NSUMMER / 16, SPEC = 3;
+            const int hs = ht - NSTAGER, s0 = hs >> 4, c4 = hs & 15;
+            bar_arrive(BAR_STAGE_FREE, NWG);
+            int hbuf = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G, hbuf ^= 1) {
+                group_sync(BAR_STAGE_FULL, NWG);                 // messages of `tile` are staged
+                const int2* sg = seg_s + hbuf * L::SEG;
+                int2 h[SPEC + 1];                                // speculative: entries beyond the count are never used
+#pragma unroll
+                for (int k = 0; k < SPEC; ++k) h[k] = sg[min(s0 + k * NGRP, TM)];
+                int2 hn[SPEC];
+#pragma unroll
+                for (int k = 0; k < SPEC; ++k) hn[k] = sg[min(s0 + k * NGRP + 1, TM)];
+                const int nseg = nseg_s[hbuf];
+                const int cut = cut_s[hbuf];       // bit 0: first segment continues from the previous tile; bit 1: last one continues
+                int k = 0;
+                for (int s = s0; s < nseg; s += NGRP, ++k) {
+                    int2 a0, a1;
+                    if (k == 0) { a0 = h[0]; a1 = hn[0]; }
+                    else if (k == 1) { a0 = h[1]; a1 = hn[1]; }
+                    else if (k == 2) { a0 = h[2]; a1 = hn[2]; }
+                    else { a0 = sg[s]; a1 = sg[s + 1]; }
+                    const int rs = a0.x, re = a1.x;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r0 = rs; r0 < re; r0 += RB) {
+                        float4 v[RB];
+#pragma unroll
+                        for (int j = 0; j < RB; ++j) {
+                            const int r = r0 + j;
+                            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r < re) v[j] = *reinterpret_cast<const float4*>(stage + r * CN + ((c4 ^ (r & 7)) << 2));
+                        }
+#pragma unroll
+                        for (int j = 0; j < RB; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+                    }
+                    // whole rows are stored (source-ascending order, as the reference's index_add_); a row cut by a tile
+                    // boundary is completed with atomicAdd onto the zero-initialised output
+                    const bool whole = !((s == 0 && (cut & 1)) || (s == nseg - 1 && (cut & 2)));
+                    float* o = a.agg + (size_t)a0.y * CN + 4 * c4;
+                    if (whole) {
+                        *reinterpret_cast<float4*>(o) = acc;
+                    } else {
+                        atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+                    }
+                }
+                __syncwarp();
+                if (tile + G < n_tiles) bar_arrive(BAR_STAGE_FREE, NWG);
+            }
         }
+    } else if (tid >= NW) {
+        // =========================== MMA issue warp ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
         constexpr uint32_t IDESC1 = tc::idesc_tf32(TM, H);
         constexpr uint32_t IDESC2 = tc::idesc_tf32(TM, CN);
-        constexpr uint32_t LBO_A = TM * 16, LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
-        const uint32_t sA = tc::smem_u32(As), sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
-        long long g1 = 0, g2 = 0, tm0 = 0;
-        uint32_t mph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, mph ^= 1) {
-            // GEMM1: D1 = A * W1e^T.  3xTF32: small terms first (lo*hi, hi*lo), then hi*hi
+        constexpr uint32_t LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
+        const uint32_t sW1 = tc::smem_u32(w1s), sW2 = tc::smem_u32(w2s);
+        // 3xTF32: small terms first (lo*hi, hi*lo), then hi*hi
+        auto gemm1 = [&]() {   // D1 = emb (TMEM) * W1e^T
             group_sync(BAR_A_READY, NMMA);
             tc::tc_fence_after();
-            if (PROFILE) tm0 = clock64();
             if (lane == 0) {
                 bool acc = false;
                 for (int p = 0; p < np; ++p) {
                     const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
                     const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                    const uint64_t ad0 = tc::smem_desc(sA + pa * (L::A * 4), LBO_A, SBO);
                     const uint64_t bd0 = tc::smem_desc(sW1 + pb * (L::W1 * 4), LBO_W1, SBO);
                     const uint32_t ecol = tmem + (pa ? L::COL_ELO : L::COL_EHI);
 #pragma unroll
                     for (int ks = 0; ks < CE / 8; ++ks) {
-                        if (ATM) tc::mma_tf32_ts(tmem, ecol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
-                        else tc::mma_tf32_ss(tmem, ad0 + (uint64_t)((ks * 2 * LBO_A) >> 4), bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
+                        tc::mma_tf32_ts(tmem, ecol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, acc);
                         acc = true;
                     }
                 }
                 tc::mma_commit(&bars[0]);
-                if (PROFILE) { tc::mbar_wait(&bars[0], mph); g1 += clock64() - tm0; }   // issue -> completion as the tensor pipe sees it
             }
             __syncwarp();
-            // GEMM2: D2 = y1 * W2^T, A operand from TMEM
+        };
+        auto gemm2 = [&]() {   // D2 = y1 (TMEM) * W2^T
             group_sync(BAR_Y_READY, NMMA);
             tc::tc_fence_after();
-            if (PROFILE) tm0 = clock64();
             if (lane == 0) {
                 bool acc = false;
                 for (int p = 0; p < np; ++p) {
@@ -291,85 +306,57 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                     }
                 }
                 tc::mma_commit(&bars[1]);
-                if (PROFILE) { tc::mbar_wait(&bars[1], mph); g2 += clock64() - tm0; }
             }
             __syncwarp();
+        };
+        if (pipelined) {
+            gemm1();
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G) {
+                gemm2();
+                if (tile + G < n_tiles) gemm1();
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G) { gemm1(); gemm2(); }
         }
-        if (PROFILE && lane == 0 && a.prof != nullptr) { a.prof[blockIdx.x * 12 + 10] = g1; a.prof[blockIdx.x * 12 + 11] = g2; }
     } else {
         // =========================== worker warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
         const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
 
-        // emb tile -> A operand mapping: a warp instruction reads 8 rows x 64 B (4 chunks per row) and each
-        // quarter-warp writes one contiguous 128-byte core matrix (rgnn_tc.cuh).  UNITS such instructions per warp.
-        constexpr int UNITS = (TM / 8) * (CE / 16) / (NW / 32);
-        static_assert(UNITS >= 1 && (TM / 8) * (CE / 16) % (NW / 32) == 0, "emb tile load mapping");
-        const int r8 = lane & 7, kq = lane >> 3;
-        float4 pre[UNITS];
+        // emb rows of a tile, prefetched into registers one tile ahead: thread = (edge row, column part), EQ contiguous
+        // floats of its own row, 32 bytes per request
+        float4 pre[EQ / 4];
         auto prefetch = [&](int tile) {
-            const int row0 = tile * TM;
-            if constexpr (ATM) {   // thread = (edge row, column part): EQ contiguous floats of its own row, 32 bytes per request
-                static_assert(EQ / 4 == UNITS, "both prefetch mappings hold the same number of registers");
-                const bool v = row0 + row < a.n_edges;
-                const float* p = a.emb + (size_t)(v ? row0 + row : 0) * CE + q * EQ;
-#pragma unroll
-                for (int c8 = 0; c8 < EQ / 8; ++c8) {
-                    float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
-                    if (v) ldg256(p + 8 * c8, x0, x1, x2, x3);
-                    pre[2 * c8] = make_float4(x0.x, x0.y, x1.x, x1.y);
-                    pre[2 * c8 + 1] = make_float4(x2.x, x2.y, x3.x, x3.y);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < UNITS; ++u) {
-                    const int unit = warp * UNITS + u;
-                    const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
-                    pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row0 + r < a.n_edges) pre[u] = __ldg(reinterpret_cast<const float4*>(a.emb + (size_t)(row0 + r) * CE) + kc);
-                }
-            }
-        };
-
-        // per-row inputs of one tile, fetched ONE TILE AHEAD so that their latency hides behind the GEMMs:
-        //   t_my / s_my : target / source node of this thread's edge row;  e_first (lane 0 of the first four warps):
-        //   target of the edge just before this warp's rows;  e_last (thread TM-1): target of the edge after the tile
-        constexpr int RPW = TM / (NW / 32);     // P_s rows staged per warp
-        auto load_src = [&](int tile) {   // source of the (lane % RPW)-th row this warp stages
-            const int es = tile * TM + warp * RPW + (lane % RPW);
-            return (tile < n_tiles && es < a.n_edges) ? __ldg(a.src + es) : -1;
-        };
-        auto load_idx = [&](int tile, int& t_my, int& s_my, int& e_first, int& e_last) {
             const int e = tile * TM + row;
-            const bool v = e < a.n_edges;
-            t_my = v ? __ldg(a.tgt + e) : -1;
-            if (!ATM) s_my = load_src(tile);
-            e_first = (tid < TM && lane == 0 && v && e > 0) ? __ldg(a.tgt + e - 1) : -2;
-            e_last = (tid == TM - 1 && e + 1 < a.n_edges) ? __ldg(a.tgt + e + 1) : -3;
-        };
-        // P_s[source] rows of a tile -> shared memory, whole 512-byte rows per warp instruction (cp.async, 16 B per
-        // lane; sector-granular per-thread gathers run ~2.5x slower, tools/micro/bench_gather.cu).  Row r is stored
-        // with its 16-byte chunks XOR-swizzled by (r & 7) so that the row-owning threads read it conflict-free.
-        auto stage_ps = [&](int s_my) {
-            static_assert(H == 128, "one warp instruction copies one H-float row");
+            const bool v = tile < n_tiles && e < a.n_edges;
+            const float* p = a.emb + (size_t)(v ? e : 0) * CE + q * EQ;
 #pragma unroll
-            for (int i = 0; i < RPW; ++i) {
-                const int r = warp * RPW + i;
-                const int sn = __shfl_sync(0xffffffffu, s_my, i);
-                if (sn >= 0 && !(a.debug & 1))
-                    cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+            for (int c8 = 0; c8 < EQ / 8; ++c8) {
+                float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
+                if (v) ldg256(p + 8 * c8, x0, x1, x2, x3);
+                pre[2 * c8] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                pre[2 * c8 + 1] = make_float4(x2.x, x2.y, x3.x, x3.y);
             }
-            cp_async_commit();
         };
-        // z = P_t[target] + P_s[source] for this thread's quarter of the row (the hoisted node part of msg.0; the
-        // Linear bias is already inside P_t).  P_t rows repeat over consecutive edges: few distinct sectors per warp.
-        auto load_pt = [&](float2 (&z)[HQ / 2], int t_my) {
-            const bool v = t_my >= 0;
-            const float* Pt = a.P + (size_t)(v ? t_my : 0) * (2 * H) + q * HQ;
+        // per-row indices of one tile, fetched one tile ahead:  t : target node of this thread's edge row;  first (lane 0
+        // of the first four warps): target of the edge just before this warp's rows;  last (thread TM-1): target of the
+        // edge after the tile
+        auto load_idx = [&](int tile, int& t, int& first, int& last) {
+            const int e = tile * TM + row;
+            const bool v = tile < n_tiles && e < a.n_edges;
+            t = v ? __ldg(a.tgt + e) : -1;
+            first = (tid < TM && lane == 0 && v && e > 0) ? __ldg(a.tgt + e - 1) : -2;
+            last = (tid == TM - 1 && v && e + 1 < a.n_edges) ? __ldg(a.tgt + e + 1) : -3;
+        };
+        // z = P_t[target] + P_s[source] for this thread's part of the row (the hoisted node part of msg.0; the Linear
+        // bias is already inside P_t).  P_t rows repeat over consecutive edges: few distinct sectors per warp.
+        auto load_pt = [&](float2 (&z)[HQ / 2], int t) {
+            const bool v = t >= 0;
+            const float* Pt = a.P + (size_t)(v ? t : 0) * (2 * H) + q * HQ;
 #pragma unroll
             for (int c8 = 0; c8 < HQ / 8; ++c8) {
                 z[4 * c8] = z[4 * c8 + 1] = z[4 * c8 + 2] = z[4 * c8 + 3] = make_float2(0.f, 0.f);
-                if (v && !(a.debug & 2)) ldg256(Pt + 8 * c8, z[4 * c8], z[4 * c8 + 1], z[4 * c8 + 2], z[4 * c8 + 3]);
+                if (v) ldg256(Pt + 8 * c8, z[4 * c8], z[4 * c8 + 1], z[4 * c8 + 2], z[4 * c8 + 3]);
             }
         };
         auto add_ps = [&](float2 (&z)[HQ / 2]) {
@@ -383,9 +370,8 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
 
         long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
         auto tick = [&](int i) {
-            if (PROFILE && tid == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
+            if (PROFILE && lane == 0) { const long long now = clock64(); pt[i] += now - tlast; tlast = now; }
         };
-        if (PROFILE) tlast = clock64();
         // per-layer constants once, in registers (no global load may sit in the epilogues' dependent chains)
         const bool norm1 = a.s1 != nullptr, norm2 = a.s2 != nullptr;
         const float s1v = norm1 ? __ldg(a.s1) : 1.f, m1v = norm1 ? __ldg(a.m1) : 0.f;
@@ -394,98 +380,56 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
 #pragma unroll
         for (int c = 0; c < CQ / 2; ++c)
             b2v[c] = a.b2 ? __ldg(reinterpret_cast<const float2*>(a.b2 + q * CQ) + c) : make_float2(0.f, 0.f);
-        uint32_t phase = 0;
-        int buf = 0;
-        bool have_prev = false;
-        int t_my = -1, s_my = 0, e_first = -2, e_last = -3;
-        int s_ahead = -1;   // ATM: source ids of the NEXT tile, loaded one tile earlier than the other indices (their consumer, the
-                            // P_s staging, is issued right after the segmented sum and must not wait for a DRAM round trip)
         float2 z[HQ / 2];
-        if ((int)blockIdx.x < n_tiles) {
-            prefetch(blockIdx.x);
-            load_idx(blockIdx.x, t_my, s_my, e_first, e_last);
-            if (ATM) { s_my = load_src(blockIdx.x); if (!helpers) s_ahead = load_src(blockIdx.x + gridDim.x); }
-            stage_ps(s_my);
-            cp_async_wait<0>();
-            group_sync(BAR_WORKERS, NW);
-            load_pt(z, t_my);
-            add_ps(z);
-            group_sync(BAR_WORKERS, NW);     // the A region is about to be overwritten by the first tile's operand
-            if (helpers) bar_arrive(BAR_PS_FREE, NWH);
-        }
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1, buf ^= 1) {
-            const int row0 = tile * TM;
-            const int nvalid = min(TM, a.n_edges - row0);
 
-            tick(0);
-            // ---- (a) A operand (hi/lo split) from the prefetched registers; target ids and segment heads ----
-            {
-                float4* Ahi = reinterpret_cast<float4*>(As);
-                float4* Alo = reinterpret_cast<float4*>(As + L::A);
-                if (ATM) {
+        // ---- fill: emb tile (hi | lo split) from the prefetched registers -> TMEM; segment-head ballots of the tile ----
+        auto fill = [&](int fbuf, int nvalid, int t, int first, int last) {
 #pragma unroll
-                    for (int c = 0; c < EQ; c += 16) {
-                        float2 hi[8], lo[8];
+            for (int c = 0; c < EQ; c += 16) {
+                float2 hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 v = pre[c / 4 + j];
-                            tc::split_tf32(make_float2(v.x, v.y), hi[2 * j], lo[2 * j]);
-                            tc::split_tf32(make_float2(v.z, v.w), hi[2 * j + 1], lo[2 * j + 1]);
-                        }
-                        tc::tmem_st16(t_row + L::COL_EHI + q * EQ + c, hi);
-                        if (np != 1) tc::tmem_st16(t_row + L::COL_ELO + q * EQ + c, lo);
-                    }
-                    tc::tmem_wait_st();
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = pre[c / 4 + j];
+                    tc::split_tf32(make_float2(v.x, v.y), hi[2 * j], lo[2 * j]);
+                    tc::split_tf32(make_float2(v.z, v.w), hi[2 * j + 1], lo[2 * j + 1]);
                 }
-#pragma unroll
-                for (int u = 0; u < (ATM ? 0 : UNITS); ++u) {
-                    const int unit = warp * UNITS + u;
-                    const int r = (unit / (CE / 16)) * 8 + r8, kc = (unit % (CE / 16)) * 4 + kq;
-                    float4 hi, lo;
-                    tc::split_tf32(pre[u].x, hi.x, lo.x);
-                    tc::split_tf32(pre[u].y, hi.y, lo.y);
-                    tc::split_tf32(pre[u].z, hi.z, lo.z);
-                    tc::split_tf32(pre[u].w, hi.w, lo.w);
-                    Ahi[kc * TM + r] = hi;
-                    Alo[kc * TM + r] = lo;
-                }
-                if (tid < TM) {
-                    const bool v = tid < nvalid;
-                    int prev = __shfl_up_sync(0xffffffffu, t_my, 1);
-                    if (lane == 0) prev = e_first;
-                    const unsigned m = __ballot_sync(0xffffffffu, v && (tid == 0 || t_my != prev));
-                    if (lane == 0) mask_s[buf * 4 + warp] = m;
-                    if (tid == 0) cut_first_s[buf] = (e_first == t_my) ? 1 : 0;
-                    if (tid == nvalid - 1) cut_last_s[buf] = (tid == TM - 1 && e_last == t_my) ? 2 : 0;
-                }
+                tc::tmem_st16(t_row + L::COL_EHI + q * EQ + c, hi);
+                if (np != 1) tc::tmem_st16(t_row + L::COL_ELO + q * EQ + c, lo);
             }
-            if (!ATM) tc::fence_async_smem();
+            if (tid < TM) {
+                const bool v = tid < nvalid;
+                int prev = __shfl_up_sync(0xffffffffu, t, 1);
+                if (lane == 0) prev = first;
+                const unsigned m = __ballot_sync(0xffffffffu, v && (tid == 0 || t != prev));
+                if (lane == 0) mask_s[fbuf * 4 + warp] = m;
+                if (tid == 0) cut_first_s[fbuf] = (first == t) ? 1 : 0;
+                if (tid == nvalid - 1) cut_last_s[fbuf] = (tid == TM - 1 && last == t) ? 2 : 0;
+            }
+            tc::tmem_wait_st();
             tc::tc_fence_before();
             bar_arrive(BAR_A_READY, NMMA);          // -> MMA warp issues GEMM1
-            tick(1);
-
-            // ---- while GEMM1 runs: issue the next tile's emb / index loads, finish the previous tile's segsum ----
-            const int next = tile + (int)gridDim.x;
-            const bool has_next = next < n_tiles;
-            int n_t = -1, n_s = 0, n_first = -2, n_last = -3;
-            if (has_next) {
-                prefetch(next);
-                load_idx(next, n_t, n_s, n_first, n_last);
+        };
+        // ---- segment table {first row, target node} of a tile from its ballots (after a worker-wide barrier) ----
+        auto build_seg = [&](int sbuf, int nvalid, int t) {
+            if (tid < TM) {
+                const unsigned* mk = mask_s + sbuf * 4;
+                const unsigned m = mk[warp];
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
+                if ((m >> lane) & 1u) seg_s[sbuf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = make_int2(tid, t);
+                if (tid == TM - 1) {
+                    const int n = base + __popc(m);
+                    seg_s[sbuf * L::SEG + n] = make_int2(nvalid, -1);
+                    nseg_s[sbuf] = n;
+                    cut_s[sbuf] = cut_first_s[sbuf] | cut_last_s[sbuf];
+                }
             }
-            int s_ahead2 = -1;
-            if (ATM && !helpers) { n_s = s_ahead; s_ahead2 = load_src(next + (int)gridDim.x); }
-            tick(2);
-            if (!helpers) {
-                if (have_prev && !(a.debug & 4)) segsum(buf ^ 1, tid >> 4, NW / 16, tid & 15);
-                if (ATM && has_next && !(a.debug & 64)) stage_ps(n_s);     // the staging region is no operand: the copies overlap GEMM1
-            }
-            tick(3);
-
-            // ---- (c) epilogue 1: z1 = D1 + (P_t + P_s) -> norm -> act -> y1 (hi | lo) back into TMEM ----
+        };
+        // ---- epilogue 1: z1 = D1 + (P_t + P_s) -> norm -> act -> y1 (hi | lo) back into TMEM ----
+        auto epi1 = [&](uint32_t phase, int tk) {
             tc::mbar_wait(&bars[0], phase);
             tc::tc_fence_after();
-            tick(4);
-            if (!ATM && has_next) stage_ps(n_s);    // GEMM1 is done with the A region: next tile's P_s rows land there
+            tick(tk);
             {
                 float2 d[HQ / 2];
 #pragma unroll
@@ -511,39 +455,14 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             tc::tmem_wait_st();
             tc::tc_fence_before();
             bar_arrive(BAR_Y_READY, NMMA);          // -> MMA warp issues GEMM2
-            tick(5);
-
-            // ---- while GEMM2 runs: the next tile's projection gathers (consumed by its epilogue 1) ----
-            if (has_next) load_pt(z, n_t);          // issue first: their latency overlaps the barrier below
-            if (helpers) {
-                group_sync(BAR_PS_READY, NWH);      // the helpers' staged rows (and this tile's ballots) are visible
-            } else {
-                cp_async_wait<0>();
-                group_sync(BAR_WORKERS, NW);        // every warp's staged rows (and this tile's ballots) are visible
-            }
-            if (tid < TM) {   // segment start rows of this tile (consumed by the deferred segsum)
-                const unsigned* mk = mask_s + buf * 4;
-                const unsigned m = mk[warp];
-                int base = 0;
-                for (int w = 0; w < warp; ++w) base += __popc(mk[w]);
-                if ((m >> lane) & 1u) seg_s[buf * L::SEG + base + __popc(m & ((1u << lane) - 1u))] = make_int2(tid, t_my);
-                if (tid == TM - 1) {
-                    const int n = base + __popc(m);
-                    seg_s[buf * L::SEG + n] = make_int2(nvalid, -1);
-                    nseg_s[buf] = n;
-                    cut_s[buf] = cut_first_s[buf] | cut_last_s[buf];
-                }
-            }
-            if (has_next) add_ps(z);
-            if (helpers) bar_arrive(BAR_PS_FREE, NWH);
-            t_my = n_t; s_my = n_s; e_first = n_first; e_last = n_last; s_ahead = s_ahead2;
-            tick(6);
-
-            // ---- (e) epilogue 2: message = act(norm(D2 + b2)) -> stage ----
+            tick(tk + 1);
+        };
+        // ---- epilogue 2: message = act(norm(D2 + b2)) -> stage -> helpers' segmented sum ----
+        auto epi2 = [&](uint32_t phase, int tk, bool seg_next, int sbuf, int nv_next, int t_next) {
             float2 m[CQ / 2];
             tc::mbar_wait(&bars[1], phase);
             tc::tc_fence_after();
-            tick(7);
+            tick(tk);
             {
                 float2 d[CQ / 2];
 #pragma unroll
@@ -553,22 +472,93 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(b2v[c], d[c]);
             }
             row_norm_act<CQ / 2, NQ>(m, CN, norm2, s2v, m2v, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
-            if (helpers) group_sync(BAR_STAGE_FREE, NWH);   // the previous tile's segmented sum has read the stage
+            group_sync(BAR_STAGE_FREE, NWG);        // the previous tile's segmented sum has read the stage and its segment table
+            if (seg_next) build_seg(sbuf, nv_next, t_next);
 #pragma unroll
             for (int c4 = 0; c4 < CQ / 4; ++c4) {
                 const int chunk = (q * (CQ / 4) + c4) ^ (row & 7);
                 *reinterpret_cast<float4*>(stage + row * CN + chunk * 4) = make_float4(m[2 * c4].x, m[2 * c4].y, m[2 * c4 + 1].x, m[2 * c4 + 1].y);
             }
-            tc::tc_fence_before();
-            if (helpers) bar_arrive(BAR_STAGE_FULL, NWH);
-            else group_sync(BAR_WORKERS, NW);
-            tick(8);
-            have_prev = true;
+            tc::tc_fence_before();                  // D2 has been read: the next GEMM2 may overwrite it
+            bar_arrive(BAR_STAGE_FULL, NWG);
+            tick(tk + 1);
+        };
+
+        // ---- prologue: the first tile's inputs (the workers stage its P_s rows themselves) ----
+        int t_my, e_first, e_last;
+        {
+            constexpr int RPW = TM / (NW / 32);     // P_s rows staged per warp
+            const int es = blockIdx.x * TM + warp * RPW + (lane % RPW);
+            const int s_my = es < a.n_edges ? __ldg(a.src + es) : -1;
+            prefetch(blockIdx.x);
+            load_idx(blockIdx.x, t_my, e_first, e_last);
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp * RPW + i;
+                const int sn = __shfl_sync(0xffffffffu, s_my, i);
+                if (sn >= 0) cp_async16(Gs + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
+            }
+            cp_async_commit();
+            load_pt(z, t_my);
+            cp_async_wait<0>();
+            group_sync(BAR_WORKERS, NW);
+            add_ps(z);
         }
-        if (have_prev && !helpers) segsum(buf ^ 1, tid >> 4, NW / 16, tid & 15);
-        tick(9);
-        if (PROFILE && tid == 0 && a.prof != nullptr)
-            for (int i = 0; i < 10; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];   // 10, 11: GEMM1 / GEMM2 durations (MMA warp)
+        uint32_t phase = 0;
+        int buf = 0;
+        if (PROFILE) tlast = clock64();
+        if (pipelined) {
+            const int nv0 = min(TM, a.n_edges - (int)blockIdx.x * TM);
+            fill(0, nv0, t_my, e_first, e_last);                 // -> G1 of the first tile
+            group_sync(BAR_WORKERS, NW);                         // its ballots are visible
+            build_seg(0, nv0, t_my);
+            prefetch(blockIdx.x + G);
+            load_idx(blockIdx.x + G, t_my, e_first, e_last);     // from here on the index registers describe the NEXT tile
+            bar_arrive(BAR_PS_FREE, NWS);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G, phase ^= 1, buf ^= 1) {
+                const int next = tile + G;
+                const bool has_next = next < n_tiles;
+                const int nv_next = min(TM, a.n_edges - next * TM);
+                epi1(phase, 0);                                  // ticks 0 (wait G1), 1 (epilogue 1)
+                if (has_next) {
+                    fill(buf ^ 1, nv_next, t_my, e_first, e_last);   // -> G1(next), queued behind G2(tile)
+                    prefetch(next + G);
+                    load_pt(z, t_my);
+                }
+                tick(2);
+                group_sync(BAR_PS_READY, NWS);                   // staged P_s rows of `next` (and its ballots) are visible
+                tick(3);
+                if (has_next) add_ps(z);
+                bar_arrive(BAR_PS_FREE, NWS);
+                tick(4);
+                epi2(phase, 5, has_next, buf ^ 1, nv_next, t_my);    // ticks 5 (wait G2), 6 (epilogue 2 + next segment table)
+                load_idx(next + G, t_my, e_first, e_last);
+            }
+        } else {
+            bar_arrive(BAR_PS_FREE, NWS);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G, phase ^= 1, buf ^= 1) {
+                const int next = tile + G;
+                const bool has_next = next < n_tiles;
+                const int nvalid = min(TM, a.n_edges - tile * TM);
+                fill(buf, nvalid, t_my, e_first, e_last);
+                int n_t, n_first, n_last;
+                prefetch(next);
+                load_idx(next, n_t, n_first, n_last);
+                tick(2);
+                epi1(phase, 0);
+                if (has_next) load_pt(z, n_t);                   // issue first: their latency overlaps the barrier below
+                group_sync(BAR_PS_READY, NWS);                   // the helpers' staged rows (and this tile's ballots) are visible
+                tick(3);
+                build_seg(buf, nvalid, t_my);
+                if (has_next) add_ps(z);
+                bar_arrive(BAR_PS_FREE, NWS);
+                t_my = n_t; e_first = n_first; e_last = n_last;
+                tick(4);
+                epi2(phase, 5, false, 0, 0, 0);
+            }
+        }
+        if (PROFILE && lane == 0 && a.prof != nullptr)
+            for (int i = 0; i < 12; ++i) a.prof[(blockIdx.x * (NW / 32) + warp) * 12 + i] = pt[i];
     }
 
 teardown:
@@ -620,35 +610,38 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
     return RGNN_OK;
 }
 
-template <int NQ, bool ATM>
+template <int NQ>
 static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
     using L = MpTcLayout<64, 128, 64, NQ>;
     static bool configured = false;
     if (!configured) {
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
         configured = true;
     }
     const int n_tiles = (n_edges + L::TM - 1) / L::TM;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (g_debug & 8) {   // developer aid: per-phase cycle counters of thread 0, printed to stderr (synchronises!)
         long long* prof = nullptr;
-        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid));
+        constexpr int WW = L::NT / 32;
+        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid * WW));
         a.prof = prof;
-        mp_edge_tc_kernel<64, 128, 64, NQ, true, ATM><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
+        mp_edge_tc_kernel<64, 128, 64, NQ, true><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
-        long long* h = new long long[12 * grid];
-        RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost));
-        double tot[12] = {0};
-        for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) tot[i] += (double)h[b * 12 + i];
-        fprintf(stderr, "[mp_edge_tc profile NQ=%d] cycles per tile (thread 0 view):", NQ);
-        for (int i = 0; i < 12; ++i) fprintf(stderr, " p%d=%.0f", i, tot[i] / (double)n_tiles);
-        fprintf(stderr, "\n");
+        long long* h = new long long[12 * grid * WW];
+        RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * 12 * grid * WW, cudaMemcpyDeviceToHost));
+        for (int w = 0; w < WW; ++w) {
+            double tot[12] = {0};
+            for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) tot[i] += (double)h[(b * WW + w) * 12 + i];
+            fprintf(stderr, "[mp_edge_tc profile NQ=%d] cycles per tile, worker warp %d:", NQ, w);
+            for (int i = 0; i < 7; ++i) fprintf(stderr, " p%d=%.0f", i, tot[i] / (double)n_tiles);
+            fprintf(stderr, "\n");
+        }
         delete[] h;
         cudaFree(prof);
         return RGNN_OK;
     }
-    mp_edge_tc_kernel<64, 128, 64, NQ, false, ATM><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
+    mp_edge_tc_kernel<64, 128, 64, NQ, false><<<grid, L::NT + 128, L::BYTES, stream>>>(a);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
@@ -668,8 +661,7 @@ int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g
     a.debug = g_debug;
     a.prof = nullptr;
     (void)d;
-    if (g_debug & 32) return launch_mp_tc<2, false>(a, g.n_edges, stream);   // legacy: A operand of GEMM1 in shared memory
-    return (g_debug & 16) ? launch_mp_tc<4, true>(a, g.n_edges, stream) : launch_mp_tc<2, true>(a, g.n_edges, stream);
+    return (g_debug & 16) ? launch_mp_tc<4>(a, g.n_edges, stream) : launch_mp_tc<2>(a, g.n_edges, stream);
 }
 
 }  // namespace rgnn

@@ -231,6 +231,34 @@ int rgnn_cluster_proposals(const float* px, const float* py, const float* node_c
                            const int32_t* cl_members, int n_clusters, const float* noise_cov_host, float* mean, float* cov,
                            int32_t* size, int32_t* vote, void* stream);
 
+/* Sliding-window accumulation pre-pass: replaces the per-scan Python loop of
+ * extract_and_sync_radar_data (modules/data_utils/read_data.py:227-303: stationary gate meas_selection.py:39-70,169-200;
+ * vr_cartesian_vf and ego compensation meas_sync.py:15-21,44-102), the float32 casts / flip of get_data_for_datagen
+ * (read_data.py:524-537), generate_gt_labels (compute_groundtruth/compute_node_labels.py:71-86),
+ * grid_properties.select_meas_within_the_grid (compute_features/grid_features.py:162-173) and select_moving_data
+ * (compute_features/graph_features.py:167-182) for MANY windows per call.
+ * Inputs (device, detections of all windows concatenated, scans in window order): the RadarScenes radar_data fields
+ * x_cc, y_cc, vr, vr_compensated, azimuth_sc, rcs (float32), timestamp (int64), label_id (uint8), has_track (uint8,
+ * track_id != b''), point_scan (int32 row of scan_params for each detection); scan_params (n_scans_total, 9) float64 =
+ * [R00 R01 R10 R11 tx ty mount_yaw vx_sensor vy_sensor] with [R|t] = inv(T_curr) T_prev of the window (meas_sync.py:55)
+ * and the ego velocity at the sensor in the sensor frame (meas_selection.py:24-37), computed by the host in float64;
+ * window_ptr_dev (n_windows+1) detection offsets; flip_dev (n_windows) uint8 or NULL (flip_along_x augmentation).
+ * select != 0 keeps the detections inside [min_x,max_x) x [min_y,max_y) whose class label is not STATIC (7), select == 0
+ * keeps all.  Outputs (device, capacity n_points, windows back to back, detections in their original order):
+ * meas_px .. meas_rcs (float32), meas_timestamp (int64), class_labels (float32, labels.py:60-70 ids), src_index (int32,
+ * index of the detection inside its window), stationary_flag (n_points uint8, per INPUT detection, or NULL), out_ptr_dev
+ * (n_windows+1) offsets of the windows in the outputs = frame_ptr of rgnn_graph_build.  Positions, flags, labels and
+ * selection are exact; velocities within 2 ulp (float32 cos/sin). */
+size_t rgnn_accumulate_workspace_bytes(int n_windows);
+int rgnn_accumulate_windows(const float* x_cc, const float* y_cc, const float* vr, const float* vr_compensated,
+                            const float* azimuth_sc, const float* rcs, const int64_t* timestamp, const uint8_t* label_id,
+                            const uint8_t* has_track, const int32_t* point_scan, const double* scan_params,
+                            const int32_t* window_ptr_dev, const uint8_t* flip_dev, int n_windows, int n_points, int select,
+                            float min_x, float max_x, float min_y, float max_y, float* meas_px, float* meas_py,
+                            float* meas_vx, float* meas_vy, float* meas_vr, float* meas_rcs, int64_t* meas_timestamp,
+                            float* class_labels, int32_t* src_index, uint8_t* stationary_flag, int32_t* out_ptr_dev,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* predict_class on clusters found after the forward pass: the per-node stem output of predict_class is still in the
  * workspace of the preceding rgnn_detector_fwd call on the same graph (same `training` flag); g carries the new
  * cl_ptr / cl_members / n_clusters.  obj_cls (n_clusters, n_classes). */

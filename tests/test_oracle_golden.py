@@ -113,3 +113,33 @@ def test_cluster_oracle_matches_reference_dbscan(golden_dir):
                                              0.5 * np.eye(2, dtype=np.float32), g[p + 'node_logits'])
         assert np.array_equal(mean, g[p + 'prop_mean']) and np.array_equal(cov, g[p + 'prop_cov'])
         assert np.array_equal(size, g[p + 'prop_size']) and np.array_equal(vote, g[p + 'prop_vote'])
+
+
+def test_accumulation_oracle_matches_reference_bit_exact(golden_dir):
+    """the restated window accumulation (oracle/accumulate_np.py) against the outputs of the
+    reference's own extract_and_sync_radar_data / compute_ground_truth / select_* (tests/golden/make_golden_accumulate.py)."""
+    from oracle import accumulate_np as acc
+    from graph_neural_network_for_radar_perception_b200 import synth
+    g = np.load(os.path.join(golden_dir, 'accumulate.npz'))
+    n_cases = len([k for k in g.files if k.endswith('_args')])
+    assert n_cases >= 5
+    for c in range(n_cases):
+        p = f'c{c}_'
+        w, ns, pps, flip = (int(v) for v in g[p + 'args'])
+        mounts, rad, odo, win = synth.make_raw_window(w, ns, pps)
+        d = acc.accumulate_window(mounts, rad, odo, win, flip_along_x=bool(flip))
+        for k in ('meas_px', 'meas_py', 'meas_vx', 'meas_vy', 'meas_vr', 'meas_rcs', 'meas_timestamp', 'stationary_meas_flag'):
+            assert d[k].dtype == g[p + 'all_' + k].dtype, (c, k)
+            assert np.array_equal(d[k], g[p + 'all_' + k]), (c, k)
+        lab = acc.class_labels(d)
+        assert np.array_equal(lab, g[p + 'all_class_labels']), c
+        d_dyn, lab_dyn, idx = acc.select(d, lab)
+        for k in ('meas_px', 'meas_py', 'meas_vx', 'meas_vy', 'meas_vr', 'meas_rcs', 'meas_timestamp', 'meas_sensorid',
+                  'meas_label_id', 'stationary_meas_flag', 'meas_trackid'):
+            assert np.array_equal(d_dyn[k], g[p + 'dyn_' + k]), (c, k)
+        assert np.array_equal(lab_dyn, g[p + 'dyn_class_labels']), c
+        assert np.all(np.diff(idx) > 0)
+        # the fast (non-emulated) float64 product may differ in the last float64 bit only; after the float32 cast it is
+        # the same array on these fixtures
+        d2 = acc.accumulate_window(mounts, rad, odo, win, flip_along_x=bool(flip), exact_dgemm=False)
+        assert np.array_equal(d2['meas_px'], d['meas_px']) and np.array_equal(d2['meas_py'], d['meas_py'])

@@ -65,6 +65,17 @@ def main():
         s = stream_ptr()
         fn = lambda: check(lib().rgnn_conv_block_fwd(C.byref(conv), C.byref(g), ptr(x), ptr(e), ptr(out), ptr(agg),
                                                      ptr(proj), s), 'conv')
+    elif args.what == 'edges':      # the message kernel alone (its launch also zero-fills agg)
+        table = detector_table(det)
+        table.refill(None)
+        check(lib().rgnn_pack_detector(C.byref(table.det), stream_ptr()), 'pack')
+        e = torch.randn(E, 64, device=dev)
+        agg = torch.empty(N, 64, device=dev)
+        proj = torch.randn(N, 256, device=dev)
+        g = gb.c_struct()
+        conv = table.det.conv[0]
+        s = stream_ptr()
+        fn = lambda: check(lib().rgnn_conv_edges_fwd(C.byref(conv), C.byref(g), ptr(e), ptr(proj), ptr(agg), s), 'edges')
     elif args.what == 'forward':
         gb.set_clusters([[torch.arange(i, min(i + 4, n)) for i in range(0, n, 4)] for n in np.diff(fp)], fp[:-1], dev)
 
