@@ -310,11 +310,30 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             __syncwarp();
         };
         if (pipelined) {
+            // PROFILE: the tensor pipe's view (lane 0): m0 = wait for y1 (Y_READY), m1 = G2 issue -> G2 complete,
+            // m2 = G2 complete -> G1(next) complete (0 when it finished earlier), m3 = G2 issue -> G1(next) issued
+            long long m[4] = {0, 0, 0, 0};
+            uint32_t mph = 0;
             gemm1();
-            for (int tile = blockIdx.x; tile < n_tiles; tile += G) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += G, mph ^= 1) {
+                const bool nx = tile + G < n_tiles;
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (PROFILE) t0 = clock64();
                 gemm2();
-                if (tile + G < n_tiles) gemm1();
+                if (PROFILE) t1 = clock64();
+                if (nx) gemm1();
+                if (PROFILE && lane == 0) {
+                    t2 = clock64();
+                    tc::mbar_wait(&bars[1], mph);
+                    const long long t3 = clock64();
+                    if (nx) tc::mbar_wait(&bars[0], mph ^ 1);
+                    const long long t4 = clock64();
+                    m[0] += t1 - t0; m[1] += t3 - t1; m[2] += t4 - t3; m[3] += t2 - t1;
+                }
+                __syncwarp();
             }
+            if (PROFILE && lane == 0 && a.prof != nullptr)
+                for (int i = 0; i < 4; ++i) a.prof[(blockIdx.x * (NW / 32)) * 12 + 8 + i] = m[i];
         } else {
             for (int tile = blockIdx.x; tile < n_tiles; tile += G) { gemm1(); gemm2(); }
         }
@@ -472,7 +491,9 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 for (int c = 0; c < CQ / 2; ++c) m[c] = __fadd2_rn(b2v[c], d[c]);
             }
             row_norm_act<CQ / 2, NQ>(m, CN, norm2, s2v, m2v, a.act2 != 0, t_row + COL_XS + 2 * NQ, q, bar_id);
+            tick(tk + 1);                           // PROFILE: p6 = epilogue 2 arithmetic, p7 = wait for STAGE_FREE
             group_sync(BAR_STAGE_FREE, NWG);        // the previous tile's segmented sum has read the stage and its segment table
+            tick(7);
             if (seg_next) build_seg(sbuf, nv_next, t_next);
 #pragma unroll
             for (int c4 = 0; c4 < CQ / 4; ++c4) {
@@ -558,7 +579,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
             }
         }
         if (PROFILE && lane == 0 && a.prof != nullptr)
-            for (int i = 0; i < 12; ++i) a.prof[(blockIdx.x * (NW / 32) + warp) * 12 + i] = pt[i];
+            for (int i = 0; i < 8; ++i) a.prof[(blockIdx.x * (NW / 32) + warp) * 12 + i] = pt[i];   // 8..11 of warp 0: MMA warp
     }
 
 teardown:
@@ -634,7 +655,7 @@ static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
             double tot[12] = {0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) tot[i] += (double)h[(b * WW + w) * 12 + i];
             fprintf(stderr, "[mp_edge_tc profile NQ=%d] cycles per tile, worker warp %d:", NQ, w);
-            for (int i = 0; i < 7; ++i) fprintf(stderr, " p%d=%.0f", i, tot[i] / (double)n_tiles);
+            for (int i = 0; i < (w == 0 ? 12 : 7); ++i) fprintf(stderr, " p%d=%.0f", i, tot[i] / (double)n_tiles);
             fprintf(stderr, "\n");
         }
         delete[] h;

@@ -26,7 +26,13 @@ __device__ __forceinline__ float row_allreduce(float v, uint32_t t_cols, int q, 
 }
 
 // channel_normalization + LeakyReLU on a row whose C columns are spread over NQ threads (2*CP each, held as
-// register pairs for the packed f32x2 pipe).  Two-pass mean / unbiased std like the reference (common.py:215-220).
+// register pairs for the packed f32x2 pipe).  Mean / unbiased std as the reference's two-pass formula (common.py:215-220).
+// NQ == 2: each thread centres its own half on its own mean (two register-only passes) and the halves are merged by
+// the exact pairwise update  mean = (m0 + m1) / 2,  M2 = M2_0 + M2_1 + n (m0 - m1)^2 / 2  -- ONE exchange through TMEM
+// instead of two (every exchange is a tcgen05.st / wait / named barrier / tcgen05.ld / wait round trip on the critical
+// path of the epilogue), with the accuracy of the two-pass formula (no sum-of-squares cancellation).  The shift from
+// the own mean to the row mean is folded into the final affine.
+__device__ __forceinline__ void row_allreduce2(float& u, float& v, uint32_t t_cols, int q, int bar_id);
 template <int CP, int NQ>
 __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_norm, float scale, float shift,
                                              bool act, uint32_t t_cols /* 2*NQ spare TMEM columns of this row */, int q, int bar_id,
@@ -37,21 +43,42 @@ __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_no
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < CP; ++c) s2 = __fadd2_rn(s2, z[c]);
-        const float mean = row_allreduce<NQ>(s2.x + s2.y, t_cols, q, bar_id) / (float)C;
-        const float2 nm = make_float2(-mean, -mean);
-        float2 ss2 = make_float2(0.f, 0.f);
+        if (NQ == 2 && C == 4 * CP) {      // both threads own exactly C / 2 columns
+            const float m_own = (s2.x + s2.y) * (1.f / (float)(2 * CP));
+            const float2 nm = make_float2(-m_own, -m_own);
+            float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            z[c] = __fadd2_rn(z[c], nm);
-            ss2 = __ffma2_rn(z[c], z[c], ss2);
+            for (int c = 0; c < CP; ++c) {
+                z[c] = __fadd2_rn(z[c], nm);
+                ss2 = __ffma2_rn(z[c], z[c], ss2);
+            }
+            float msum = m_own, m2 = ss2.x + ss2.y;
+            row_allreduce2(msum, m2, t_cols, q, bar_id);        // msum = m0 + m1, m2 = M2_0 + M2_1
+            const float delta = m_own - 0.5f * msum;            // own mean - row mean = (m_own - m_other) / 2
+            const float ss = fmaf((float)(4 * CP) * delta, delta, m2);   // + n (m0 - m1)^2 / 2 with n = 2 CP, (m0 - m1) = 2 delta
+            const float sd = sqrtf(ss / (float)(C - 1));
+            if (sd_out != nullptr) *sd_out = sd;
+            const float k = scale / (sd + NORM_EPS);
+            const float2 k2 = make_float2(k, k), sh2 = make_float2(fmaf(delta, k, shift), fmaf(delta, k, shift));
+#pragma unroll
+            for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
+        } else {
+            const float mean = row_allreduce<NQ>(s2.x + s2.y, t_cols, q, bar_id) / (float)C;
+            const float2 nm = make_float2(-mean, -mean);
+            float2 ss2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                z[c] = __fadd2_rn(z[c], nm);
+                ss2 = __ffma2_rn(z[c], z[c], ss2);
+            }
+            const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
+            const float sd = sqrtf(ss / (float)(C - 1));
+            if (sd_out != nullptr) *sd_out = sd;
+            const float k = scale / (sd + NORM_EPS);
+            const float2 k2 = make_float2(k, k), sh2 = make_float2(shift, shift);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
         }
-        const float ss = row_allreduce<NQ>(ss2.x + ss2.y, t_cols + NQ, q, bar_id);
-        const float sd = sqrtf(ss / (float)(C - 1));
-        if (sd_out != nullptr) *sd_out = sd;
-        const float k = scale / (sd + NORM_EPS);
-        const float2 k2 = make_float2(k, k), sh2 = make_float2(shift, shift);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
     }
     if (act) {   // LeakyReLU(0.01): max(v, 0.01 v)
         const float2 sl = make_float2(LEAKY, LEAKY);
