@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
                                                           const int* __restrict__ frame_ptr, float eps2, int knn,
                                                           int ks /* row stride of knn_idx */,
                                                           int* __restrict__ knn_idx, int* __restrict__ degree) {
-    __shared__ float sx[KNN_TILE], sy[KNN_TILE];
+    // candidates of a tile as {x, y} pairs: one 16-byte shared-memory broadcast serves two candidates (the loop is bound by
+    // instruction issue: 2 LDS + 9 ALU per candidate before, 0.5 LDS + 8 ALU now); candidates are still visited in index order
+    __shared__ float4 sxy[KNN_TILE / 2];
+    float2* sxy2 = reinterpret_cast<float2*>(sxy);
     const int f = blockIdx.y;
     const int f0 = frame_ptr[f], f1 = frame_ptr[f + 1];
     const int nf = f1 - f0;
@@ -133,30 +136,37 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
     int bj[KCAP];
 #pragma unroll
     for (int q = 0; q < KCAP; ++q) { bd[q] = FLT_MAX; bj[q] = -1; }
-    int deg = 0;
+    int deg = -1;                      // the point itself (d = 0 <= eps2) is counted by the loop and taken out here
+    auto visit = [&](float xj, float yj, int j) {
+        const float d = dist2(xi, yi, xj, yj);
+        deg += d <= eps2 ? 1 : 0;
+        if (d < bd[KCAP - 1]) {
+#pragma unroll
+            for (int q = KCAP - 1; q > 0; --q) {
+                if (d < bd[q - 1]) { bd[q] = bd[q - 1]; bj[q] = bj[q - 1]; }
+                else if (d < bd[q]) { bd[q] = d; bj[q] = j; }
+            }
+            if (d < bd[0]) { bd[0] = d; bj[0] = j; }
+        }
+    };
     for (int t0 = 0; t0 < nf; t0 += KNN_TILE) {
         const int tn = min(KNN_TILE, nf - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < tn; i += KNN_THREADS) { sx[i] = px[f0 + t0 + i]; sy[i] = py[f0 + t0 + i]; }
+        for (int i = threadIdx.x; i < tn; i += KNN_THREADS) sxy2[i] = make_float2(px[f0 + t0 + i], py[f0 + t0 + i]);
         __syncthreads();
         if (active) {
-            for (int jj = 0; jj < tn; ++jj) {
-                const float d = dist2(xi, yi, sx[jj], sy[jj]);
-                const int j = t0 + jj;
-                deg += (d <= eps2 && j != li) ? 1 : 0;
-                if (d < bd[KCAP - 1]) {
-#pragma unroll
-                    for (int q = KCAP - 1; q > 0; --q) {
-                        if (d < bd[q - 1]) { bd[q] = bd[q - 1]; bj[q] = bj[q - 1]; }
-                        else if (d < bd[q]) { bd[q] = d; bj[q] = j; }
-                    }
-                    if (d < bd[0]) { bd[0] = d; bj[0] = j; }
-                }
+            int jj = 0;
+#pragma unroll 2
+            for (; jj + 1 < tn; jj += 2) {
+                const float4 c = sxy[jj >> 1];
+                visit(c.x, c.y, t0 + jj);
+                visit(c.z, c.w, t0 + jj + 1);
             }
+            if (jj < tn) { const float2 c = sxy2[jj]; visit(c.x, c.y, t0 + jj); }
         }
     }
     if (active) {
-        degree[gi] = deg;
+        degree[gi] = max(deg, 0);      // (eps2 < 0 or a NaN position: the point did not count itself either)
         const int kp1 = knn >= nf ? nf : knn + 1;   // graph_features.py:35
 #pragma unroll
         for (int q = 0; q < KCAP; ++q)
