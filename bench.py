@@ -152,6 +152,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # stdout carries exactly ONE line (the JSON): NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     _cabi.lib()
 

@@ -60,6 +60,29 @@ def test_blocks_standalone_match_oracle(ckpt_state_dict):
         assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), 'conv block')
 
 
+@pytest.mark.parametrize('n,e,layer', [(5000, 100_000, 0), (1500, 151_555, 3), (40_000, 420_000, 6)])
+def test_conv_block_many_tiles_per_cta_matches_oracle(ckpt_state_dict, n, e, layer):
+    """The persistent message kernel in its steady state: 780 - 3 280 tiles of 128 edges over 148 CTAs (5 - 22 tiles per CTA,
+    ragged last tile), so that every hand-over of its pipelined tile loop (GEMM1 of the next tile under epilogue 2, the
+    staging / segmented-sum helper warps, segments cut by tile boundaries, nodes without incoming edges) runs many
+    times; skewed target degrees (a few nodes own hundreds of edges, i.e. segments longer than a tile)."""
+    from oracle import model_torch as mt
+    g = torch.Generator().manual_seed(7 * n + layer)
+    m = load_model(ckpt_state_dict).pred.eval()
+    x = torch.randn(n, 64, generator=g)
+    emb = torch.randn(e, 64, generator=g)
+    src = torch.randint(0, n, (e,), generator=g)
+    tgt = torch.randint(0, n, (e,), generator=g)
+    heavy = torch.randint(0, n, (4,), generator=g)
+    tgt[: e // 50] = heavy[torch.randint(0, 4, (e // 50,), generator=g)]        # 2 % of the edges land on four nodes
+    tgt[tgt == 1] = 2                                                          # node 1 receives nothing
+    ei = torch.stack((src, tgt))
+    with torch.no_grad():
+        a = m.pass_messages.conv_blk[layer](x.cuda(), emb.cuda(), ei.cuda()).cpu()
+        b = mt.conv_block(ckpt_state_dict, f'pred.pass_messages.conv_blk.{layer}', x, emb, ei)
+    assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), f'conv block {layer}')
+
+
 @pytest.mark.parametrize('n_frames,n_pts', [(3, 150), (2, 1000)])
 def test_batched_forward_matches_oracle_per_frame(ckpt_state_dict, n_frames, n_pts):
     """Block-diagonal batch == the reference's per-frame loop (checked against the oracle frame by frame)."""
