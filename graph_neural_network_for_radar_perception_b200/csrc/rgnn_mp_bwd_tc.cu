@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(MB_NW + 128, 1) mp_edge_bwd_tc_kernel(const __
                     const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0), pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
                     const uint32_t acol = tmem + (pa ? a_lo : a_hi);
                     const uint64_t bd0 = tc::smem_desc(sB + pb * (MB_IMG * 2), lbo, 128);
-                    for (int ks = 0; ks < K / 8; ++ks) {
+#pragma unroll 8
+                    for (int ks = 0; ks < K / 8; ++ks) {      // (one lane issues: keep the k-steps independent, see rgnn_rowmlp_tc.cu)
                         tc::mma_tf32_ts(tmem + d_col, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc, acc);
                         acc = true;
                     }

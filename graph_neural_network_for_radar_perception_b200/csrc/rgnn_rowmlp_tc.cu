@@ -368,7 +368,6 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
     tc::tc_fence_after();
     const uint32_t tmem = *slot_ptr;
     const int n_tiles = (pg.n_rows + 127) / 128;
-    const int np = 3;
 
     if (tid >= RM_NW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -376,37 +375,61 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         if (w == 0) {
             // =========================== MMA issue warp ===========================
             uint32_t cnt = 0;
+            long long mt[3] = {0, 0, 0}, mlast = 0;   // PROFILE: wait for the A operand | wait for a weight chunk | issue
+            if (PROFILE) mlast = clock64();
+            auto mtick = [&](int i) { if (PROFILE) { const long long now = clock64(); mt[i] += now - mlast; mlast = now; } };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int s = 0; s < pg.n_stages; ++s) {
                     const TcStage& st = pg.st[s];
                     group_sync(BAR_Y_READY, RM_NW + 32);      // this stage's A operand is in TMEM
                     tc::tc_fence_after();
+                    mtick(0);
                     if (lane == 0) {
                         for (int j = 0; j < st.n_mma; ++j, ++cnt) {
                             const TcMma& m = st.mma[j];
                             const uint32_t slot = cnt % (uint32_t)pg.n_slots, par = (cnt / (uint32_t)pg.n_slots) & 1u;
                             tc::mbar_wait(&full[slot], par);
                             tc::tc_fence_after();
+                            mtick(1);
+                            // One lane issues every MMA, so this loop is a chain of dependent scalar instructions: with the
+                            // descriptor recomputed from the program fields inside a rolled loop it ran ~115 cycles per
+                            // MMA (an MMA executes in 16 - 32), i.e. the ISSUE paced every stage (measured: 22 k of 46 k
+                            // cycles per edge-encoder tile).  Fields in registers, four independent issues per trip.
                             const uint32_t sb = tc::smem_u32(ring + slot * TC_SLOT_FLOATS);
                             const uint32_t lbo = (uint32_t)m.ldn * 16u;
                             const uint32_t idesc = tc::idesc_tf32(128, m.N);
-                            bool acc = m.acc != 0;
-                            for (int p = 0; p < np; ++p) {     // 3xTF32, small terms first: lo*hi, hi*lo, hi*hi
-                                const int pa = p == 0 ? 1 : 0, pb = p == 1 ? 1 : 0;
-                                const uint32_t acol = tmem + (pa ? m.a_lo : m.a_hi);
-                                const uint64_t bd0 = tc::smem_desc(sb + pb * (uint32_t)(m.K * m.ldn * 4) + (uint32_t)m.n_off * 16u, lbo, 128);
-                                for (int ks = 0; ks < m.K / 8; ++ks) {
-                                    tc::mma_tf32_ts(tmem + m.d, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc, acc);
-                                    acc = true;
+                            const uint32_t dcol = tmem + (uint32_t)m.d, a_hi = tmem + (uint32_t)m.a_hi, a_lo = tmem + (uint32_t)m.a_lo;
+                            const uint32_t lo_off = (uint32_t)(m.K * m.ldn * 4), n_off = (uint32_t)m.n_off * 16u;
+                            const int k8 = m.K >> 3;
+                            const uint64_t step = (uint64_t)((2 * lbo) >> 4);     // descriptor address units per k-step
+                            uint32_t acc = m.acc != 0 ? 1u : 0u;
+#pragma unroll
+                            for (int p = 0; p < 3; ++p) {      // 3xTF32, small terms first: lo*hi, hi*lo, hi*hi
+                                uint32_t ac = p == 0 ? a_lo : a_hi;
+                                uint64_t bd = tc::smem_desc(sb + (p == 1 ? lo_off : 0u) + n_off, lbo, 128);
+                                int ks = 0;
+                                for (; ks + 4 <= k8; ks += 4) {
+                                    tc::mma_tf32_ts(dcol, ac, bd, idesc, acc != 0);
+                                    tc::mma_tf32_ts(dcol, ac + 8, bd + step, idesc, true);
+                                    tc::mma_tf32_ts(dcol, ac + 16, bd + 2 * step, idesc, true);
+                                    tc::mma_tf32_ts(dcol, ac + 24, bd + 3 * step, idesc, true);
+                                    acc = 1u; ac += 32; bd += 4 * step;
+                                }
+                                for (; ks < k8; ++ks) {
+                                    tc::mma_tf32_ts(dcol, ac, bd, idesc, acc != 0);
+                                    acc = 1u; ac += 8; bd += step;
                                 }
                             }
                             tc::mma_commit(&empty[slot]);     // slot reusable once these MMAs have read it
+                            mtick(2);
                         }
                         tc::mma_commit(d_ready);              // accumulator of the stage complete
                     }
                     __syncwarp();
                 }
             }
+            if (PROFILE && lane == 0 && prof != nullptr)
+                for (int i = 0; i < 3; ++i) prof[blockIdx.x * (2 * TC_MAX_STAGES + 5) + 2 * TC_MAX_STAGES + 2 + i] = mt[i];
         } else if (w == 1) {
             // =========================== weight load warp ===========================
             if (lane == 0) {
@@ -717,7 +740,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
             tick(1);
         }
         if (PROFILE && tid == 0 && prof != nullptr)
-            for (int i = 0; i < 2 * TC_MAX_STAGES + 2; ++i) prof[blockIdx.x * (2 * TC_MAX_STAGES + 2) + i] = pt[i];
+            for (int i = 0; i < 2 * TC_MAX_STAGES + 2; ++i) prof[blockIdx.x * (2 * TC_MAX_STAGES + 5) + i] = pt[i];
     }
 
     tc::tc_fence_before();
@@ -752,7 +775,7 @@ int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
     const int n_tiles = (pg.n_rows + 127) / 128;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (g_rowmlp_profile) {   // developer aid (rgnn_set_option("debug", 8)): per-stage cycles of worker thread 0; synchronises
-        constexpr int NP = 2 * TC_MAX_STAGES + 2;
+        constexpr int NP = 2 * TC_MAX_STAGES + 5;
         long long* prof = nullptr;
         RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * NP * grid));
         rowmlp_tc_kernel<true><<<grid, RM_NT, RM_SMEM, stream>>>(pg, prof);
@@ -763,7 +786,7 @@ int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
         for (int b = 0; b < grid; ++b) for (int i = 0; i < NP; ++i) tot[i] += (double)h[b * NP + i];
         fprintf(stderr, "[rowmlp_tc profile rows=%d stages=%d] cycles/tile: input=%.0f end=%.0f |", pg.n_rows, pg.n_stages, tot[0] / n_tiles, tot[1] / n_tiles);
         for (int s = 0; s < pg.n_stages; ++s) fprintf(stderr, " s%d wait=%.0f epi=%.0f", s, tot[2 + 2 * s] / n_tiles, tot[3 + 2 * s] / n_tiles);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " | mma warp: wait A=%.0f wait W=%.0f issue=%.0f\n", tot[NP - 3] / n_tiles, tot[NP - 2] / n_tiles, tot[NP - 1] / n_tiles);
         delete[] h;
         cudaFree(prof);
         return RGNN_OK;
