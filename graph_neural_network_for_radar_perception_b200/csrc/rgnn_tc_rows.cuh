@@ -62,6 +62,34 @@ __device__ __forceinline__ void row_norm_act(float2 (&z)[CP], int C, bool has_no
             const float2 k2 = make_float2(k, k), sh2 = make_float2(fmaf(delta, k, shift), fmaf(delta, k, shift));
 #pragma unroll
             for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
+        } else if (NQ == 4 && C == 8 * CP) {   // four threads own C / 4 columns each: the same merge over four partitions
+            const float m_own = (s2.x + s2.y) * (1.f / (float)(2 * CP));
+            const float2 nm = make_float2(-m_own, -m_own);
+            float2 ss2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                z[c] = __fadd2_rn(z[c], nm);
+                ss2 = __ffma2_rn(z[c], z[c], ss2);
+            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t_cols + 2 * q), "f"(m_own), "f"(ss2.x + ss2.y) : "memory");
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            group_sync(bar_id, 128);
+            tc::tc_fence_after();
+            float m0, v0, m1, v1, m2, v2, m3, v3;
+            tc::tmem_ld4(t_cols, m0, v0, m1, v1);
+            tc::tmem_ld4(t_cols + 4, m2, v2, m3, v3);
+            tc::tmem_wait_ld();
+            const float mean = 0.25f * ((m0 + m1) + (m2 + m3));
+            const float d0 = m0 - mean, d1 = m1 - mean, d2 = m2 - mean, d3 = m3 - mean;
+            const float ss = fmaf((float)(2 * CP), (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3), (v0 + v1) + (v2 + v3));
+            const float delta = m_own - mean;
+            const float sd = sqrtf(ss / (float)(C - 1));
+            if (sd_out != nullptr) *sd_out = sd;
+            const float k = scale / (sd + NORM_EPS);
+            const float2 k2 = make_float2(k, k), sh2 = make_float2(fmaf(delta, k, shift), fmaf(delta, k, shift));
+#pragma unroll
+            for (int c = 0; c < CP; ++c) z[c] = __ffma2_rn(z[c], k2, sh2);
         } else {
             const float mean = row_allreduce<NQ>(s2.x + s2.y, t_cols, q, bar_id) / (float)C;
             const float2 nm = make_float2(-mean, -mean);
