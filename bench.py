@@ -152,9 +152,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # stdout carries exactly ONE line (the JSON): NCCL's own log (the "NCCL version ..." banner of NCCL_DEBUG=VERSION / WARN
+        # goes to stdout by default) is sent to stderr instead
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _cabi.lib()
 
