@@ -60,3 +60,23 @@ def test_no_cuda_device_raises_instead_of_falling_back():
     from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
     with pytest.raises(RgnnError):
         acc.accumulate_windows([synth.make_raw_window(0, 2, 10)])
+
+
+def test_window_shards_of_two_ranks_concatenate_to_the_single_process_pack():
+    """Inference shards windows across ranks with no collective: the packs of the per-rank shards
+    (training.shard_range) are exactly the slices of the single-process pack, so per-rank results concatenate to the batch."""
+    from graph_neural_network_for_radar_perception_b200.training import shard_range
+    windows = [synth.make_raw_window(40 + i, 3 + i % 4, 30 + 7 * i) for i in range(7)]
+    raw, scan_of, params, raw_ptr = acc._pack_windows(windows)
+    got_raw, got_params, n0 = [], [], 0
+    for rank in range(2):
+        rg = shard_range(len(windows), rank, 2)
+        a, b = rg.start, rg.stop
+        r, s, p, rp = acc._pack_windows(windows[a:b])
+        assert rp == [v - raw_ptr[a] for v in raw_ptr[a:b + 1]]
+        got_raw.append(r)
+        got_params.append(p)
+        n0 += b - a
+    assert n0 == len(windows)
+    assert np.array_equal(np.concatenate(got_raw), raw)
+    assert np.array_equal(np.concatenate(got_params), params)
