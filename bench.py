@@ -127,7 +127,7 @@ def run_reference(args):
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{sample} frames x {args.points} points per step (graph build + forward, per-frame loop)'},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -152,9 +152,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): NCCL's own log (the "NCCL version ..." banner of NCCL_DEBUG=VERSION / WARN
-        # goes to stdout by default) is sent to stderr instead
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _cabi.lib()
 
@@ -288,7 +285,7 @@ def run_gpu(args):
         line['train'] = train
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -426,7 +423,29 @@ def cpu_baseline(args):
             'sample': f'{reps} x {sample} frames x {args.points} points (graph build + forward per frame, oracle port of the reference)'}
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE line, the JSON.  Libraries write there too (NCCL prints its version banner to stdout
+    from C), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the original descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
