@@ -542,9 +542,9 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
                 const int nv_next = min(TM, a.n_edges - next * TM);
                 epi1(phase, 0);                                  // ticks 0 (wait G1), 1 (epilogue 1)
                 if (has_next) {
+                    load_pt(z, t_my);                                // gathers first: their round trip runs under the fill
                     fill(buf ^ 1, nv_next, t_my, e_first, e_last);   // -> G1(next), queued behind G2(tile)
                     prefetch(next + G);
-                    load_pt(z, t_my);
                 }
                 tick(2);
                 group_sync(BAR_PS_READY, NWS);                   // staged P_s rows of `next` (and its ballots) are visible
