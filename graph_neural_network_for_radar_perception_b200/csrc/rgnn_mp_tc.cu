@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128 * NQ + 128, 1) mp_edge_tc_kernel(const __g
     constexpr int NMMA = NW + 32;            // threads that take part in the worker <-> MMA-warp barriers
     // register budget (setmaxnreg): the auxiliary warpgroup (MMA issue warp + three helper warps) keeps AUX_REGS,
     // the workers take the rest
-    constexpr int WORKER_REGS = NQ == 4 ? 104 : 208, AUX_REGS = NQ == 4 ? 64 : 80;
+    constexpr int WORKER_REGS = NQ == 4 ? 104 : 216, AUX_REGS = NQ == 4 ? 64 : 72;
     constexpr int LAUNCH_REGS = (65536 / NALL) / 8 * 8;     // what __launch_bounds__(NALL, 1) compiles to (168 / 96)
     static_assert(128 * AUX_REGS + NW * WORKER_REGS <= 65536, "register file");
     // setmaxnreg.inc only draws from what setmaxnreg.dec released (measured: asking for the never-allocated remainder
