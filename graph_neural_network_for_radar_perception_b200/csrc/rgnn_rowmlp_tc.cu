@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(RM_NT, 1) rowmlp_tc_kernel(const __grid_consta
         }
     } else {
         // =========================== worker warps ===========================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");   // all the auxiliary warpgroup released: 128 x (168 - 40) = 256 x (232 - 168)
         const int row = tid & 127, q = tid >> 7;
         const int bar_id = 1 + (row >> 5);
         const uint32_t t_row = tmem + ((uint32_t)(row & ~31) << 16);
