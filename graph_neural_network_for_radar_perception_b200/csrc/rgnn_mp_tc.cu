@@ -7,7 +7,7 @@
 // produced by the node kernel), so per edge
 //   z1 = emb_e W_e^T + P_t[tgt] + P_s[src]                  (msg.0's bias rides on P_t)
 // A CTA owns tiles of 128 target-major edges (UMMA M = 128, thread = TMEM lane = edge row):
-//   GEMM1  D1[128 x H]  = A(emb tile, TMEM) * W_e^T (smem)          tcgen05.mma kind::tf32, TS (ATM) / SS (legacy)
+//   GEMM1  D1[128 x H]  = A(emb tile, TMEM) * W_e^T (smem)          tcgen05.mma kind::tf32, TS
 //   epi 1  z1 -> mean / unbiased std / scalar affine / LeakyReLU -> y1, written back to TMEM (hi and lo parts)
 //   GEMM2  D2[128 x Cn] = y1 (TMEM) * W_2^T (smem)                  tcgen05.mma kind::tf32, TS
 //   epi 2  + b2 -> norm -> act -> staged in smem -> segmented sum over equal consecutive targets -> agg
