@@ -88,16 +88,38 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference algorithm)
 # -------------------------------------------------------------------------------------------------
-def cpu_frame_pass(sd, data, lab_src, train=False):
+def cpu_frame_pass(sd, data, lab_src, train=False, times=None):
+    """One frame through the oracle port of the reference's per-frame path (graph_features.py:58-164 ->
+    gnn_detector.py:141-162 [-> loss.py:37-76 + autograd when train]).  times (optional list of 3) accumulates the
+    seconds of the graph / forward / loss+backward legs (SURVEY.md section 8d asks for them separately)."""
     from oracle import graph_np, model_torch
+    t0 = time.perf_counter()
     adj = graph_np.adjacency_information(data, EPS2, KNN)
     nf = torch.from_numpy(graph_np.node_features(data, adj['degree'], True, 0, GRID_MAX_R, 0, GRID_MAX_TH).astype(np.float32))
     ef = torch.from_numpy(graph_np.edge_features(data, adj['adj_list']).astype(np.float32))
     ei = torch.from_numpy(adj['adj_list'])
+    t1 = time.perf_counter()
     lab = synth.make_labels(data, lab_src, adj['adj_list'])
     cl = [torch.from_numpy(c) for c in lab['cluster_node_idx']]
-    with torch.no_grad():
-        model_torch.detector_forward(sd, nf, ef, ei, cl)
+    t2 = time.perf_counter()
+    t3 = t2
+    if train:
+        sdg = {k: v.requires_grad_(True) for k, v in sd.items()}
+        labels = {'cluster_node_idx': [cl], **{k: [torch.from_numpy(lab[k])] for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}}
+        loss, _, _ = model_torch.training_forward(sdg, [nf], [ef], [ei], labels)
+        t3 = time.perf_counter()
+        sum(loss.values()).backward()
+        for v in sdg.values():
+            v.grad = None
+    else:
+        with torch.no_grad():
+            model_torch.detector_forward(sd, nf, ef, ei, cl)
+        t3 = time.perf_counter()
+    t4 = time.perf_counter()
+    if times is not None:
+        times[0] += t1 - t0
+        times[1] += t3 - t2
+        times[2] += t4 - t3
     return ei.shape[1]
 
 
@@ -172,7 +194,6 @@ def run_gpu(args):
         fp.append(fp[-1] + f[0]['meas_px'].shape[0])
     n_nodes = fp[-1]
     # clusters: synthetic blobs + singletons (labels are inputs of the object head)
-    from oracle import graph_np  # noqa: F401  (only the CPU-baseline leg below executes oracle code)
     pts_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     bf0 = gf.build_graph_batch(pts_dev, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
     cl_lists = []
@@ -402,25 +423,47 @@ def measure_train(dev, args, timed, rank, world):
 
 
 def cpu_baseline(args):
+    """The reference's CPU path (oracle port, pinned to the reference's own outputs) on this box's host cores, on a bounded
+    sample of the same workload: graph construction, eval forward and a training step (forward + losses + backward) timed
+    separately, plus the reference's own CPU-runnable case (BASELINE.json configs[0]: one frame of ~1000 points)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = torch.load(CKPT, map_location='cpu', weights_only=True)
     sample = max(1, min(args.ref_frames, args.frames))
     frames = make_frames(sample, args.points)
     cpu_frame_pass(sd, *frames[0])
+    times = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
-    edges = 0
-    reps = 0
+    edges = reps = 0
     while True:
         for f in frames:
-            edges += cpu_frame_pass(sd, *f)
+            edges += cpu_frame_pass(sd, *f, times=times)
         reps += 1
         if time.perf_counter() - t0 > 10.0 or reps >= 3:
             break
     dt = time.perf_counter() - t0
-    return {'value': reps * sample / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+    n = reps * sample
+    # training step, per-frame loop as Model_Training.forward does it (2-frame sample)
+    tt = [0.0, 0.0, 0.0]
+    tr_frames = frames[:2]
+    t1 = time.perf_counter()
+    tr_edges = sum(cpu_frame_pass(sd, *f, train=True, times=tt) for f in tr_frames)
+    dtr = time.perf_counter() - t1
+    # configs[0]: one frame of 1000 points
+    f1k = make_frames(1, 1000)[0]
+    cpu_frame_pass(sd, *f1k)
+    t1k = [0.0, 0.0, 0.0]
+    for _ in range(3):
+        cpu_frame_pass(sd, *f1k, times=t1k)
+    return {'value': n / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
             'edges_per_s': edges / dt,
-            'sample': f'{reps} x {sample} frames x {args.points} points (graph build + forward per frame, oracle port of the reference)'}
+            'sample': f'{reps} x {sample} frames x {args.points} points (graph build + forward per frame, oracle port of the reference)',
+            'ms_per_frame': {'graph_build_and_features': 1e3 * times[0] / n, 'forward': 1e3 * times[1] / n},
+            'train': {'value': len(tr_frames) / dtr, 'unit': 'frames/s', 'edges_per_s': tr_edges / dtr,
+                      'sample': f'{len(tr_frames)} frames x {args.points} points, forward + 4 losses + backward per frame (no optimizer step)',
+                      'ms_per_frame': {'graph_build_and_features': 1e3 * tt[0] / len(tr_frames), 'forward_and_loss': 1e3 * tt[1] / len(tr_frames),
+                                       'backward': 1e3 * tt[2] / len(tr_frames)}},
+            'c1_one_frame_1000_points_ms': {'graph_build_and_features': 1e3 * t1k[0] / 3, 'forward': 1e3 * t1k[1] / 3}}
 
 
 _JSON_FD = None

@@ -98,7 +98,7 @@ SIGNATURES = {
     'rgnn_detector_bwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_wgrad': (_I, [_V, _I, _I, _V, _I, _I, C.c_longlong, _V, _V, _V, _V]),
     'rgnn_losses_fwdbwd': (_I, [C.POINTER(rgnn_loss_cfg), _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I,
-                                C.c_double, C.c_double, C.c_double, _V, _V, _V, _V, _V, _V, _V]),
+                                C.c_double, C.c_double, C.c_double, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     'rgnn_sgd_step': (_I, [_V, _V, _V, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, _I, _V]),
     'rgnn_sgd_step_guarded': (_I, [_V, _V, _V, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, _I, _V, _V]),
 }

@@ -217,12 +217,16 @@ class GraphBatch:
         return g
 
     def set_clusters(self, cluster_lists: Sequence[Sequence[torch.Tensor]], node_offsets: Sequence[int], device):
-        """cluster_lists[f] = list of LongTensors with frame-local node ids (reference labels['cluster_node_idx'])."""
-        lens, parts, fptr = [], [], [0]
+        """cluster_lists[f] = list of LongTensors with frame-local node ids (reference labels['cluster_node_idx']).
+        One concatenation of all member tensors + one offset add (the offsets per member are expanded on the host from the
+        list lengths, which are host values anyway) instead of one tiny launch per cluster."""
+        import numpy as np
+        lens, parts, offs, fptr = [], [], [], [0]
         for clusters, off in zip(cluster_lists, node_offsets):
             for c in clusters:
                 lens.append(int(c.shape[0]))
-                parts.append(c if off == 0 else c + off)
+                parts.append(c)
+                offs.append(int(off))
             fptr.append(len(lens))
         self.n_clusters = len(lens)
         self.frame_cluster_ptr = fptr
@@ -230,15 +234,31 @@ class GraphBatch:
             self.cl_ptr = torch.zeros(1, dtype=torch.int32, device=device)
             self.cl_members = torch.zeros(1, dtype=torch.int32, device=device)
             return
-        cl_ptr = torch.zeros(self.n_clusters + 1, dtype=torch.int32)
-        cl_ptr[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
-        self.cl_ptr = cl_ptr.to(device, non_blocking=True)
-        self.cl_members = torch.cat([p.to(device) for p in parts]).to(torch.int32)
+        lens_np = np.asarray(lens, dtype=np.int64)
+        cl_ptr = np.zeros(self.n_clusters + 1, dtype=np.int32)
+        np.cumsum(lens_np, out=cl_ptr[1:])
+        self.cl_ptr = torch.from_numpy(cl_ptr).to(device, non_blocking=True)
+        dev = torch.device(device)
+        if any(p.device != dev for p in parts):
+            parts = [p.to(dev) for p in parts]
+        members = parts[0] if len(parts) == 1 else torch.cat(parts)
+        if any(offs):
+            off_dev = torch.from_numpy(np.repeat(np.asarray(offs, dtype=np.int64), lens_np)).to(dev, non_blocking=True)
+            members = members + off_dev
+        self.cl_members = members.to(torch.int32)
+
+    def set_clusters_packed(self, cl_ptr: torch.Tensor, cl_members: torch.Tensor, frame_cluster_ptr=None):
+        """Already packed clusters: cl_ptr (C+1,) / cl_members (global node ids), int32 on the device."""
+        self.cl_ptr, self.cl_members = cl_ptr, cl_members
+        self.n_clusters = int(cl_ptr.shape[0]) - 1
+        self.frame_cluster_ptr = frame_cluster_ptr
 
     @staticmethod
     def from_edge_index(edge_index: torch.Tensor, n_nodes: int) -> 'GraphBatch':
         """General path: any (2,E) int64 edge list with global node ids (reference edge_index convention:
-        row 0 = source, row 1 = target; gnn_blocks.py:57 flow='source_to_target')."""
+        row 0 = source, row 1 = target; gnn_blocks.py:57 flow='source_to_target').  The number of undirected links
+        (src < dst) sizes the link head's output, so it is the ONE value this path reads back from the device;
+        graph_features.build_graph_batch, whose adjacency is symmetric by construction, does not need it."""
         _require_cuda(edge_index)
         if edge_index.dtype != torch.int64:
             edge_index = edge_index.to(torch.int64)
@@ -327,7 +347,20 @@ class DetectorTable:
         _check_params(tab.tensors)
         self.tab, self.det, self.plan = tab, det, plan
         self.packed = torch.empty(tab.packed_floats(), dtype=torch.float32, device=tab.tensors[0].device)
+        self.packed_versions = None     # parameter versions the packed images were built from (None: stale)
         self.refill(grads)
+
+    def ensure_packed(self, stream):
+        """(Re)build the packed / split weight images only when a parameter changed since the last call: ATen bumps
+        `_version` on every in-place update (optimizers, load_state_dict, .copy_); code that writes parameter memory
+        behind ATen's back (DataParallelTrainer's fused SGD kernel) calls invalidate_packed()."""
+        versions = tuple(t._version for t in self.tab.tensors)
+        if self.packed_versions != versions:
+            check(lib().rgnn_pack_detector(C.byref(self.det), stream), 'rgnn_pack_detector')
+            self.packed_versions = versions
+
+    def invalidate_packed(self):
+        self.packed_versions = None
 
     def refill(self, grads=None):
         off = 0
@@ -364,7 +397,7 @@ class DetectorFn(torch.autograd.Function):
         table.refill(None)
         s = stream_ptr()
         g = gb.c_struct()
-        check(lib().rgnn_pack_detector(C.byref(table.det), s), 'rgnn_pack_detector')
+        table.ensure_packed(s)
         nbytes = lib().rgnn_detector_workspace_bytes(C.byref(table.det), C.byref(g), 1 if training else 0)
         if nbytes == 0:
             raise _cabi.RgnnError('rgnn_detector_workspace_bytes: ' + lib().rgnn_last_error().decode())

@@ -15,11 +15,14 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-    static int n = 0;
+    static int cache[64] = {0};         // per device; a racing first call writes the same value twice
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& n = cache[dev & 63];
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n = v;
     }
     return n;
 }

@@ -553,11 +553,11 @@ int launch_program(const Program& p_in, cudaStream_t stream) {
     const size_t smem = program_smem_bytes(p);
     RGNN_REQUIRE(smem <= SMEM_LIMIT, "tile program needs %zu bytes of shared memory (> %zu)", smem, SMEM_LIMIT);
     RGNN_REQUIRE(p.tr == 64 || p.tr == 32, "tile program with tr=%d", p.tr);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(tile_program_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(tile_program_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        configured = true;
+        once.mark();
     }
     const int n_tiles = (p.n_rows + p.tr - 1) / p.tr;
     // two CTAs share an SM when their shared memory allows it: one CTA's global-memory phases overlap the other's math

@@ -14,23 +14,28 @@
 namespace rgnn {
 
 __device__ __forceinline__ int uf_find(int* parent, int i) {
-    int p = parent[i];
+    int p = __ldcg(parent + i);  // L2 reads: other CTAs hook roots concurrently, an L1 line may be stale
     while (p != i) {            // path halving; concurrent hooks only ever lower parent[] towards smaller ids
-        const int gp = parent[p];
+        const int gp = __ldcg(parent + p);
         if (gp != p) parent[i] = gp;
         i = p;
-        p = parent[i];
+        p = __ldcg(parent + i);
     }
     return i;
 }
 
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-    while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
-        if (a == b) return;
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    while (a != b) {
         if (a < b) { const int t = a; a = b; b = t; }          // a > b: hook a under b
-        if (atomicCAS(parent + a, a, b) == a) return;
+        const int seen = atomicCAS(parent + a, a, b);
+        if (seen == a) return;
+        // a is no longer a root: `seen` is the parent another thread gave it.  Continue from the value the atomic itself
+        // returned (an L2-coherent read) instead of re-reading parent[] through L1, where a stale line could keep
+        // returning the old root and the loop would only end when that line happens to be evicted.
+        a = uf_find(parent, seen);
+        b = uf_find(parent, b);
     }
 }
 

@@ -16,7 +16,17 @@ constexpr float NORM_EPS = 1e-5f;     // reference modules/neural_net/constants.
 constexpr float LEAKY = 0.01f;        // reference modules/neural_net/constants.py:10
 
 void set_error(const char* fmt, ...);
-int sm_count();
+int sm_count();          // of the CURRENT device
+
+// Per-device one-time setup at a launch site (cudaFuncSetAttribute is a per-device setting): `needed()` is true until
+// `mark()` has run on the current device.  The attribute calls are idempotent, so two threads racing through the same
+// site is harmless; the bit mask is atomic.
+struct PerDeviceOnce {
+    unsigned long long done = 0;
+    static int device() { int d = 0; cudaGetDevice(&d); return d & 63; }
+    bool needed() const { return ((__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> device()) & 1ull) == 0; }
+    void mark() { __atomic_fetch_or(&done, 1ull << device(), __ATOMIC_RELEASE); }
+};
 
 #define RGNN_CHECK_CUDA(expr)                                                          \
     do {                                                                               \

@@ -15,6 +15,8 @@ struct LossArgs {
     float *g_node_cls, *g_node_off, *g_link, *g_obj;
     double* losses;
     int* correct;
+    const double* counts_dev;   // optional (3): device-resident global counts (all-reduced on the stream); overrides inv_*
+    float* dp_tail;             // optional (5): [0] = 1 when a loss term is NaN, [1..4] += this rank's weighted loss shares
 };
 
 __device__ __forceinline__ float softplus(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
@@ -71,28 +73,35 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int C = a.cfg.n_classes, CE = a.cfg.n_edge_classes;
+    float inv_nodes = a.inv_nodes, inv_und = a.inv_und, inv_clusters = a.inv_clusters;
+    if (a.counts_dev != nullptr) {      // data parallel: the counts were summed over the ranks on this stream, never seen by the host
+        const double cn = a.counts_dev[0], cu = a.counts_dev[1], cc = a.counts_dev[2];
+        inv_nodes = cn > 0. ? (float)(1.0 / cn) : 0.f;
+        inv_und = cu > 0. ? (float)(1.0 / cu) : 0.f;
+        inv_clusters = cc > 0. ? (float)(1.0 / cc) : 0.f;
+    }
     for (int i = t0; i < a.n_nodes; i += stride) {
         bool hit;
         const int y = (int)a.node_gt[i];
-        acc[0] += ce_row(a.node_cls + (size_t)i * C, C, y, a.cfg.class_weights[y], a.cfg.w_node_cls * a.inv_nodes,
+        acc[0] += ce_row(a.node_cls + (size_t)i * C, C, y, a.cfg.class_weights[y], a.cfg.w_node_cls * inv_nodes,
                          a.g_node_cls ? a.g_node_cls + (size_t)i * C : nullptr, &hit);
         hits[0] += hit;
         const float dx = a.node_off[2 * i] - a.off_gt[2 * i], dy = a.node_off[2 * i + 1] - a.off_gt[2 * i + 1];
         acc[1] += 0.5f * (dx * dx + dy * dy);
         if (a.g_node_off) {
-            a.g_node_off[2 * i] = a.cfg.w_node_reg * a.inv_nodes * dx;
-            a.g_node_off[2 * i + 1] = a.cfg.w_node_reg * a.inv_nodes * dy;
+            a.g_node_off[2 * i] = a.cfg.w_node_reg * inv_nodes * dx;
+            a.g_node_off[2 * i + 1] = a.cfg.w_node_reg * inv_nodes * dy;
         }
     }
     for (int i = t0; i < a.n_und; i += stride) {
         bool hit;
         acc[2] += focal_row(a.link_cls + (size_t)i * CE, CE, (int)a.link_gt[i], a.cfg.focal_alpha, a.cfg.focal_gamma,
-                            a.cfg.w_edge_cls * a.inv_und, a.g_link ? a.g_link + (size_t)i * CE : nullptr, &hit);
+                            a.cfg.w_edge_cls * inv_und, a.g_link ? a.g_link + (size_t)i * CE : nullptr, &hit);
         hits[1] += hit;
     }
     for (int i = t0; i < a.n_clusters; i += stride) {
         bool hit;
-        acc[3] += ce_row(a.obj_cls + (size_t)i * C, C, (int)a.obj_gt[i], 1.f, a.cfg.w_obj_cls * a.inv_clusters,
+        acc[3] += ce_row(a.obj_cls + (size_t)i * C, C, (int)a.obj_gt[i], 1.f, a.cfg.w_obj_cls * inv_clusters,
                          a.g_obj ? a.g_obj + (size_t)i * C : nullptr, &hit);
         hits[2] += hit;
     }
@@ -111,11 +120,16 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
     if (threadIdx.x < 4) {
         double v = 0.;
         for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
-        const double scale = threadIdx.x == 0 ? (double)a.cfg.w_node_cls * a.inv_nodes
-                           : threadIdx.x == 1 ? (double)a.cfg.w_node_reg * a.inv_nodes
-                           : threadIdx.x == 2 ? (double)a.cfg.w_edge_cls * a.inv_und
-                                              : (double)a.cfg.w_obj_cls * a.inv_clusters;
+        const double scale = threadIdx.x == 0 ? (double)a.cfg.w_node_cls * inv_nodes
+                           : threadIdx.x == 1 ? (double)a.cfg.w_node_reg * inv_nodes
+                           : threadIdx.x == 2 ? (double)a.cfg.w_edge_cls * inv_und
+                                              : (double)a.cfg.w_obj_cls * inv_clusters;
         atomicAdd(a.losses + threadIdx.x, v * scale);
+        if (a.dp_tail != nullptr) {
+            // a NaN total has a NaN partial: the reference's skip_batch test (gnn/training.py:40-45) without a host read
+            if (v != v) a.dp_tail[0] = 1.f;
+            atomicAdd(a.dp_tail + 1 + threadIdx.x, (float)(v * scale));
+        }
     } else if (threadIdx.x >= 32 && threadIdx.x < 35) {
         int v = 0;
         for (int w = 0; w < 8; ++w) v += shc[threadIdx.x - 32][w];
@@ -149,7 +163,8 @@ extern "C" int rgnn_losses_fwdbwd(const rgnn_loss_cfg* cfg, const float* node_cl
                                   const float* node_off_gt, const int64_t* link_gt, const int64_t* obj_gt, int n_nodes,
                                   int n_und, int n_clusters, double count_nodes, double count_und, double count_clusters,
                                   float* grad_node_cls, float* grad_node_off, float* grad_link_cls, float* grad_obj_cls,
-                                  double* losses_out, int32_t* correct_out, void* stream_) {
+                                  double* losses_out, int32_t* correct_out, const double* counts_dev, float* dp_tail,
+                                  void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     RGNN_REQUIRE(cfg->n_classes >= 1 && cfg->n_classes <= 16 && cfg->n_edge_classes >= 1 && cfg->n_edge_classes <= 16,
                  "losses: class counts out of range");
@@ -163,6 +178,7 @@ extern "C" int rgnn_losses_fwdbwd(const rgnn_loss_cfg* cfg, const float* node_cl
     a.inv_clusters = count_clusters > 0 ? (float)(1.0 / count_clusters) : 0.f;
     a.g_node_cls = grad_node_cls; a.g_node_off = grad_node_off; a.g_link = grad_link_cls; a.g_obj = grad_obj_cls;
     a.losses = losses_out; a.correct = correct_out;
+    a.counts_dev = counts_dev; a.dp_tail = dp_tail;
     RGNN_CHECK_CUDA(cudaMemsetAsync(losses_out, 0, 4 * sizeof(double), stream));
     RGNN_CHECK_CUDA(cudaMemsetAsync(correct_out, 0, 3 * sizeof(int32_t), stream));
     int m = n_nodes > n_und ? n_nodes : n_und;

@@ -660,10 +660,10 @@ int run_conv_edges_bwd_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_grap
     float* y1 = scratch;
     float* dz1 = y1 + E * d.h;
     float* dz2 = dz1 + E * d.h;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM));
-        configured = true;
+        once.mark();
     }
     MpBwdArgs a;
     a.emb = emb; a.P = P; a.dagg = dagg; a.tgt = g.tgt; a.src = g.src;

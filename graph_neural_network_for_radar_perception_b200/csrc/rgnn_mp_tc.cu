@@ -634,11 +634,11 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
 template <int NQ>
 static int launch_mp_tc(MpTcArgs& a, int n_edges, cudaStream_t stream) {
     using L = MpTcLayout<64, 128, 64, NQ>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_tc_kernel<64, 128, 64, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        configured = true;
+        once.mark();
     }
     const int n_tiles = (n_edges + L::TM - 1) / L::TM;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();

@@ -766,11 +766,11 @@ int g_rowmlp_profile = 0;
 
 int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
     if (pg.n_rows <= 0) return RGNN_OK;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(rowmlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
-        configured = true;
+        once.mark();
     }
     const int n_tiles = (pg.n_rows + 127) / 128;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();

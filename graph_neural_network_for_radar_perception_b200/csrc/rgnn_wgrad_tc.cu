@@ -445,11 +445,11 @@ int launch_wgrad_tc(const float* A, int lda, int wa, const float* B, int ldb, in
                     long long sn, float* colsum_a, float* colsum_b, cudaStream_t stream, const int* b_ridx) {
     if (rows <= 0 || (dst == nullptr && colsum_a == nullptr && colsum_b == nullptr)) return RGNN_OK;
     RGNN_REQUIRE(wa >= 1 && wa <= WG_MA && wb >= 1 && wb <= WG_NB_MAX, "wgrad: operand widths %d x %d outside 128 x 256", wa, wb);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgLayout<2>::SMEM));
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgLayout<8>::SMEM));
-        configured = true;
+        once.mark();
     }
     WgradArgs a;
     a.A = A; a.B = B; a.lda = lda; a.ldb = ldb; a.wa = wa; a.wb = wb;

@@ -126,7 +126,6 @@ class Model_Training(nn.Module):
         self.device = device
         self.offset_mu = net_config.offset_mu
         self.offset_sigma = net_config.offset_sigma
-        self.global_counts = None    # set by the data-parallel driver: (N, E_u, C) summed over ranks
 
     @staticmethod
     def pack_batch(node_features: List[torch.Tensor], edge_features: List[torch.Tensor],
@@ -144,14 +143,21 @@ class Model_Training(nn.Module):
         gb, nf, ef = self.pack_batch(node_features, edge_features, edge_index, labels['cluster_node_idx'])
         return self.forward_packed(gb, nf, ef, labels)
 
-    def forward_packed(self, gb: GraphBatch, nf: torch.Tensor, ef: torch.Tensor, labels: Dict[str, List[torch.Tensor]]):
+    def forward_packed(self, gb: GraphBatch, nf: torch.Tensor, ef: torch.Tensor, labels: Dict[str, List[torch.Tensor]],
+                       global_counts=None, dp_tail: Optional[torch.Tensor] = None):
+        """global_counts / dp_tail are supplied by DataParallelTrainer.step only (counts summed over the ranks, NaN flag +
+        loss shares that ride in the gradient all-reduce); every other caller divides by this batch's own counts, as
+        the reference does (gnn/loss.py:58-70)."""
         node_cls, node_off, link_cls, obj_cls = run_detector(self.pred, gb, nf, ef)
         cat = lambda v: v if isinstance(v, torch.Tensor) else torch.concat(v, dim=0)
         obj_gt, edge_gt, node_gt = cat(labels['cluster_labels']), cat(labels['edge_class']), cat(labels['node_class'])
+        # Like the reference (gnn_detector.py:463-465) the in-place normalize_gt_offsets acts on the FRESH tensor that
+        # torch.concat returns, so the caller's per-frame label tensors keep their values; an already concatenated tensor
+        # (this library's packed fast path) is cloned for the same reason.
         off = labels['node_offsets']
         off = off.clone() if isinstance(off, torch.Tensor) else torch.concat(off, dim=0)
         off_gt = normalize_gt_offsets(off, self.offset_mu, self.offset_sigma)
-        loss = self.loss((node_cls, node_off, link_cls, obj_cls), (node_gt, off_gt, edge_gt, obj_gt), self.global_counts)
+        loss = self.loss((node_cls, node_off, link_cls, obj_cls), (node_gt, off_gt, edge_gt, obj_gt), global_counts, dp_tail)
         correct = self.loss.last_correct.to(torch.float32)
         accuracy = {'segment_accuracy': correct[0] / node_gt.shape[0],
                     'edge_accuracy': correct[1] / max(edge_gt.shape[0], 1),

@@ -90,7 +90,10 @@ def build_graph_batch(points: Dict[str, torch.Tensor], frame_ptr: Sequence[int],
     ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
     check(lib().rgnn_graph_finalize(ptr(row_ptr), ptr(col), n, E, ptr(gb.tgt), ptr(gb.perm), ptr(gb.und_a),
                                     ptr(gb.und_b), ptr(n_und), ptr(ws2), nb2, s), 'rgnn_graph_finalize')
-    gb.n_und = int(n_und.item())
+    # the adjacency built here is symmetric without self loops (sym-kNN / radius U kNN), so exactly half of the
+    # directed edges have source < target: no second device-to-host read (tests hold n_und_dev to it)
+    gb.n_und = E // 2
+    gb.n_und_dev = n_und
     gb.cl_ptr = torch.zeros(1, **i32)
     gb.cl_members = torch.zeros(1, **i32)
     out = BatchedFrames()

@@ -20,12 +20,20 @@ from ._engine import _f32c, _require_cuda
 
 class _LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cfg, counts, node_cls, node_off, link_cls, obj_cls, node_gt, off_gt, link_gt, obj_gt):
+    def forward(ctx, cfg, counts, dp_tail, node_cls, node_off, link_cls, obj_cls, node_gt, off_gt, link_gt, obj_gt):
         _require_cuda(node_cls, node_off, link_cls, obj_cls, node_gt, off_gt, link_gt, obj_gt)
         node_cls, node_off, link_cls, obj_cls, off_gt = map(_f32c, (node_cls, node_off, link_cls, obj_cls, off_gt))
         node_gt, link_gt, obj_gt = (t.to(torch.int64).contiguous() for t in (node_gt, link_gt, obj_gt))
         dev = node_cls.device
         n, eu, nc = node_cls.shape[0], link_cls.shape[0], obj_cls.shape[0]
+        counts_dev = None
+        if isinstance(counts, torch.Tensor):          # device-resident global counts (data parallel): never read by the host
+            if not counts.is_cuda or counts.dtype != torch.float64 or counts.numel() != 3:
+                raise _cabi.RgnnError('global_counts tensor must be 3 float64 values on the CUDA device')
+            counts_dev, counts = counts.contiguous(), None
+        if dp_tail is not None and (not dp_tail.is_cuda or dp_tail.dtype != torch.float32 or dp_tail.numel() < 5
+                                    or not dp_tail.is_contiguous()):
+            raise _cabi.RgnnError('dp_tail must be >= 5 contiguous float32 values on the CUDA device')
         cn, cu, cc = counts if counts is not None else (n, eu, nc)
         grads = [torch.empty_like(t) for t in (node_cls, node_off, link_cls, obj_cls)]
         losses = torch.empty(4, dtype=torch.float64, device=dev)
@@ -33,7 +41,8 @@ class _LossFn(torch.autograd.Function):
         check(lib().rgnn_losses_fwdbwd(C.byref(cfg), ptr(node_cls), ptr(node_off), ptr(link_cls), ptr(obj_cls),
                                        ptr(node_gt), ptr(off_gt), ptr(link_gt), ptr(obj_gt), n, eu, nc,
                                        float(cn), float(cu), float(cc), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]),
-                                       ptr(grads[3]), ptr(losses), ptr(correct), stream_ptr()), 'rgnn_losses_fwdbwd')
+                                       ptr(grads[3]), ptr(losses), ptr(correct), ptr(counts_dev), ptr(dp_tail),
+                                       stream_ptr()), 'rgnn_losses_fwdbwd')
         ctx.save_for_backward(*grads)
         ctx.mark_non_differentiable(correct)
         out = losses.to(torch.float32)
@@ -42,7 +51,7 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g0, g1, g2, g3, _gc):
         d_node_cls, d_node_off, d_link, d_obj = ctx.saved_tensors
-        return (None, None, d_node_cls * g0, d_node_off * g1, d_link * g2, d_obj * g3, None, None, None, None)
+        return (None, None, None, d_node_cls * g0, d_node_off * g1, d_link * g2, d_obj * g3, None, None, None, None)
 
 
 class Loss_Graph(nn.Module):
@@ -70,12 +79,14 @@ class Loss_Graph(nn.Module):
     def compute_valid_object_mask(self, gt_class_logits):
         return gt_class_logits != self.new_labels_to_id_dict['FALSE']
 
-    def forward(self, pred, gt, global_counts: Optional[Sequence[float]] = None):
+    def forward(self, pred, gt, global_counts=None, dp_tail: Optional[torch.Tensor] = None):
         """pred / gt: 4-tuples (node_class_logits, node_reg_deltas, edge_class_logits, obj_class_logits); gt classes
         are index tensors, gt offsets already normalised.  global_counts = (N, E_u, C) over all data-parallel
-        ranks makes each rank's share sum to the reference's global-batch loss (loss.py:58,62,66,70)."""
+        ranks -- host numbers or a 3-element float64 device tensor -- makes each rank's share sum to the reference's
+        global-batch loss (loss.py:58,62,66,70); None = this batch's own counts, as the reference divides.
+        dp_tail: 5 float32 device values receiving the NaN flag and this rank's four loss shares (include/rgnn.h)."""
         l_node, l_reg, l_edge, l_obj, correct = _LossFn.apply(
-            self._cfg, global_counts, pred[0], pred[1], pred[2], pred[3], gt[0], gt[1], gt[2], gt[3])
+            self._cfg, global_counts, dp_tail, pred[0], pred[1], pred[2], pred[3], gt[0], gt[1], gt[2], gt[3])
         self.last_correct = correct
         return {'loss_node_cls': l_node, 'loss_node_reg': l_reg, 'loss_edge_cls': l_edge, 'loss_obj_cls': l_obj}
 

@@ -3,13 +3,17 @@ reference's `train_model`, modules/neural_net/gnn/training.py:66-85, with torch.
 modules/set_configurations/set_param_for_training_gnn.py:46).
 
 Frames are independent graphs, so a global batch is sharded by frame: one process per GPU, each packs its frames
-into one block-diagonal graph and runs the fused forward/backward kernels.  Two collectives per step, both SUM:
+into one block-diagonal graph and runs the fused forward/backward kernels.  Two collectives per step, both SUM, both
+enqueued on the stream -- the host never reads a device value inside a step:
 
-  1. three int64 counts (nodes, undirected links, clusters).  The reference divides every loss term by the count of
-     the WHOLE batch (gnn/loss.py:58,62,66,70); each rank therefore scales its own sums by the global counts, which
-     makes the per-rank losses (and gradients) add up to exactly the single-process result.  Averaging per-rank
-     mean-losses would be wrong whenever ranks hold different numbers of nodes / links / clusters.
-  2. one flat fp32 gradient buffer (463 144 floats = 1.85 MB for the reference configuration) over NCCL/NVLink.
+  1. three counts (nodes, undirected links, clusters) as a float64 device tensor.  The reference divides every loss
+     term by the count of the WHOLE batch (gnn/loss.py:58,62,66,70); each rank therefore scales its own sums by the
+     global counts, which makes the per-rank losses (and gradients) add up to exactly the single-process result.  The
+     counts must be known before the backward starts (a shared-trunk gradient mixes all four terms), so they cannot ride
+     behind the gradients; the loss kernel reads them from device memory (rgnn_losses_fwdbwd, counts_dev).
+  2. one flat fp32 buffer: the gradients (463 144 floats = 1.85 MB for the reference configuration) followed by a 5-float
+     tail written by the loss kernel: the NaN flag of the reference's skip_batch and this rank's four loss shares, so the
+     same all-reduce yields the global skip decision and the GLOBAL losses for logging.
 
 The update itself is one fused kernel (rgnn_sgd_step) on the flat parameter buffer.  The communication helpers are
 backend agnostic (they are covered on CPU with gloo, world size 2, in tests/test_dp_cpu.py); the compute is CUDA only.
@@ -54,6 +58,13 @@ def allreduce_counts(local_counts: Sequence[int], device, group=None) -> Tuple[i
     return tuple(int(v) for v in t.tolist())
 
 
+def allreduce_counts_device_(counts: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM of a 3-element count tensor that stays on its device (no host read; identity at world size 1)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
 def allreduce_flat_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """In-place SUM all-reduce of one contiguous buffer (no bucketing: the whole model is 1.85 MB)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -80,8 +91,10 @@ class FlatBuffers:
             total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.params = params
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        # one extra slot behind the gradients: the "skip this batch" flag (NaN loss on any rank), all-reduced with them
+        # behind the gradients: the tail the loss kernel writes (include/rgnn.h, dp_tail): [0] "skip this batch" flag (NaN
+        # loss on any rank), [1..4] this rank's loss shares; all-reduced with the gradients
         self.flat_grad = torch.zeros(total + self.ALIGN, dtype=torch.float32, device=dev)
+        self.tail = self.flat_grad[total:total + 5]
         self.skip_flag = self.flat_grad[total:total + 1]
         self.momentum = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, off in zip(params, self.offsets):
@@ -99,9 +112,12 @@ class FlatBuffers:
                 p.grad = g
 
 
-def multistep_lr(base_lr: float, iteration: int, milestones: Sequence[int], gamma: float = 0.1) -> float:
-    """torch.optim.lr_scheduler.MultiStepLR as the reference configures it (set_param_for_training_gnn.py:50-56)."""
-    return base_lr * (gamma ** sum(1 for m in milestones if iteration >= m))
+def multistep_lr(base_lr: float, steps_done: int, milestones: Sequence[int], gamma: float = 0.1) -> float:
+    """torch.optim.lr_scheduler.MultiStepLR as the reference configures it (set_param_for_training_gnn.py:50-56).
+    `steps_done` counts scheduler steps since the loop started: the reference creates the scheduler afresh on resume and
+    gives it milestones RELATIVE to the start iteration (`int(0.5 * max_train_iter - init_start)`), so pass
+    `iteration - iter_start_offset`, not the absolute iteration."""
+    return base_lr * (gamma ** sum(1 for m in milestones if steps_done >= m))
 
 
 # -------------------------------------------------------------------------------------------------
@@ -118,6 +134,7 @@ class DataParallelTrainer:
         self.lr, self.mu, self.wd = float(lr), float(momentum), float(weight_decay)
         self.buffers = FlatBuffers(model)
         self.steps = 0
+        self._counts = None
 
     @property
     def world_size(self) -> int:
@@ -127,25 +144,37 @@ class DataParallelTrainer:
              lr: Optional[float] = None):
         """gb / node_features / edge_features: this rank's packed frames (Model_Training.pack_batch or
         graph_features.build_graph_batch); labels: dict of concatenated tensors or per-frame lists.
-        Returns (loss dict, accuracy dict) of THIS rank's share; summing the losses over ranks gives the global loss."""
+        Returns (loss dict, accuracy dict).  The losses are those of the GLOBAL batch (identical on every rank: the four
+        shares ride in the gradient all-reduce); the accuracies are this rank's.  Nothing in here reads device memory from
+        the host."""
         from ._cabi import check, lib, ptr, stream_ptr
         dev = node_features.device
-        n_obj = gb.n_clusters
-        counts = allreduce_counts((gb.n_nodes, gb.n_und, n_obj), dev, self.group)
-        self.model.global_counts = counts
-        self.buffers.zero_grad()
-        loss, acc = self.model.forward_packed(gb, node_features, edge_features, labels)
+        b = self.buffers
+        b.zero_grad()                       # also clears the tail (NaN flag, loss shares)
+        counts = None
+        if self.world_size > 1:
+            if self._counts is None:
+                self._counts = torch.zeros(3, dtype=torch.float64, device=dev)
+            # scalar fills are kernel arguments: no pageable host-to-device copy, no stream drain
+            for i, v in enumerate((gb.n_nodes, gb.n_und, gb.n_clusters)):
+                self._counts[i].fill_(float(v))
+            counts = allreduce_counts_device_(self._counts, self.group)
+        loss, acc = self.model.forward_packed(gb, node_features, edge_features, labels, global_counts=counts, dp_tail=b.tail)
         total = loss['loss_node_cls'] + loss['loss_node_reg'] + loss['loss_edge_cls'] + loss['loss_obj_cls']
         total.backward()
-        b = self.buffers
         # reference skip_batch (gnn/training.py:40-45,79-84): a NaN loss on ANY rank skips the update on every rank; the flag
-        # rides behind the gradients through the all-reduce, nothing is read back to the host
-        b.skip_flag.copy_(torch.isnan(total.detach()).to(torch.float32).reshape(1))
+        # (written by the loss kernel) rides behind the gradients through the all-reduce
         allreduce_flat_(b.flat_grad, self.group)
         check(lib().rgnn_sgd_step_guarded(ptr(b.flat_param), ptr(b.flat_grad), ptr(b.momentum), b.numel,
                                           self.lr if lr is None else float(lr), self.mu, self.wd, 1.0,
                                           1 if self.steps == 0 else 0, ptr(b.skip_flag), stream_ptr()), 'rgnn_sgd_step_guarded')
         self.steps += 1
+        table = getattr(self.model.pred, '_rgnn_table', None)
+        if table is not None:
+            table.invalidate_packed()       # the SGD kernel wrote the parameters behind ATen's back
+        if self.world_size > 1:
+            g = b.tail[1:5].clone()         # global losses (the buffer is cleared by the next step)
+            loss = {k: g[i] for i, k in enumerate(_LOSS_KEYS)}
         return loss, acc
 
     # ---- optimizer-state checkpointing (the reference saves only detector.state_dict(), training.py:16-18) ----
@@ -273,7 +302,9 @@ class AccuracyTracker:
 def train_model(detector, trainer: DataParallelTrainer, lr_milestones: Sequence[int], dataloader_train, dataloader_val, tb_writer,
                 max_iters: int, log_period: int, val_period: int, iter_start_offset: int = 0, save_fn=None, base_lr: Optional[float] = None):
     """The reference's `train_model` (gnn/training.py:48-186) on top of DataParallelTrainer: same iteration structure, logging
-    and validation cadence, but no host synchronisation inside a training step (no loss.item(), no isnan() on the host).
+    and validation cadence, but no host synchronisation inside a training step (no loss.item(), no isnan() on the host);
+    under data parallelism the logged training losses are those of the global batch.  LR milestones count from
+    `iter_start_offset`, as the reference's freshly created scheduler does on resume.
     dataloader_*: iterables of (graph_features, labels) in the reference's collate format (datagen_gnn.py:143-190:
     dict with 'node_features_dyn', 'edge_features_dyn', 'edge_index_dyn', 'adj_matrix_dyn').  tb_writer may be None;
     save_fn(detector, trainer, iteration) is called where the reference saves weights."""
@@ -287,7 +318,7 @@ def train_model(detector, trainer: DataParallelTrainer, lr_milestones: Sequence[
             detector.train()
             gb, nf, ef = detector.pack_batch(graph_features['node_features_dyn'], graph_features['edge_features_dyn'],
                                              graph_features['edge_index_dyn'], labels['cluster_node_idx'])
-            loss, accuracy = trainer.step(gb, nf, ef, labels, lr=multistep_lr(base_lr, it, lr_milestones))
+            loss, accuracy = trainer.step(gb, nf, ef, labels, lr=multistep_lr(base_lr, it - iter_start_offset, lr_milestones))
             total = sum(loss.values())
             loss_tracker.append_training_loss_for_tb(total, loss)
             acc_tracker.append_training_acc_for_tb(accuracy)

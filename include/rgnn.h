@@ -287,7 +287,11 @@ int rgnn_wgrad(const float* A, int lda, int wa, const float* B, int ldb, int wb,
  * counts_* are the GLOBAL batch sizes each sum is divided by (loss.py:58,62,66,70) -- under data parallelism
  * they are the all-reduced counts, which is what makes per-rank sums add up to the reference's loss.
  * losses_out (4) f64: node_cls, node_reg, edge_cls, obj_cls (already weighted, this rank's share);
- * correct_out (3) int32: argmax hits for node / edge / object.  node_off_gt is already normalised. */
+ * correct_out (3) int32: argmax hits for node / edge / object.  node_off_gt is already normalised.
+ * counts_dev (nullable, 3 x f64 on the device): when given it overrides count_* -- the data-parallel driver all-reduces
+ * the counts on the stream and the host never reads them.  dp_tail (nullable, 5 x f32, zeroed by the caller): [0] is set
+ * to 1 when a loss term is NaN (the reference's skip_batch test, gnn/training.py:40-45), [1..4] += this rank's four
+ * weighted loss shares; the driver keeps it behind the flat gradient buffer so that it rides in the one all-reduce. */
 typedef struct rgnn_loss_cfg {
     float class_weights[16];
     int n_classes, n_edge_classes;
@@ -299,7 +303,7 @@ int rgnn_losses_fwdbwd(const rgnn_loss_cfg* cfg, const float* node_cls, const fl
                        const int64_t* link_gt, const int64_t* obj_gt, int n_nodes, int n_und, int n_clusters,
                        double count_nodes, double count_und, double count_clusters,
                        float* grad_node_cls, float* grad_node_off, float* grad_link_cls, float* grad_obj_cls,
-                       double* losses_out, int32_t* correct_out, void* stream);
+                       double* losses_out, int32_t* correct_out, const double* counts_dev, float* dp_tail, void* stream);
 
 /* torch.optim.SGD(momentum, weight_decay) step on a flat parameter buffer
  * (modules/set_configurations/set_param_for_training_gnn.py:46): g += wd*p; buf = mu*buf + g; p -= lr*buf.

@@ -83,23 +83,27 @@ def test_conv_block_many_tiles_per_cta_matches_oracle(ckpt_state_dict, n, e, lay
     assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), f'conv block {layer}')
 
 
-@pytest.mark.parametrize('n_frames,n_pts', [(3, 150), (2, 1000)])
-def test_batched_forward_matches_oracle_per_frame(ckpt_state_dict, n_frames, n_pts):
-    """Block-diagonal batch == the reference's per-frame loop (checked against the oracle frame by frame)."""
+@pytest.mark.parametrize('n_frames,n_pts,knn', [(3, 150, 10), (2, 1000, 10), (4, 3000, 10), (1, 1200, 64)])
+def test_batched_forward_matches_oracle_per_frame(ckpt_state_dict, n_frames, n_pts, knn):
+    """Block-diagonal batch == the reference's per-frame loop (checked against the oracle frame by frame).  (4, 3000) is the
+    BASELINE.json configs[1] frame shape (4 x ~3000 points, E ~ 137 k: every CTA of every persistent kernel runs several
+    tiles); (1, 1200, k=64) the dense end of the configs[4] sweep (degree up to ~100, segments longer than a tile row
+    group)."""
     from graph_neural_network_for_radar_perception_b200 import graph_features as gf, synth
     from oracle import graph_np, model_torch as mt
     m = load_model(ckpt_state_dict).pred.eval()
     frames, labs = [], []
     for i in range(n_frames):
-        d, src = synth.make_frame(500 + i, n_pts + 13 * i)
+        d, src = synth.make_frame(500 + i, n_pts + 13 * i, knn=knn)
         frames.append(d)
         labs.append(src)
     pts, fp = gf.frames_to_device(frames)
     R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
-    bf = gf.build_graph_batch(pts, fp, 25, 10, max_range=R, max_azimuth=np.pi * 0.5)
+    bf = gf.build_graph_batch(pts, fp, 25, knn, max_range=R, max_azimuth=np.pi * 0.5)
+    assert int(bf.gb.n_und_dev.item()) == bf.gb.n_und          # symmetric adjacency: E / 2 links, no read-back needed
     cl_lists, o_out = [], []
     for i, d in enumerate(frames):
-        adj = graph_np.adjacency_information(d, 25, 10)
+        adj = graph_np.adjacency_information(d, 25, knn)
         lab = synth.make_labels(d, labs[i], adj['adj_list'])
         cl = [torch.from_numpy(c) for c in lab['cluster_node_idx']]
         cl_lists.append(cl)

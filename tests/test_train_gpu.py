@@ -1,17 +1,16 @@
 """GPU: training step (forward + multi-task loss + backward kernels) through the C-ABI against the reference's
 own losses / gradients (tests/golden/train_2frames.npz) and against torch autograd over the oracle.
 
-Tolerance for gradients: north_star asks rtol 1e-4; elements near zero need an absolute floor, stated as a
-fraction of the tensor's largest reference gradient: |got - want| <= 1e-4 |want| + GRAD_ATOL_FRAC * max|want|.
-The floor is 5e-3: the loss gradient of a LeakyReLU(0.01) stack is discontinuous in the activations, and
-tools/grad_sensitivity.py shows that perturbing the REFERENCE's own layer outputs by 2e-6 (fp32 rounding noise)
-moves single parameter gradients by 1e-3..4e-3 of their maximum (kink flips) while typical tensors move by 1e-6.
-Measured on B200 (tools/grad_diag.py, 3xTF32 path): worst tensor 3.0e-4 of its maximum on the 2-frame fixture and
-3.1e-3 on the tiny ragged batch (one flipped activation among ~1000 rows), median tensor < 1e-5; the
-median is asserted too (GRAD_MEDIAN), so a general loss of precision cannot hide behind the kink allowance.
-Scalar channel_normalization parameters (one element, a heavily cancelling sum over a whole layer output; the
-reference's own float32 value is up to 5e-4 off its float64 value there) are compared on the scale of the largest
-scalar-parameter gradient of the model."""
+Losses and accuracies: rtol 1e-4 (+1e-6) against the reference's float32 values.
+Gradients: north_star asks rtol 1e-4.  The yardstick for everything rtol 1e-4 cannot decide is the reference's OWN
+float32 rounding noise, per tensor, measured in the test (gpu_util.GradientYardstick): the exact gradient is the oracle in
+float64; five float32 evaluations of the oracle (one plain, four with inputs and parameters moved by one float32 ulp)
+give each tensor's noise floor; an element passes when |got - exact| <= max(1e-4 |exact|, noise(tensor)) times a factor
+that is calibrated by holding each float32 run out in turn -- the CUDA gradient may score at most 2x the worst held-out
+float32 run.  There is no constant floor: where the reference is quiet (small graphs, random-init weights) the bound is
+rtol 1e-4 plus a few 1e-6 of the tensor maximum and a 0.3 % error in one tensor fails; where the reference's own
+gradient moves by per cent under a one-ulp perturbation (trained checkpoint, 2 x 3000 points: cancelling sums + LeakyReLU
+kinks, tools/grad_noise.py) the bound follows it."""
 import os
 
 import numpy as np
@@ -20,23 +19,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import assert_close, clusters_from, load_model
-
-GRAD_ATOL_FRAC = 5e-3
-GRAD_MEDIAN = 2e-5
+from gpu_util import GradientYardstick, assert_close, batch_labels, clusters_from, load_model, synth_batch
 
 
-def check_grads(pairs):
-    """pairs: iterable of (name, got, ref) numpy arrays."""
-    pairs = [(n, np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)) for n, a, b in pairs]
-    scalar_scale = max([np.abs(b).max() for n, a, b in pairs if b.size == 1] + [1e-6])
-    rel = []
-    for n, a, b in pairs:
-        scale = scalar_scale if b.size == 1 else max(np.abs(b).max(), 1e-6)
-        assert_close(a, b, 1e-4, GRAD_ATOL_FRAC * scale, n)
-        rel.append(np.abs(a - b).max() / scale)
-    assert np.median(rel) < GRAD_MEDIAN, np.median(rel)
-    return max(rel)
+def model_grads(m):
+    return {n: p.grad.detach().cpu().numpy() for n, p in m.named_parameters() if p.grad is not None}
 
 
 def _golden_batch(g, dev):
@@ -68,81 +55,85 @@ def test_training_step_matches_reference_fixture(golden_dir, ckpt_state_dict):
     names = [str(n) for n in g['grad_names']]
     params = dict(m.named_parameters())
     assert set(names) == set(params)
-    pairs = []
-    l2_scalar = max(float(l2) for n, l2 in zip(names, g['grad_norms']) if params[n].numel() == 1)
-    for n, l2_ref in zip(names, g['grad_norms']):
-        gr = params[n].grad
-        assert gr is not None, n
-        gr = gr.detach().cpu().numpy().astype(np.float64)
-        l2 = np.sqrt((gr ** 2).sum())
-        assert abs(l2 - l2_ref) <= GRAD_ATOL_FRAC * (l2_scalar if gr.size == 1 else l2_ref) + 1e-7, (n, l2, l2_ref)
+    # element-wise: against the float64 oracle on the fixture's inputs, with the float32 oracle's noise as the yardstick (the
+    # oracle is pinned to this very fixture's reference gradients by tests/test_oracle_golden.py)
+    frames = [dict(nf=torch.from_numpy(g[f'f{i}_node_features']), ef=torch.from_numpy(g[f'f{i}_edge_features']),
+                   ei=torch.from_numpy(g[f'f{i}_edge_index']),
+                   lab={'cluster_node_idx': [c.numpy() for c in clusters_from(g[f'f{i}_cluster_ptr'], g[f'f{i}_cluster_members'])],
+                        **{k: g[f'f{i}_{k}'] for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}})
+              for i in range(2)]
+    ys = GradientYardstick(ckpt_state_dict, frames)
+    got = model_grads(m)
+    assert set(got) == set(names)
+    ys.check(got, what='2-frame reference fixture')
+    # and the reference's own stored float32 gradients sit inside the same yardstick (fixture <-> oracle <-> CUDA)
+    for n in names:
         key = 'grad::' + n
         if key in g.files:
-            pairs.append((n, gr, g[key]))
-    print('worst relative-to-max gradient error', check_grads(pairs))
+            noise = max(ys._noise(ys.runs, n), 1e-30)
+            assert np.all(np.abs(g[key] - ys.exact[n]) <= np.maximum(1e-4 * np.abs(ys.exact[n]), 4 * noise)), n
+
+
+def _train_case(sd0, sizes, seed0, members=5, knn=10):
+    frames = synth_batch(sizes, seed0=seed0, knn=knn)
+    ys = GradientYardstick(sd0, frames, members=members)
+    m = load_model(sd0).train()
+    loss, acc = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
+                  [None] * len(frames), batch_labels(frames, 'cuda'))
+    for k in loss:
+        assert_close(loss[k].item(), ys.loss32[k].item(), 1e-4, 1e-6, k)
+    for k in acc:
+        assert abs(acc[k].item() - ys.acc32[k].item()) < 2.0 / max(sum(sizes), 1) + 1e-6, k    # one arg-max tie at most
+    sum(loss.values()).backward()
+    return ys, model_grads(m)
 
 
 def test_training_step_matches_oracle_autograd_all_parameters(ckpt_state_dict):
     """Every one of the 184 parameter tensors, on a 3-frame batch with ragged sizes (one frame smaller than k)."""
-    from graph_neural_network_for_radar_perception_b200 import synth
-    from oracle import graph_np, model_torch as mt
-    R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
-    frames = []
-    for i, n in enumerate((90, 7, 161)):
-        d, src = synth.make_frame(700 + i, n)
-        adj = graph_np.adjacency_information(d, 25, 10)
-        lab = synth.make_labels(d, src, adj['adj_list'])
-        frames.append(dict(
-            nf=torch.from_numpy(graph_np.node_features(d, adj['degree'], True, 0, R, 0, np.pi * 0.5).astype(np.float32)),
-            ef=torch.from_numpy(graph_np.edge_features(d, adj['adj_list']).astype(np.float32)),
-            ei=torch.from_numpy(adj['adj_list']), lab=lab))
+    ys, got = _train_case(ckpt_state_dict, (90, 7, 161), 700)
+    assert set(got) == set(ys.names)
+    ys.check(got, what='ragged 3-frame batch, trained checkpoint')
 
-    def labels_on(dev):
-        return {'cluster_node_idx': [[torch.from_numpy(c).to(dev) for c in f['lab']['cluster_node_idx']] for f in frames],
-                'cluster_labels': [torch.from_numpy(f['lab']['cluster_labels']).to(dev) for f in frames],
-                'edge_class': [torch.from_numpy(f['lab']['edge_class']).to(dev) for f in frames],
-                'node_class': [torch.from_numpy(f['lab']['node_class']).to(dev) for f in frames],
-                'node_offsets': [torch.from_numpy(f['lab']['node_offsets']).to(dev) for f in frames]}
-    # The oracle runs twice: in float32 (what the reference computes) and in float64 (the exact gradient).
-    # The scalar channel_normalization parameters' gradients are sums over every element of a layer output with
-    # heavy cancellation; the reference's own float32 result is up to 5e-4 away from the float64 value there
-    # (measured), so the CUDA gradients are held to the float64 oracle, and outputs/losses to the float32 one.
-    grads = {}
-    for dt in (torch.float32, torch.float64):
-        sd = {k: v.clone().to(dt).requires_grad_(True) for k, v in ckpt_state_dict.items()}
-        lab = labels_on('cpu')
-        lab['node_offsets'] = [t.to(dt) for t in lab['node_offsets']]
-        loss_o, acc_o, _ = mt.training_forward(sd, [f['nf'].to(dt) for f in frames], [f['ef'].to(dt) for f in frames],
-                                               [f['ei'] for f in frames], lab)
-        sum(loss_o.values()).backward()
-        grads[dt] = {k: v.grad.double().numpy() for k, v in sd.items()}
-        if dt == torch.float32:
-            loss32, acc32 = loss_o, acc_o
-    m = load_model(ckpt_state_dict).train()
-    loss, acc = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
-                  [None] * 3, labels_on('cuda'))
-    for k in loss:
-        assert_close(loss[k].item(), loss32[k].item(), 1e-4, 1e-6, k)
-    for k in acc:
-        assert abs(acc[k].item() - acc32[k].item()) < 1e-6
-    sum(loss.values()).backward()
-    check_grads((n, p.grad.cpu().numpy(), grads[torch.float64][n]) for n, p in m.named_parameters())
+
+def test_training_step_random_init_is_tight(ckpt_state_dict):
+    """Random-init weights (seed 1234): gradients are not cancelling sums, the reference's noise floor is ~1e-6 of each
+    tensor's maximum, so this case holds the CUDA backward to rtol 1e-4 almost everywhere and catches a systematic
+    error of a few 1e-4 in any single tensor."""
+    from graph_neural_network_for_radar_perception_b200 import config, Model_Training
+    torch.manual_seed(1234)
+    sd0 = {k: v.detach().clone() for k, v in Model_Training(config(), 'cpu').state_dict().items()}
+    ys, got = _train_case(sd0, (150, 260), 720)
+    r = ys.check(got, what='2 frames, random-init weights')
+    worst_noise = max(ys._noise(ys.runs, n) / max(np.abs(ys.exact[n]).max(), 1e-30) for n in ys.names)
+    assert worst_noise < 5e-3, worst_noise          # the yardstick really is tight here
+
+
+@pytest.mark.timeout(900)
+def test_training_step_at_baseline_shape_two_frames_of_3000_points(ckpt_state_dict):
+    """BASELINE.json configs[2] shape: 3000 points per frame (E ~ 68 k directed edges, 530 edge tiles + the split-K
+    weight-gradient chunks + scratch reuse across the 7 layers), trained checkpoint."""
+    ys, got = _train_case(ckpt_state_dict, (3000, 3000), 740, members=5)
+    ys.check(got, what='2 frames x 3000 points, trained checkpoint')
 
 
 def test_ffn_stack_backward_standalone(ckpt_state_dict):
     """graph_feature_encoding used on its own with autograd (block-level API of gnn_blocks.py)."""
+    from gpu_util import one_ulp
     from oracle import model_torch as mt
     torch.manual_seed(3)
     m = load_model(ckpt_state_dict).pred
     x = torch.randn(77, 7)
     w = torch.randn(77, 64)
     (m.encode_edge_feat(x.cuda()) * w.cuda()).sum().backward()
-    sd = {k: v.clone().requires_grad_(True) for k, v in ckpt_state_dict.items() if 'encode_edge_feat' in k}
-    xo = x.clone().requires_grad_(True)
-    (mt.ffn_stack(sd, 'pred.encode_edge_feat.encoder', xo) * w).sum().backward()
-    for n, p in m.encode_edge_feat.named_parameters():
-        ref = sd['pred.encode_edge_feat.' + n].grad.numpy()
-        assert_close(p.grad.cpu().numpy(), ref, 1e-4, GRAD_ATOL_FRAC * np.abs(ref).max(), n)
+
+    def grad_fn(dtype, seed):
+        gen = torch.Generator().manual_seed(seed or 0)
+        pert = (lambda t: t) if seed is None else (lambda t: one_ulp(t, gen))
+        sd = {k: pert(v.clone()).to(dtype).requires_grad_(True) for k, v in ckpt_state_dict.items() if 'encode_edge_feat' in k}
+        (mt.ffn_stack(sd, 'pred.encode_edge_feat.encoder', pert(x).to(dtype)) * w.to(dtype)).sum().backward()
+        return {k[len('pred.encode_edge_feat.'):]: v.grad.double().numpy() for k, v in sd.items()}
+    ys = GradientYardstick(grad_fn=grad_fn)
+    ys.check({n: p.grad.cpu().numpy() for n, p in m.encode_edge_feat.named_parameters()}, what='edge encoder stand-alone')
 
 
 def test_frozen_layers_get_no_gradient(ckpt_state_dict, golden_dir):
@@ -152,14 +143,16 @@ def test_frozen_layers_get_no_gradient(ckpt_state_dict, golden_dir):
     nf, ef, ei, labels = _golden_batch(g, 'cuda')
     loss, _ = m(nf, ef, ei, [None, None], labels)
     sum(loss.values()).backward()
+    frames = [dict(nf=torch.from_numpy(g[f'f{i}_node_features']), ef=torch.from_numpy(g[f'f{i}_edge_features']),
+                   ei=torch.from_numpy(g[f'f{i}_edge_index']),
+                   lab={'cluster_node_idx': [c.numpy() for c in clusters_from(g[f'f{i}_cluster_ptr'], g[f'f{i}_cluster_members'])],
+                        **{k: g[f'f{i}_{k}'] for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}})
+              for i in range(2)]
+    ys = GradientYardstick(ckpt_state_dict, frames, members=4)
+    live = [n for n, p in m.named_parameters() if 'predict_class' in n]
     for n, p in m.named_parameters():
-        if 'predict_class' in n:
-            ref = g['grad::' + n] if ('grad::' + n) in g.files else None
-            assert p.grad is not None
-            if ref is not None:
-                assert_close(p.grad.cpu().numpy(), ref, 1e-4, GRAD_ATOL_FRAC * np.abs(ref).max(), n)
-        else:
-            assert p.grad is None, n
+        assert (p.grad is not None) == (n in live), n
+    ys.check(model_grads(m), names=live, what='object-class head only')
 
 
 def test_sgd_step_matches_torch():
