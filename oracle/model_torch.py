@@ -34,6 +34,44 @@ import torch.nn.functional as F
 EPS = 1e-5            # modules/neural_net/constants.py:9
 LEAKY_SLOPE = 0.01    # constants.py:10
 
+# Test knob (tests/gpu_util.GradientYardstick; 0 everywhere else): every Linear output is multiplied by (1 - LINEAR_OUTPUT_SHRINK) -- what
+# accumulating a dot product with round-toward-zero instead of round-to-nearest does on average (the tensor cores truncate
+# their fp32 accumulator: measured signed bias of -1.5e-7 .. -5.4e-7 per GEMM on B200, tools/mma_noise.py).
+LINEAR_OUTPUT_SHRINK = 0.0
+
+
+class ActivationProbe:
+    """Test instrumentation (tests/gpu_util.GradientYardstick).  The loss gradient of a LeakyReLU(0.01) stack is
+    DISCONTINUOUS where a pre-activation crosses zero: two evaluations that agree to float32 rounding can sit on different
+    sides of a kink and their gradients differ by a finite jump.  The probe (a) lists the activations whose pre-activation
+    lies within `window` of zero, and (b) re-evaluates with chosen activations taken on the OTHER branch, which gives the
+    exact size of each jump.  Activations are addressed as (ffn call index, row, channel); the call order of the functions
+    below is deterministic."""
+
+    def __init__(self, window=None, flips=None):
+        self.window, self.flips = window, flips or {}
+        self.calls, self.found = 0, []
+
+
+_PROBE = None
+
+
+def _leaky(z: torch.Tensor) -> torch.Tensor:
+    y = F.leaky_relu(z, LEAKY_SLOPE)
+    p = _PROBE
+    if p is not None:
+        idx = p.calls
+        p.calls += 1
+        if p.window is not None:
+            for r, c in (z.detach().abs() < p.window).nonzero().tolist():
+                p.found.append((idx, r, c))
+        if idx in p.flips:
+            mask = torch.zeros(z.shape, dtype=torch.bool)
+            for r, c in p.flips[idx]:
+                mask[r, c] = True
+            y = torch.where(mask, torch.where(z > 0, LEAKY_SLOPE * z, z), y)
+    return y
+
 
 def channel_norm(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
     """common.py:215-220: per-row mean, UNBIASED std, eps added to the std, scalar affine."""
@@ -45,9 +83,11 @@ def channel_norm(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> t
 def ffn(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor) -> torch.Tensor:
     """One ffn_block whose parameters live under `prefix` ('....block'): Linear -> [norm] -> LeakyReLU."""
     z = F.linear(x, sd[prefix + '.0.weight'], sd[prefix + '.0.bias'])
+    if LINEAR_OUTPUT_SHRINK:
+        z = z * (1.0 - LINEAR_OUTPUT_SHRINK)
     if (prefix + '.1.mu') in sd:
         z = channel_norm(z, sd[prefix + '.1.std'], sd[prefix + '.1.mu'])
-    return F.leaky_relu(z, LEAKY_SLOPE)
+    return _leaky(z)
 
 
 def _count(sd, stem: str) -> int:

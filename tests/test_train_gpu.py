@@ -7,10 +7,13 @@ float32 rounding noise, per tensor, measured in the test (gpu_util.GradientYards
 float64; five float32 evaluations of the oracle (one plain, four with inputs and parameters moved by one float32 ulp)
 give each tensor's noise floor; an element passes when |got - exact| <= max(1e-4 |exact|, noise(tensor)) times a factor
 that is calibrated by holding each float32 run out in turn -- the CUDA gradient may score at most 2x the worst held-out
-float32 run.  There is no constant floor: where the reference is quiet (small graphs, random-init weights) the bound is
-rtol 1e-4 plus a few 1e-6 of the tensor maximum and a 0.3 % error in one tensor fails; where the reference's own
-gradient moves by per cent under a one-ulp perturbation (trained checkpoint, 2 x 3000 points: cancelling sums + LeakyReLU
-kinks, tools/grad_noise.py) the bound follows it."""
+float32 run.  LeakyReLU kinks are handled explicitly instead of by a blanket floor (FLIP_WINDOW): the oracle lists the
+activations whose pre-activation is closer to zero than rounding can resolve and measures, in float64, the exact jump of
+every gradient tensor when one of them takes the other branch; only those jumps widen the tolerance.  There is no
+constant floor: where the reference is quiet (random-init weights) the bound is rtol 1e-4 plus a few 1e-6 of the tensor
+maximum, and a 0.3 % error in one tensor fails (tests/test_yardstick_cpu.py); where the reference's own gradient moves by
+per cent under a one-ulp perturbation (trained checkpoint, 2 x 3000 points: every gradient is a heavily cancelling sum)
+the bound follows it."""
 import os
 
 import numpy as np
@@ -20,6 +23,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from gpu_util import GradientYardstick, assert_close, batch_labels, clusters_from, load_model, synth_batch
+
+# |pre-activation| below which the branch of a LeakyReLU is treated as undecidable.  Activations are O(1) after
+# channel_normalization; the tensor cores' round-toward-zero accumulation shifts a GEMM output by up to -5.4e-7 relative
+# (tools/mma_noise.py) and a few GEMMs stack up between two normalisations.
+FLIP_WINDOW = 2e-6
 
 
 def model_grads(m):
@@ -62,7 +70,7 @@ def test_training_step_matches_reference_fixture(golden_dir, ckpt_state_dict):
                    lab={'cluster_node_idx': [c.numpy() for c in clusters_from(g[f'f{i}_cluster_ptr'], g[f'f{i}_cluster_members'])],
                         **{k: g[f'f{i}_{k}'] for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}})
               for i in range(2)]
-    ys = GradientYardstick(ckpt_state_dict, frames)
+    ys = GradientYardstick(ckpt_state_dict, frames, flip_window=FLIP_WINDOW)
     got = model_grads(m)
     assert set(got) == set(names)
     ys.check(got, what='2-frame reference fixture')
@@ -74,9 +82,9 @@ def test_training_step_matches_reference_fixture(golden_dir, ckpt_state_dict):
             assert np.all(np.abs(g[key] - ys.exact[n]) <= np.maximum(1e-4 * np.abs(ys.exact[n]), 4 * noise)), n
 
 
-def _train_case(sd0, sizes, seed0, members=5, knn=10):
+def _train_case(sd0, sizes, seed0, members=5, knn=10, flip_window=FLIP_WINDOW):
     frames = synth_batch(sizes, seed0=seed0, knn=knn)
-    ys = GradientYardstick(sd0, frames, members=members)
+    ys = GradientYardstick(sd0, frames, members=members, flip_window=flip_window)
     m = load_model(sd0).train()
     loss, acc = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
                   [None] * len(frames), batch_labels(frames, 'cuda'))
@@ -112,7 +120,9 @@ def test_training_step_random_init_is_tight(ckpt_state_dict):
 def test_training_step_at_baseline_shape_two_frames_of_3000_points(ckpt_state_dict):
     """BASELINE.json configs[2] shape: 3000 points per frame (E ~ 68 k directed edges, 530 edge tiles + the split-K
     weight-gradient chunks + scratch reuse across the 7 layers), trained checkpoint."""
-    ys, got = _train_case(ckpt_state_dict, (3000, 3000), 740, members=5)
+    # ~1.5e8 activations: the kinks are too many to enumerate (and the reference's own one-ulp noise is already 4e-5 of
+    # the tensor maximum in the median, 2.6e-2 in the worst tensor, tools/grad_noise.py), so the yardstick is the noise alone
+    ys, got = _train_case(ckpt_state_dict, (3000, 3000), 740, members=5, flip_window=None)
     ys.check(got, what='2 frames x 3000 points, trained checkpoint')
 
 
@@ -148,7 +158,7 @@ def test_frozen_layers_get_no_gradient(ckpt_state_dict, golden_dir):
                    lab={'cluster_node_idx': [c.numpy() for c in clusters_from(g[f'f{i}_cluster_ptr'], g[f'f{i}_cluster_members'])],
                         **{k: g[f'f{i}_{k}'] for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}})
               for i in range(2)]
-    ys = GradientYardstick(ckpt_state_dict, frames, members=4)
+    ys = GradientYardstick(ckpt_state_dict, frames, members=4, flip_window=FLIP_WINDOW)
     live = [n for n, p in m.named_parameters() if 'predict_class' in n]
     for n, p in m.named_parameters():
         assert (p.grad is not None) == (n in live), n
