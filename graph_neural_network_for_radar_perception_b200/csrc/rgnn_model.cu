@@ -87,6 +87,7 @@ struct Packer {
         if (c.msg.n == 2 && c.msg.layer[1].weight != nullptr) {
             int r = mp_tc_pack(c, d, wp + conv_msg0_tc_offset(d), stream);
             if (r == RGNN_OK) r = tc_pack_projection(c, d, stream);
+            if (r == RGNN_OK) r = mp_f16_pack(c, d, wp + conv_msg0_f16_offset(d), stream);
             if (r != RGNN_OK) rc = r;
         }
     }
@@ -175,12 +176,23 @@ void add_message_layers(ProgBuilder& b, const rgnn_conv& c, const ConvDims& d, c
 
 // message + aggregation: agg[t] = sum_{e: s->t} msg(x_t, x_s, e)
 int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, const float* P, float* agg,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const uint32_t* emb_hl = nullptr) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
     RGNN_REQUIRE(c.msg.n == 2, "conv block: msg stack must have 2 ffn_blocks (has %d)", c.msg.n);
     RGNN_CHECK_CUDA(cudaMemsetAsync(agg, 0, (size_t)g.n_nodes * d.cn * sizeof(float), stream));
     RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
+    if (g.n_edges > 0 && mp_f16_supported(d)) {
+        const float* wpack = c.msg.layer[0].weight_t + conv_msg0_f16_offset(d);
+        if (emb_hl != nullptr) return run_conv_edges_f16(c, d, g, emb_hl, P, wpack, agg, stream);
+        // stand-alone call with fp32 edge embeddings (block-level API): split them into a stream-ordered temporary
+        uint32_t* tmp = nullptr;
+        RGNN_CHECK_CUDA(cudaMallocAsync(&tmp, mp_f16_emb_words(g.n_edges) * sizeof(uint32_t), stream));
+        int rc = mp_f16_split_emb(emb, g.n_edges, tmp, stream);
+        if (rc == RGNN_OK) rc = run_conv_edges_f16(c, d, g, tmp, P, wpack, agg, stream);
+        cudaFreeAsync(tmp, stream);
+        return rc;
+    }
     if (g.n_edges > 0 && mp_tc_supported(d)) {
         const float* wpack = c.msg.layer[0].weight_t + conv_msg0_tc_offset(d);
         return run_conv_edges_tc(c, d, g, emb, P, wpack, agg, stream);
@@ -265,6 +277,7 @@ int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, v
         for (int l = 0; l < L; ++l) { pl->P[l] = P; pl->agg[l] = agg; }
     }
     pl->emb = take(E * d.ce);
+    pl->emb_hl = (E > 0 && mp_f16_supported(d)) ? reinterpret_cast<uint32_t*>(take(mp_f16_emb_words(g.n_edges))) : nullptr;
     pl->hlink = take(N * pl->link_w);
     pl->gcls = take(N * pl->cls_w);
     pl->enc_tc_bwd = pl->link_tc_bwd = pl->conv_tc_bwd = false;
@@ -326,8 +339,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
+    if (pl.emb_hl != nullptr && (rc = mp_f16_split_emb(pl.emb, E, pl.emb_hl, stream))) return rc;
     for (int l = 0; l < L; ++l) {
-        if ((rc = run_conv_edges(net.conv[l], g, pl.emb, pl.P[l], pl.agg[l], stream))) return rc;
+        if ((rc = run_conv_edges(net.conv[l], g, pl.emb, pl.P[l], pl.agg[l], stream, pl.emb_hl))) return rc;
         if ((rc = run_conv_nodes(net.conv[l], N, pl.x[l], pl.agg[l], pl.x[l + 1], l + 1 < L ? &net.conv[l + 1] : nullptr,
                                  l + 1 < L ? pl.P[l + 1] : nullptr, stream, pl.conv_tc_bwd ? pl.u_save[l] : nullptr,
                                  pl.conv_tc_bwd ? pl.usd_save[l] : nullptr)))
@@ -423,6 +437,18 @@ extern "C" int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, co
     return run_conv_edges(*blk, *g, e, proj, agg, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rgnn_split_edge_embedding(const float* e, int n_edges, void* e_split, void* stream) {
+    return mp_f16_split_emb(e, n_edges, static_cast<uint32_t*>(e_split), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rgnn_conv_edges_f16_fwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj,
+                                       float* agg, void* stream) {
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(mp_f16_supported(d), "conv_edges_f16: channel plan %d / %d / %d is not instantiated (64 / 64 / 128)", d.cn, d.ce, d.h);
+    return run_conv_edges(*blk, *g, nullptr, proj, agg, static_cast<cudaStream_t>(stream), static_cast<const uint32_t*>(e_split));
+}
+
 extern "C" size_t rgnn_detector_workspace_bytes(const rgnn_detector* net, const rgnn_graph* g, int training) {
     DetPlan pl;
     if (plan_detector(*net, *g, training, nullptr, &pl) != RGNN_OK) return 0;
@@ -457,5 +483,5 @@ extern "C" int rgnn_detector_obj_head(const rgnn_detector* net, const rgnn_graph
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d) + tc_proj_pack_floats(d);
+    return conv_msg0_f16_offset(d) + mp_f16_pack_floats(d);
 }

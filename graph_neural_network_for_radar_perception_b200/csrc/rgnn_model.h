@@ -22,6 +22,7 @@ struct DetPlan {
     float* P[RGNN_MAX_CONV];       // per-node projections of msg.0: [x W1_target^T | x W1_source^T]
     float* agg[RGNN_MAX_CONV];     // aggregated messages
     float* emb;                    // edge embedding, target-major order
+    uint32_t* emb_hl;              // the same rows pre-split for the f16 message kernel: [hi 64 fp16 | lo 64 fp16] x 16 (nullptr: not used)
     float* hlink;                  // predict_link.compute_edge.stem output per node
     float* gcls;                   // predict_class.stem output per node
     // ---- backward only ----
@@ -63,6 +64,19 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
 int run_conv_edges_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
                       const float* wpack, float* agg, cudaStream_t stream);
 
+// fp16-split role-pipelined message kernel, rgnn_mp_f16.cu (forward; the packed images sit behind the projection images)
+bool mp_f16_supported(const ConvDims& d);
+int mp_f16_passes();
+size_t mp_f16_pack_floats(const ConvDims& d);
+size_t mp_f16_emb_words(int n_edges);
+int mp_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
+int mp_f16_split_emb(const float* emb, int n_edges, uint32_t* out, cudaStream_t stream);
+int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const uint32_t* emb_hl, const float* P,
+                       const float* wpack, float* agg, cudaStream_t stream);
+int mp_f16_set_option(const char* name, int value);
+int mp_f16_get_option(const char* name);
+inline size_t conv_msg0_f16_offset(const ConvDims& d);
+
 // tensor-core backward of the message function (rgnn_mp_bwd_tc.cu) and the generic weight-gradient GEMM (rgnn_wgrad_tc.cu)
 bool mp_bwd_tc_supported(const ConvDims& d);
 size_t mp_bwd_tc_scratch_floats(const ConvDims& d, int n_edges);
@@ -84,6 +98,7 @@ bool tc_proj_supported(const ConvDims& d);
 size_t tc_proj_pack_floats(const ConvDims& d);
 int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream);
 int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t stream);
+inline size_t conv_msg0_f16_offset(const ConvDims& d) { return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d) + tc_proj_pack_floats(d); }
 int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream,
                  const TcSave* save = nullptr);
 bool tc_stack_bwd_supported(const rgnn_stack& s);

@@ -195,6 +195,14 @@ int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* 
  * agg[t] = sum over edges s->t of msg(x_t, x_s, e); proj = the hoisted node projections written by
  * rgnn_conv_block_fwd (or by the previous block).  This is the dominant kernel of the forward; bench.py times it. */
 int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, float* agg, void* stream);
+/* The fp16-split message kernel (csrc/rgnn_mp_f16.cu) reads the edge embedding PRE-SPLIT: per edge 64 32-bit words
+ * = [hi: 64 fp16 | lo: 64 fp16] of 16 x the embedding (hi = fp16(16 e), lo = fp16(16 e - hi); 256 bytes per edge like the
+ * fp32 row).  The embedding is produced once per forward and read by every conv block, so it is split once.
+ * rgnn_split_edge_embedding: e (n_edges, 64) fp32, target-major -> e_split (n_edges * 64 words).
+ * rgnn_conv_edges_f16_fwd: rgnn_conv_edges_fwd on the split rows (64 / 64 / 128 channel plan; other plans return an error). */
+int rgnn_split_edge_embedding(const float* e, int n_edges, void* e_split, void* stream);
+int rgnn_conv_edges_f16_fwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj, float* agg,
+                            void* stream);
 
 /* Model_Inference.forward with cluster_node_idx given (gnn_detector.py:141-162).
  * edge_features rows are in the caller's order (g->perm maps them).  Outputs: node_cls (N,7), node_off (N,2),

@@ -50,44 +50,28 @@ def _grads(model, batch):
     return {n: p.grad.detach().double().cpu().numpy() for n, p in model.named_parameters()}
 
 
-def test_tensor_core_backward_matches_ffma_backward(ckpt_state_dict):
-    """Same forward, same losses; only the backward of the message function differs (tcgen05 + scratch + wgrad GEMM
-    vs recompute tile programs on the CUDA cores).  Both are fp32-equivalent, so they agree far inside the tolerance
-    either has against the reference (test_train_gpu.py)."""
-    from gpu_util import load_model
-    from graph_neural_network_for_radar_perception_b200 import synth
-    from oracle import graph_np
+def test_tensor_core_backward_and_ffma_backward_both_meet_the_yardstick(ckpt_state_dict):
+    """Same forward, same losses; only the backward of the message function differs (tcgen05 + scratch + wgrad GEMM vs
+    recompute tile programs on the CUDA cores).  The two recompute the edge activations with different (both
+    fp32-equivalent) arithmetic, so they may land on different sides of an undecidable LeakyReLU kink: they are not
+    compared with each other through a blanket allowance but each is held to the reference's float64 gradient with the
+    yardstick of tests/test_train_gpu.py (float32 noise of the reference + the exact jumps of the listed kinks)."""
+    from gpu_util import GradientYardstick, batch_labels, load_model, synth_batch
+    from test_train_gpu import FLIP_WINDOW
+    frames = synth_batch((260, 97), seed0=70)
+    ys = GradientYardstick(ckpt_state_dict, frames, members=4, flip_window=FLIP_WINDOW)
     m = load_model(ckpt_state_dict).train()
-    R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
-    nf, ef, ei = [], [], []
-    labels = {k: [] for k in ('cluster_node_idx', 'cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
-    for i, n in enumerate((700, 431, 97)):
-        d, src = synth.make_frame(70 + i, n)
-        adj = graph_np.adjacency_information(d, 25, 10)
-        lab = synth.make_labels(d, src, adj['adj_list'])
-        nf.append(torch.from_numpy(graph_np.node_features(d, adj['degree'], True, 0, R, 0, np.pi * 0.5).astype(np.float32)).cuda())
-        ef.append(torch.from_numpy(graph_np.edge_features(d, adj['adj_list']).astype(np.float32)).cuda())
-        ei.append(torch.from_numpy(adj['adj_list']).cuda())
-        labels['cluster_node_idx'].append([torch.from_numpy(c).cuda() for c in lab['cluster_node_idx']])
-        for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets'):
-            labels[k].append(torch.from_numpy(lab[k]).cuda())
-    off0 = [t.clone() for t in labels['node_offsets']]
 
-    def batch():
-        lb = dict(labels)
-        lb['node_offsets'] = [t.clone() for t in off0]       # normalised in place by the training forward
-        return nf, ef, ei, lb
+    def grads():
+        m.zero_grad(set_to_none=True)
+        loss, _ = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
+                    [None] * len(frames), batch_labels(frames, 'cuda'))
+        sum(loss.values()).backward()
+        return {n: p.grad.detach().double().cpu().numpy() for n, p in m.named_parameters()}
     assert lib().rgnn_get_option(b'tensor_cores_bwd') == 1
-    g_tc = _grads(m, batch())
+    ys.check(grads(), what='tensor-core backward')
     try:
         check(lib().rgnn_set_option(b'tensor_cores_bwd', 0), 'set_option')
-        g_ff = _grads(m, batch())
+        ys.check(grads(), what='FFMA backward')
     finally:
         check(lib().rgnn_set_option(b'tensor_cores_bwd', 1), 'set_option')
-    rel = []
-    for n in g_tc:
-        scale = max(np.abs(g_ff[n]).max(), 1e-9)
-        rel.append(np.abs(g_tc[n] - g_ff[n]).max() / scale)
-        if g_ff[n].size > 1:
-            assert rel[-1] < 5e-3, (n, rel[-1])      # kink allowance, see test_train_gpu.py
-    assert np.median(rel) < 2e-5, (np.median(rel), max(rel))

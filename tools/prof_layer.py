@@ -76,6 +76,19 @@ def main():
         conv = table.det.conv[0]
         s = stream_ptr()
         fn = lambda: check(lib().rgnn_conv_edges_fwd(C.byref(conv), C.byref(g), ptr(e), ptr(proj), ptr(agg), s), 'edges')
+    elif args.what == 'edges16':    # the fp16-split message kernel alone on pre-split rows (its launch also zero-fills agg)
+        table = detector_table(det)
+        table.refill(None)
+        check(lib().rgnn_pack_detector(C.byref(table.det), stream_ptr()), 'pack')
+        e = torch.randn(E, 64, device=dev)
+        es = torch.empty(E * 64, dtype=torch.int32, device=dev)
+        check(lib().rgnn_split_edge_embedding(ptr(e), E, ptr(es), stream_ptr()), 'split')
+        agg = torch.empty(N, 64, device=dev)
+        proj = torch.randn(N, 256, device=dev)
+        g = gb.c_struct()
+        conv = table.det.conv[0]
+        s = stream_ptr()
+        fn = lambda: check(lib().rgnn_conv_edges_f16_fwd(C.byref(conv), C.byref(g), ptr(es), ptr(proj), ptr(agg), s), 'edges16')
     elif args.what == 'forward':
         gb.set_clusters([[torch.arange(i, min(i + 4, n)) for i in range(0, n, 4)] for n in np.diff(fp)], fp[:-1], dev)
 
