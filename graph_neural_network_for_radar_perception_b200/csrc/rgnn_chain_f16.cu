@@ -1,0 +1,364 @@
+// Fixed-shape 64-wide ffn_block chains on the tensor cores with fp16-split operands (rgnn_f16.cuh): the stems and
+// FFN_TaskSpecificHeads behind the message-passing layers (reference gnn_blocks.py:167-344: node_segmentation,
+// node_offset_predictions, edge_formation + link_predictions, the stem of object_classification):
+//
+//   input rows (n, 64) fp32  [or pair sums h[a] + h[b] for the link head]
+//     -> N_HIDDEN x ( Linear 64 -> 64, channel_normalization, LeakyReLU )
+//     -> either the activation itself (n, 64) fp32   or   a bare Linear 64 -> n_out (n_out <= 16)
+//
+// One CTA per SM, persistent.  Thread = TMEM lane = row.  FOUR tiles of 128 rows are in flight per CTA, each owned by one group
+// of 4 epilogue warps that carries its tile through all layers (no row statistic crosses a thread, no hand-over between
+// groups); the single MMA-issue lane serves whichever group has an operand ready, so one group's epilogue runs under the
+// other groups' MMAs.  Every weight image (<= 68 KB as fp16 hi | lo) stays in shared memory for the whole kernel; MMA shapes
+// and descriptors are compile-time constants.  Tensor memory: 128 columns per group = two 64-column regions that alternate
+// as A operand / accumulator; an epilogue rewrites its accumulator in place into the next A operand (per 32 fp32 columns:
+// 16 packed hi columns | 16 packed lo columns).
+#include "rgnn_f16.cuh"
+#include "rgnn_model.h"
+#include "rgnn_tc_rows.cuh"
+
+namespace rgnn {
+
+constexpr int C64_MAX_LAYERS = 5;        // up to 4 hidden + 1 tail Linear
+
+struct Chain64Args {
+    int n_rows;
+    int in_mode;                // 0: rows of x; 1: pair sums x[ia[r]] + x[ib[r]]
+    const float* x;             // (n, 64) fp32, row stride ldx
+    int ldx;
+    const int* ia;
+    const int* ib;
+    int n_hidden;               // 1 .. 4
+    int tail;                   // 0: store the last activation (n, 64); 1: bare Linear to n_out columns
+    int n_out;
+    const uint32_t* w[C64_MAX_LAYERS];      // per layer [hi | lo] images (K = 64; N = 64, tail: 16 rows, zero padded)
+    const float* bias[C64_MAX_LAYERS];
+    const float* scale[C64_MAX_LAYERS];     // channel_normalization gain (device scalar) or nullptr
+    const float* shift[C64_MAX_LAYERS];
+    int act[C64_MAX_LAYERS];
+    float* y;
+    int ldy;
+    int passes;
+};
+
+namespace c64 {
+constexpr int W = 64, TM = 128, NGROUPS = 4, NT_OUT = 16;
+constexpr int NTHREADS = 128 * NGROUPS + 128;          // + the warp group holding the MMA-issue warp
+constexpr int IMG_WORDS = W * W;                       // hi + lo of a 64 x 64 layer (2 x 64 x 64 x 2 B)
+constexpr int TAIL_WORDS = W * NT_OUT;
+constexpr int OFF_W = 0;
+constexpr int OFF_CST = OFF_W + 4 * IMG_WORDS + TAIL_WORDS;         // per layer: bias[64], gain, shift (stride 72)
+constexpr int CST_LD = 72;
+constexpr int OFF_BAR = OFF_CST + C64_MAX_LAYERS * CST_LD;          // a_full[4], d_full[4]
+constexpr int OFF_SLOT = OFF_BAR + 2 * 2 * NGROUPS;
+constexpr int WORDS = OFF_SLOT + 2;
+constexpr size_t SMEM = (size_t)WORDS * 4;
+static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+}  // namespace c64
+
+__global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __grid_constant__ Chain64Args a) {
+    using namespace c64;
+    extern __shared__ __align__(1024) uint32_t smem_u[];
+    float* smem_f = reinterpret_cast<float*>(smem_u);
+    uint32_t* wsm = smem_u + OFF_W;
+    float* cst = smem_f + OFF_CST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_u + OFF_BAR);
+    uint64_t* a_full = bars;
+    uint64_t* d_full = bars + NGROUPS;
+    uint32_t* slot = smem_u + OFF_SLOT;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = warp >> 2, w4 = warp & 3, row = tid & 127;
+    const int G = (int)gridDim.x;
+    const int n_tiles = (a.n_rows + TM - 1) / TM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int np = a.passes == 1 ? 1 : 3;
+    const int n_mma = a.n_hidden + (a.tail ? 1 : 0);
+
+    // ---- one-time setup ----
+    for (int l = 0; l < n_mma; ++l) {
+        const int words = l < a.n_hidden ? IMG_WORDS : TAIL_WORDS;
+        const uint4* src = reinterpret_cast<const uint4*>(a.w[l]);
+        uint4* dst = reinterpret_cast<uint4*>(wsm + l * IMG_WORDS);
+        for (int i = tid; i < words / 4; i += NTHREADS) dst[i] = __ldg(src + i);
+    }
+    for (int i = tid; i < n_mma * CST_LD; i += NTHREADS) {
+        const int l = i / CST_LD, c = i - l * CST_LD;
+        const int nb = l < a.n_hidden ? W : a.n_out;
+        float v = 0.f;
+        if (c < W) v = (a.bias[l] != nullptr && c < nb) ? __ldg(a.bias[l] + c) : 0.f;
+        else if (c == W) v = a.scale[l] != nullptr ? __ldg(a.scale[l]) : 1.f;
+        else if (c == W + 1) v = a.shift[l] != nullptr ? __ldg(a.shift[l]) : 0.f;
+        cst[i] = v;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NGROUPS; ++i) { tc::mbar_init(&a_full[i], 4); tc::mbar_init(&d_full[i], 1); }
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(slot, 512);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *slot;
+
+    if (g < NGROUPS) {
+        // =========================== epilogue groups ===========================
+        const uint32_t t_base = tmem + ((uint32_t)w4 << 21) + (uint32_t)g * 128;    // this group's 128 columns, this warp's lanes
+        uint32_t uses = 0;          // completed phases of this group's barriers (one per MMA group)
+        for (int j = g; j < my_tiles; j += NGROUPS) {
+            const int tile = (int)blockIdx.x + j * G;
+            const int r = tile * TM + row;
+            const bool valid = r < a.n_rows;
+            // ---- input rows -> A operand in region 0 (x 16, hi | lo per 32 columns) ----
+            {
+                const float* pa = a.x;
+                const float* pb = nullptr;
+                if (a.in_mode == 1) {
+                    const int na = valid ? __ldg(a.ia + r) : 0, nb = valid ? __ldg(a.ib + r) : 0;
+                    pa = a.x + (size_t)na * a.ldx;
+                    pb = a.x + (size_t)nb * a.ldx;
+                } else {
+                    pa = a.x + (size_t)(valid ? r : 0) * a.ldx;
+                }
+                const float2 s16 = make_float2(f16::A_SCALE, f16::A_SCALE);
+#pragma unroll 1
+                for (int c = 0; c < W; c += 32) {
+                    float2 v[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ldg256(pa + c + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    if (pb != nullptr) {
+                        float2 u[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ldg256(pb + c + 8 * i, u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __fadd2_rn(v[i], u[i]);
+                    }
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f16::split(valid ? __fmul2_rn(v[i], s16) : make_float2(0.f, 0.f), hi[i], lo[i]);
+                    f16::tmem_st16u(t_base + c, hi);
+                    if (np != 1) f16::tmem_st16u(t_base + c + 16, lo);
+                }
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                warp_arrive(&a_full[g], lane);
+            }
+            // ---- hidden layers ----
+            for (int l = 0; l < a.n_hidden; ++l) {
+                const float* cb = cst + l * CST_LD;
+                const uint32_t dreg = t_base + (uint32_t)(((l + 1) & 1) * W);
+                tc::mbar_wait(&d_full[g], uses & 1u);
+                ++uses;
+                tc::tc_fence_after();
+                float2 va[16], vb[16];
+                tc::tmem_ld16(dreg, va);
+                tc::tmem_ld16(dreg + 16, va + 8);
+                tc::tmem_ld16(dreg + 32, vb);
+                tc::tmem_ld16(dreg + 48, vb + 8);
+                tc::tmem_wait_ld();
+                const float2 us = make_float2(f16::D_UNSCALE, f16::D_UNSCALE);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    va[c] = __ffma2_rn(va[c], us, *reinterpret_cast<const float2*>(cb + 2 * c));
+                    vb[c] = __ffma2_rn(vb[c], us, *reinterpret_cast<const float2*>(cb + 32 + 2 * c));
+                }
+                const bool last = (l + 1 == a.n_hidden) && !a.tail;
+                const float osc = last ? 1.f : f16::A_SCALE;          // the next A operand carries x 16
+                float k = osc, sh = 0.f, mean = 0.f;
+                if (a.scale[l] != nullptr) {
+                    RowStats st;
+                    st.init();
+                    st.add_chunk(va);
+                    st.add_chunk(vb);
+                    k = osc * cb[W] * __frcp_rn(st.sigma(W) + NORM_EPS);
+                    sh = osc * cb[W + 1];
+                    mean = st.mean;
+                }
+                const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean, -mean);
+                const bool act = a.act[l] != 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    va[c] = __ffma2_rn(__fadd2_rn(va[c], nm), k2, sh2);
+                    vb[c] = __ffma2_rn(__fadd2_rn(vb[c], nm), k2, sh2);
+                    if (act) {
+                        const float2 ta = __fmul2_rn(va[c], sl), tb = __fmul2_rn(vb[c], sl);
+                        va[c].x = fmaxf(va[c].x, ta.x); va[c].y = fmaxf(va[c].y, ta.y);
+                        vb[c].x = fmaxf(vb[c].x, tb.x); vb[c].y = fmaxf(vb[c].y, tb.y);
+                    }
+                }
+                if (last) {
+                    if (valid) {
+                        float* o = a.y + (size_t)r * a.ldy;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            stg256(o + 8 * i, va[4 * i], va[4 * i + 1], va[4 * i + 2], va[4 * i + 3]);
+                            stg256(o + 32 + 8 * i, vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
+                        }
+                    }
+                } else {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f16::split(va[i], hi[i], lo[i]);
+                    f16::tmem_st16u(dreg, hi);
+                    if (np != 1) f16::tmem_st16u(dreg + 16, lo);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f16::split(vb[i], hi[i], lo[i]);
+                    f16::tmem_st16u(dreg + 32, hi);
+                    if (np != 1) f16::tmem_st16u(dreg + 48, lo);
+                    tc::tmem_wait_st();
+                    tc::tc_fence_before();
+                    warp_arrive(&a_full[g], lane);
+                }
+            }
+            // ---- tail Linear (<= 16 outputs, no norm / activation) ----
+            if (a.tail) {
+                const float* cb = cst + a.n_hidden * CST_LD;
+                const uint32_t dreg = t_base + (uint32_t)(((a.n_hidden + 1) & 1) * W);
+                tc::mbar_wait(&d_full[g], uses & 1u);
+                ++uses;
+                tc::tc_fence_after();
+                float2 v[8];
+                tc::tmem_ld16(dreg, v);
+                tc::tmem_wait_ld();
+                if (valid) {
+                    float* o = a.y + (size_t)r * a.ldy;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (2 * c < a.n_out) o[2 * c] = fmaf(v[c].x, f16::D_UNSCALE, cb[2 * c]);
+                        if (2 * c + 1 < a.n_out) o[2 * c + 1] = fmaf(v[c].y, f16::D_UNSCALE, cb[2 * c + 1]);
+                    }
+                }
+            }
+            tc::tc_fence_before();      // this tile's last TMEM reads precede the next tile's operand stores
+        }
+    } else if (warp == 4 * NGROUPS) {
+        // =========================== MMA issue warp ===========================
+        if (lane == 0) {
+            constexpr uint32_t IDESC64 = f16::idesc(TM, W), IDESC16 = f16::idesc(TM, NT_OUT);
+            const uint32_t sW = tc::smem_u32(wsm);
+            int tile_j[NGROUPS], layer[NGROUPS];
+            uint32_t uses[NGROUPS];
+            int remaining = 0;
+            for (int i = 0; i < NGROUPS; ++i) {
+                tile_j[i] = i; layer[i] = 0; uses[i] = 0;
+                if (i < my_tiles) ++remaining;
+            }
+            while (remaining > 0) {
+                bool did = false;
+#pragma unroll
+                for (int i = 0; i < NGROUPS; ++i) {
+                    if (tile_j[i] >= my_tiles) continue;
+                    if (!f16::mbar_test(&a_full[i], uses[i] & 1u)) continue;
+                    tc::tc_fence_after();
+                    const int l = layer[i];
+                    const bool is_tail = l == a.n_hidden;
+                    const uint32_t areg = tmem + (uint32_t)i * 128 + (uint32_t)((l & 1) * W);
+                    const uint32_t dreg = tmem + (uint32_t)i * 128 + (uint32_t)(((l + 1) & 1) * W);
+                    const uint32_t nrows = is_tail ? NT_OUT : W;
+                    const uint32_t lbo = nrows * 16, img = W * nrows * 2;       // bytes: next 8 K elements; hi image size
+                    const uint32_t wl = sW + (uint32_t)l * (IMG_WORDS * 4);
+                    bool acc = false;
+                    for (int p = 0; p < np; ++p) {      // small terms first: lo*hi, hi*lo, then hi*hi
+                        const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                        const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                        const uint64_t bd0 = tc::smem_desc(wl + pb * img, lbo, 128);
+#pragma unroll
+                        for (int ks = 0; ks < W / 16; ++ks) {
+                            const uint32_t acol = areg + (ks >> 1) * 32 + (ks & 1) * 8 + (pa ? 16u : 0u);
+                            f16::mma_ts(dreg, acol, bd0 + (uint64_t)((ks * 2 * lbo) >> 4), is_tail ? IDESC16 : IDESC64, acc);
+                            acc = true;
+                        }
+                    }
+                    tc::mma_commit(&d_full[i]);
+                    ++uses[i];
+                    if (++layer[i] == n_mma) {
+                        layer[i] = 0;
+                        tile_j[i] += NGROUPS;
+                        if (tile_j[i] >= my_tiles) --remaining;
+                    }
+                    did = true;
+                }
+                if (!did) __nanosleep(20);
+            }
+        }
+        __syncwarp();
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_chain_f16 = 1;
+int chain_f16_set_option(const char* name, int value) {
+    if (strcmp(name, "f16_chain") == 0 && (value == 0 || value == 1)) { g_chain_f16 = value; return 1; }
+    return 0;
+}
+int chain_f16_get_option(const char* name) { return strcmp(name, "f16_chain") == 0 ? g_chain_f16 : -2; }
+
+// floats appended to a Linear's packed buffer for its fp16 image pair (0: the layer has none)
+size_t f16_image_floats(int in_features, int out_features) {
+    if (in_features % 16 != 0 || in_features > 256 || out_features > 256) return 0;
+    return (size_t)in_features * round_up(out_features, 16);
+}
+
+int pack_f16_image(const float* W, int ldw, int K, int N, int n_valid, int k_valid, uint32_t* dst, cudaStream_t stream);
+
+int f16_pack_linear(const rgnn_linear& L, float* dst, cudaStream_t stream) {
+    if (f16_image_floats(L.in_features, L.out_features) == 0) return RGNN_OK;
+    return pack_f16_image(L.weight, L.in_features, L.in_features, round_up(L.out_features, 16), L.out_features, L.in_features,
+                          reinterpret_cast<uint32_t*>(dst), stream);
+}
+
+// stack = N_HIDDEN x (64 -> 64, norm, act) [+ bare Linear 64 -> n_out <= 16]
+bool chain64_supported(const rgnn_stack& s) {
+    if (!g_chain_f16 || s.n < 1 || s.n > C64_MAX_LAYERS) return false;
+    int n_hidden = s.n;
+    const rgnn_linear& last = s.layer[s.n - 1];
+    const bool tail = last.norm_scale == nullptr && !last.activation;
+    if (tail) --n_hidden;
+    if (n_hidden < 1 || n_hidden > 4) return false;
+    for (int i = 0; i < n_hidden; ++i) {
+        const rgnn_linear& L = s.layer[i];
+        if (L.in_features != 64 || L.out_features != 64 || L.norm_scale == nullptr || L.weight_t == nullptr) return false;
+    }
+    if (tail && (last.in_features != 64 || last.out_features > 16 || last.weight_t == nullptr)) return false;
+    return true;
+}
+
+const float* f16_weights(const rgnn_linear& L);      // rgnn_model_tc.cu
+
+int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream) {
+    if (n_rows <= 0) return RGNN_OK;
+    Chain64Args a;
+    memset(&a, 0, sizeof(a));
+    const rgnn_linear& last = s.layer[s.n - 1];
+    a.tail = (last.norm_scale == nullptr && !last.activation) ? 1 : 0;
+    a.n_hidden = s.n - a.tail;
+    a.n_out = a.tail ? last.out_features : 64;
+    a.n_rows = n_rows;
+    a.in_mode = ia != nullptr ? 1 : 0;
+    a.x = x; a.ldx = ldx; a.ia = ia; a.ib = ib;
+    for (int l = 0; l < s.n; ++l) {
+        const rgnn_linear& L = s.layer[l];
+        a.w[l] = reinterpret_cast<const uint32_t*>(f16_weights(L));
+        a.bias[l] = L.bias; a.scale[l] = L.norm_scale; a.shift[l] = L.norm_shift; a.act[l] = L.activation;
+    }
+    a.y = y; a.ldy = a.n_out;
+    a.passes = mp_f16_passes();
+    static PerDeviceOnce once;
+    if (once.needed()) {
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(chain64_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c64::SMEM));
+        once.mark();
+    }
+    const int n_tiles = (n_rows + c64::TM - 1) / c64::TM;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    chain64_f16_kernel<<<grid, c64::NTHREADS, c64::SMEM, stream>>>(a);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+}  // namespace rgnn

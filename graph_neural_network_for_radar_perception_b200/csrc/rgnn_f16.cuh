@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "rgnn_common.cuh"
 #include "rgnn_tc.cuh"
 
 namespace rgnn {
@@ -109,4 +110,45 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 }
 
 }  // namespace f16
+
+// one elected lane per warp arrives for its 32 rows (the warp-collective tcgen05.wait / fences come first)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(bar);
+}
+
+// Row statistics of channel_normalization for a row that is visited in chunks of 32 values (16 register pairs): every
+// chunk is centred on its own mean (two register-only passes, like the reference's two-pass formula on that chunk) and
+// the chunks are merged with the exact pairwise update  mean = mean_a + d n_b / n,  M2 = M2_a + M2_b + d^2 n_a n_b / n
+// (d = mean_b - mean_a): no sum-of-squares cancellation, and the loop body stays small enough for the instruction cache.
+struct RowStats {
+    float mean, m2, n;
+    __device__ __forceinline__ void init() { mean = 0.f; m2 = 0.f; n = 0.f; }
+    __device__ __forceinline__ void add_chunk(const float2 (&v)[16]) {
+        float2 s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+#pragma unroll
+        for (int c = 4; c < 16; c += 4) {
+            s0 = __fadd2_rn(s0, v[c]); s1 = __fadd2_rn(s1, v[c + 1]); s2 = __fadd2_rn(s2, v[c + 2]); s3 = __fadd2_rn(s3, v[c + 3]);
+        }
+        const float2 st = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
+        const float mc = (st.x + st.y) * (1.f / 32.f);
+        const float2 nm = make_float2(-mc, -mc);
+        float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float2 d0 = __fadd2_rn(v[c], nm), d1 = __fadd2_rn(v[c + 1], nm), d2 = __fadd2_rn(v[c + 2], nm), d3 = __fadd2_rn(v[c + 3], nm);
+            q0 = __ffma2_rn(d0, d0, q0); q1 = __ffma2_rn(d1, d1, q1); q2 = __ffma2_rn(d2, d2, q2); q3 = __ffma2_rn(d3, d3, q3);
+        }
+        const float2 qt = __fadd2_rn(__fadd2_rn(q0, q1), __fadd2_rn(q2, q3));
+        const float m2c = qt.x + qt.y;
+        const float nn = n + 32.f;
+        const float d = mc - mean;
+        const float w = 32.f / nn;                   // exact: n is a multiple of 32 up to 128
+        m2 = m2 + m2c + d * d * (n * w);
+        mean = fmaf(d, w, mean);
+        n = nn;
+    }
+    __device__ __forceinline__ float sigma(int count) const { return __fsqrt_rn(m2 * (1.f / (float)(count - 1))); }
+};
+
 }  // namespace rgnn

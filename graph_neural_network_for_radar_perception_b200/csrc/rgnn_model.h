@@ -77,6 +77,14 @@ int mp_f16_set_option(const char* name, int value);
 int mp_f16_get_option(const char* name);
 inline size_t conv_msg0_f16_offset(const ConvDims& d);
 
+// fixed-shape 64-wide chains with fp16-split operands, rgnn_chain_f16.cu (inference forward of the stems / heads)
+size_t f16_image_floats(int in_features, int out_features);
+int f16_pack_linear(const rgnn_linear& L, float* dst, cudaStream_t stream);
+bool chain64_supported(const rgnn_stack& s);
+int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream);
+int chain_f16_set_option(const char* name, int value);
+int chain_f16_get_option(const char* name);
+
 // tensor-core backward of the message function (rgnn_mp_bwd_tc.cu) and the generic weight-gradient GEMM (rgnn_wgrad_tc.cu)
 bool mp_bwd_tc_supported(const ConvDims& d);
 size_t mp_bwd_tc_scratch_floats(const ConvDims& d, int n_edges);

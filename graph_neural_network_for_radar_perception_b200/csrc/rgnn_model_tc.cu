@@ -269,12 +269,21 @@ size_t tc_proj_pack_floats(const ConvDims& d) {
     return (d.cn == 64 && d.h == 128) ? tc_proj_fwd_floats(d) + 2 * tc_pack_floats(d.h, d.cn) : 0;
 }
 
-size_t tc_linear_pack_floats(int in_features, int out_features) {
+static size_t tc_linear_tc_floats(int in_features, int out_features) {
     return (in_features > 256 || out_features > 256) ? 0 : tc_pack_floats(in_features, out_features) + tc_t_pack_floats(in_features, out_features);
 }
+// tf32 chunk streams (forward + transposed) followed by the fp16 image pair of the f16 kernels
+size_t tc_linear_pack_floats(int in_features, int out_features) {
+    return tc_linear_tc_floats(in_features, out_features) + f16_image_floats(in_features, out_features);
+}
+const float* f16_weights(const rgnn_linear& L) { return tc_weights(L) + tc_linear_tc_floats(L.in_features, L.out_features); }
 
 int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream) {
     if (L.in_features > 256 || L.out_features > 256) return RGNN_OK;
+    {
+        const int rc16 = f16_pack_linear(L, const_cast<float*>(f16_weights(L)), stream);
+        if (rc16) return rc16;
+    }
     const int Kp = tc_kp(L.in_features), Np = tc_np(L.out_features);
     float* dst = const_cast<float*>(tc_weights(L));
     int rc = pack_tc(L.weight, L.in_features, 0, L.out_features, 0, Np, 0, L.in_features, Kp, tc_chunk_k(Kp, Np), true, dst, stream);

@@ -81,46 +81,6 @@ constexpr int BAR_E2 = 12, BAR_E1 = 13;
 enum { B_PS_FULL = 0, B_PS_FREE = 2, B_A_FULL = 4, B_D1_FULL = 6, B_Y1_FULL = 8, B_D2_FULL = 10, B_D2_FREE = 12 };
 }  // namespace mpf
 
-// one elected lane per warp arrives for its 32 rows (the warp-collective tcgen05.wait / fences come first)
-__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive(bar);
-}
-
-// Row statistics of channel_normalization for a row that is visited in chunks of 32 values (16 register pairs): every
-// chunk is centred on its own mean (two register-only passes, like the reference's two-pass formula on that chunk) and
-// the chunks are merged with the exact pairwise update  mean = mean_a + d n_b / n,  M2 = M2_a + M2_b + d^2 n_a n_b / n
-// (d = mean_b - mean_a): no sum-of-squares cancellation, and the loop body stays small enough for the instruction cache.
-struct RowStats {
-    float mean, m2, n;
-    __device__ __forceinline__ void init() { mean = 0.f; m2 = 0.f; n = 0.f; }
-    __device__ __forceinline__ void add_chunk(const float2 (&v)[16]) {
-        float2 s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
-#pragma unroll
-        for (int c = 4; c < 16; c += 4) {
-            s0 = __fadd2_rn(s0, v[c]); s1 = __fadd2_rn(s1, v[c + 1]); s2 = __fadd2_rn(s2, v[c + 2]); s3 = __fadd2_rn(s3, v[c + 3]);
-        }
-        const float2 st = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
-        const float mc = (st.x + st.y) * (1.f / 32.f);
-        const float2 nm = make_float2(-mc, -mc);
-        float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-            const float2 d0 = __fadd2_rn(v[c], nm), d1 = __fadd2_rn(v[c + 1], nm), d2 = __fadd2_rn(v[c + 2], nm), d3 = __fadd2_rn(v[c + 3], nm);
-            q0 = __ffma2_rn(d0, d0, q0); q1 = __ffma2_rn(d1, d1, q1); q2 = __ffma2_rn(d2, d2, q2); q3 = __ffma2_rn(d3, d3, q3);
-        }
-        const float2 qt = __fadd2_rn(__fadd2_rn(q0, q1), __fadd2_rn(q2, q3));
-        const float m2c = qt.x + qt.y;
-        const float nn = n + 32.f;
-        const float d = mc - mean;
-        const float w = 32.f / nn;                   // exact: n is a multiple of 32 up to 128
-        m2 = m2 + m2c + d * d * (n * w);
-        mean = fmaf(d, w, mean);
-        n = nn;
-    }
-    __device__ __forceinline__ float sigma(int count) const { return __fsqrt_rn(m2 * (1.f / (float)(count - 1))); }
-};
-
 template <bool PROFILE>
 __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __grid_constant__ MpF16Args a) {
     using namespace mpf;
@@ -612,12 +572,12 @@ __global__ void emb_split_f16_kernel(const float* __restrict__ emb, uint32_t* __
 }
 
 // weights: element (n, k) = W[off + n * sn + k * sk], x 256 -> fp16 hi / lo chunk-major images [K/8][N][8]
-__global__ void pack_split_f16_kernel(const float* __restrict__ W, int off, int sn, int sk, int K, int N, __half* __restrict__ hi,
-                                      __half* __restrict__ lo) {
+__global__ void pack_split_f16_kernel(const float* __restrict__ W, int off, int sn, int sk, int K, int N, int n_valid, int k_valid,
+                                      __half* __restrict__ hi, __half* __restrict__ lo) {
     const int tot = K * N;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
         const int q = i & 7, n = (i >> 3) % N, kc = (i >> 3) / N;
-        const float w = W[(size_t)off + (size_t)n * sn + (size_t)(8 * kc + q) * sk] * f16::W_SCALE;
+        const float w = (n < n_valid && 8 * kc + q < k_valid) ? W[(size_t)off + (size_t)n * sn + (size_t)(8 * kc + q) * sk] * f16::W_SCALE : 0.f;
         const uint32_t h2 = f16::pack_sat(w, 0.f);
         const float hf = f16::unpack(h2).x;
         const uint32_t l2 = f16::pack_sat(w - hf, 0.f);
@@ -641,8 +601,17 @@ int mp_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t 
     const rgnn_linear& m1 = c.msg.layer[1];
     __half* w = reinterpret_cast<__half*>(dst);
     const int W1 = d.ce * d.h, W2 = d.h * d.cn;
-    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, m0.in_features, 1, d.ce, d.h, w, w + W1);
-    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, m1.in_features, 1, d.h, d.cn, w + 2 * W1, w + 2 * W1 + W2);
+    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, m0.in_features, 1, d.ce, d.h, d.h, d.ce, w, w + W1);
+    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, m1.in_features, 1, d.h, d.cn, d.cn, d.h, w + 2 * W1, w + 2 * W1 + W2);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+// (K x N) image pair of one Linear for the f16 kernels: element (n, k) = W[n * ldw + k] (n < n_valid, k < k_valid, else 0)
+int pack_f16_image(const float* W, int ldw, int K, int N, int n_valid, int k_valid, uint32_t* dst, cudaStream_t stream) {
+    __half* w = reinterpret_cast<__half*>(dst);
+    const int blocks = (K * N + 255) / 256;
+    pack_split_f16_kernel<<<blocks > 32 ? 32 : blocks, 256, 0, stream>>>(W, 0, ldw, 1, K, N, n_valid, k_valid, w, w + (size_t)K * N);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
