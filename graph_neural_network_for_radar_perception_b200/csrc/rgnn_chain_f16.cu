@@ -301,7 +301,9 @@ int chain_f16_get_option(const char* name) { return strcmp(name, "f16_chain") ==
 
 // floats appended to a Linear's packed buffer for its fp16 image pair (0: the layer has none)
 size_t f16_image_floats(int in_features, int out_features) {
-    if (in_features % 16 != 0 || in_features > 256 || out_features > 256) return 0;
+    if (in_features > 256 || out_features > 256) return 0;
+    if (in_features < 16) return (size_t)16 * round_up(out_features, 16);       // raw feature inputs: K zero padded to 16
+    if (in_features % 16 != 0) return 0;
     return (size_t)in_features * round_up(out_features, 16);
 }
 
@@ -309,7 +311,8 @@ int pack_f16_image(const float* W, int ldw, int K, int N, int n_valid, int k_val
 
 int f16_pack_linear(const rgnn_linear& L, float* dst, cudaStream_t stream) {
     if (f16_image_floats(L.in_features, L.out_features) == 0) return RGNN_OK;
-    return pack_f16_image(L.weight, L.in_features, L.in_features, round_up(L.out_features, 16), L.out_features, L.in_features,
+    const int K = L.in_features < 16 ? 16 : L.in_features;
+    return pack_f16_image(L.weight, L.in_features, K, round_up(L.out_features, 16), L.out_features, L.in_features,
                           reinterpret_cast<uint32_t*>(dst), stream);
 }
 

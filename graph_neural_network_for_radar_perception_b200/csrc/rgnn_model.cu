@@ -330,7 +330,12 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if (E > 0 && tc_stack_supported(net.edge_enc)) {
+    bool emb_split_done = false;
+    if (E > 0 && !pl.enc_tc_bwd && pl.emb_hl != nullptr && edge_enc_f16_supported(net.edge_enc)) {
+        // inference: the fixed-shape encoder writes the pre-split rows of the message kernel directly (no fp32 embedding)
+        if ((rc = run_edge_enc_f16(net.edge_enc, edge_features, g.perm, E, pl.emb_hl, nullptr, stream))) return rc;
+        emb_split_done = true;
+    } else if (E > 0 && tc_stack_supported(net.edge_enc)) {
         if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream, pl.enc_tc_bwd ? &pl.enc_save : nullptr))) return rc;
     } else if (E > 0) {   // edge encoder, rows gathered into target-major order
         FwdBuilder b(E);
@@ -341,7 +346,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if (!b.ok) return RGNN_ERR_INVALID;
         if ((rc = launch_program(b.p, stream))) return rc;
     }
-    if (pl.emb_hl != nullptr && (rc = mp_f16_split_emb(pl.emb, E, pl.emb_hl, stream))) return rc;
+    if (pl.emb_hl != nullptr && !emb_split_done && (rc = mp_f16_split_emb(pl.emb, E, pl.emb_hl, stream))) return rc;
     for (int l = 0; l < L; ++l) {
         if ((rc = run_conv_edges(net.conv[l], g, pl.emb, pl.P[l], pl.agg[l], stream, pl.emb_hl))) return rc;
         if ((rc = run_conv_nodes(net.conv[l], N, pl.x[l], pl.agg[l], pl.x[l + 1], l + 1 < L ? &net.conv[l + 1] : nullptr,
@@ -413,6 +418,7 @@ extern "C" int rgnn_pack_detector(const rgnn_detector* net, void* stream) {
     Packer pk(static_cast<cudaStream_t>(stream));
     pk.stack(net->node_enc);
     pk.stack(net->edge_enc);
+    if (pk.rc == RGNN_OK) pk.rc = edge_enc_f16_pack(net->edge_enc, static_cast<cudaStream_t>(stream));
     for (int l = 0; l < net->n_conv; ++l) pk.conv(net->conv[l]);
     pk.stack(net->head_node);
     pk.stack(net->head_offset);

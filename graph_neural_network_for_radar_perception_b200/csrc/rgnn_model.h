@@ -85,6 +85,13 @@ int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, con
 int chain_f16_set_option(const char* name, int value);
 int chain_f16_get_option(const char* name);
 
+// fixed-shape edge encoder with fp16-split operands, rgnn_edge_enc_f16.cu
+bool edge_enc_f16_supported(const rgnn_stack& s);
+int edge_enc_f16_pack(const rgnn_stack& s, cudaStream_t stream);
+int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, int n_rows, uint32_t* emb_hl, float* emb, cudaStream_t stream);
+int edge_enc_f16_set_option(const char* name, int value);
+int edge_enc_f16_get_option(const char* name);
+
 // tensor-core backward of the message function (rgnn_mp_bwd_tc.cu) and the generic weight-gradient GEMM (rgnn_wgrad_tc.cu)
 bool mp_bwd_tc_supported(const ConvDims& d);
 size_t mp_bwd_tc_scratch_floats(const ConvDims& d, int n_edges);
