@@ -245,6 +245,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_local(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     def timed(fn, steps, tail=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,7 +283,27 @@ def run_gpu(args):
     with torch.no_grad():
         ms_fwd = timed(lambda: det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False), args.steps)
     ms_graph = timed(lambda: gf.build_graph_batch(pts_dev, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH), args.steps)
-    roof = measure_roofline(det, bf0, dev, args.steps)
+    hbm, tf, which = peaks()
+    roof, roof_extra = measure_roofline(det, bf0, dev, args.steps, hbm, tf)
+    # reduced-precision mode (single fp16 pass, fp32 accumulate): its own line, never the headline
+    reduced = None
+    if rank == 0:
+        with torch.no_grad():
+            ref_out = det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False)
+            _cabi.check(_cabi.lib().rgnn_set_option(b'f16_passes', 1), 'opt')
+            try:
+                ms_fwd_1p = timed_local(lambda: det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False), args.steps)
+                out_1p = det.forward_batch(bf0.gb, bf0.node_features, bf0.edge_features, training=False)
+            finally:
+                _cabi.check(_cabi.lib().rgnn_set_option(b'f16_passes', 3), 'opt')
+        rel = [float(((a - b).abs().max() / b.abs().max().clamp_min(1e-9)).item()) for a, b in zip(out_1p, ref_out)]
+        reduced = {'dtype': 'f16 operands (single pass), f32 accumulate', 'gnn_forward_ms': ms_fwd_1p / args.steps,
+                   'frames_per_s_gnn_fwd_only': args.frames / (ms_fwd_1p / args.steps / 1e3),
+                   'max_abs_err_over_max_abs_vs_fp32_path': dict(zip(('node_cls', 'node_off', 'link_cls', 'obj_cls'), rel)),
+                   'stated_tolerance': '5e-3 of each output tensor\'s largest magnitude (tests/test_model_gpu.py::test_reduced_precision_mode)',
+                   'scope': 'edge encoder, 7 message kernels, stems / heads run single-pass; node encoder, node update and the per-cluster head stay 3xTF32'}
+    c1 = measure_c1(det, model, dev) if rank == 0 else None
+    parity = parity_check(det, bf0, frames, fp, cl_lists, ref_out) if rank == 0 else None
     train = measure_train(dev, args, timed, rank, world) if not args.no_train else None
     clocks = sampler.stop() if rank == 0 else None
 
@@ -281,7 +311,6 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    hbm, tf, which = peaks()
     total_frames = args.frames * world
     per_step_s = ms_dev / args.steps / 1e3
     line = {
@@ -299,9 +328,15 @@ def run_gpu(args):
                 'd2h_bytes_per_step': int(sum(h.numel() * h.element_size() for h in out_host[0])),
                 'overlap': 'read-back of step i on a side stream under the compute of step i+1 (double-buffered pinned results)'},
         'gpu_launches': launches_per_step(det),
-        'roofline': dict(roof, peak=hbm, frac=roof['achieved'] / hbm, peak_source=which),
+        'roofline': dict(roof, peak_source=which),
         'clocks': clocks,
     }
+    line.update({k: dict(v, peak_source=which) for k, v in roof_extra.items()})
+    line['reduced_precision'] = reduced
+    line['c1_latency'] = c1
+    line['parity_max_err'] = parity[0]
+    line['parity'] = {'what': 'frame 0 of the bench batch, four outputs vs the float32 oracle; ratio to (1e-4 |want| + 1e-5 max|want|), <= 1 passes',
+                      'max_abs_err': parity[1]}
     if train:
         line['train'] = train
     if world == 1 and not args.no_cpu_baseline:
@@ -312,45 +347,50 @@ def run_gpu(args):
 
 
 def launches_per_step(det):
-    # kernels only (memsets excluded).  graph build: knn, sym_count, add, 3 scan, copy_last, sym_fill, sort, finalize
-    # (rows, 3 scan, und, copy_last), node feat, edge feat = 17; weight packing: 2 pack_kernel + 2 pack_split per conv
-    # block; model: node enc, edge enc, per conv block (tcgen05 edge kernel, node program), 6 head programs
+    # kernels only (memsets excluded), one device_step.  graph build: knn, sym_count, add, 3 scan, copy_last, sym_fill, sort,
+    # finalize (rows, 3 scan, und, copy_last), node feat, edge feat = 17; weight images are cached between steps (0);
+    # model: node encoder, edge encoder, per conv block (mp_edge_f16_kernel, node program), 6 stem / head kernels
     L = len(det.pass_messages.conv_blk)
-    return 17 + 2 + 2 * L + 2 + 2 * L + 6
+    return 17 + 2 + 2 * L + 6
 
 
 def _traffic_from_profile(n_edges, n_nodes):
-    """DRAM bytes per launch of mp_edge_tc_kernel from the committed `ncu --set full` capture (profiles/roofline_traffic.json:
+    """DRAM bytes per launch of the message kernel from the committed `ncu --set full` capture (profiles/roofline_traffic.json:
     dram__bytes_read.sum + dram__bytes_write.sum at a stated graph size), scaled linearly to this run's graph."""
     path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if not os.path.exists(path):
         return None
     t = json.load(open(path))
-    alg_here = 260.0 * n_edges + 1280.0 * n_nodes
-    alg_there = 260.0 * t['n_edges'] + 1280.0 * t['n_nodes']
+    alg_here = 260.0 * n_edges + 512.0 * n_nodes
+    alg_there = 260.0 * t['n_edges'] + 512.0 * t['n_nodes']
     return t['dram_bytes'] * alg_here / alg_there
 
 
-def measure_roofline(det, bf, dev, steps):
-    """Dominant kernel of the forward: mp_edge_tc_kernel (message function + aggregation of one conv block), timed alone on
-    its stream with CUDA events.  Algorithmic bytes of that kernel: 260 E (edge embedding row + target/source index) +
-    1280 N (hoisted projection rows read once, aggregated messages written once).  The whole layer (projection, edge kernel,
-    node update; SURVEY.md 8d: B_f = 512 N + 260 E) is reported beside it."""
+def measure_roofline(det, bf, dev, steps, hbm, tf):
+    """Roofline entries with SURVEY.md section 8(d)'s ALGORITHMIC figures (fp32 storage, int32 indices, weights counted once):
+      per conv layer forward   B_f = 512 N + 260 E bytes,  F_f = 65 536 E + 16 384 N FLOP   (message path alone: 65 536 E)
+      per conv layer backward  B_b = 768 N + 772 E bytes,  2 F_f FLOP (the recompute is not counted)
+      edge encoder             2 x 59 136 FLOP and 28 B in + 256 B out per edge
+    Every kernel is timed alone on its stream with CUDA events, through the C-ABI entry the detector itself calls.
+    In the fp32-parity mode the message kernel executes three fp16 MMAs per product, which puts the tensor pipe (0.67 ms for
+    9.4 M edges at the measured sustained peak) above the HBM floor (0.43 ms): `bound` says so; the HBM view is reported
+    beside it, and the single-pass mode (HBM-bound) has its own entry."""
     import ctypes as C
     from graph_neural_network_for_radar_perception_b200._engine import detector_table
     from graph_neural_network_for_radar_perception_b200._cabi import check, lib, ptr, stream_ptr
     gb = bf.gb
     table = detector_table(det)
     table.refill(None)
-    check(lib().rgnn_pack_detector(C.byref(table.det), stream_ptr()), 'pack')
+    table.ensure_packed(stream_ptr())
     N, E = gb.n_nodes, gb.n_edges
     x = torch.randn(N, 64, device=dev)
     e = torch.randn(E, 64, device=dev)
-    out = torch.empty_like(x)
-    agg = torch.empty_like(x)
-    proj = torch.empty(N, 256, device=dev)
+    es = torch.empty(E * 64, dtype=torch.int32, device=dev)
+    check(lib().rgnn_split_edge_embedding(ptr(e), E, ptr(es), stream_ptr()), 'split')
+    out, agg = torch.empty_like(x), torch.empty_like(x)
+    proj, proj2 = torch.randn(N, 256, device=dev), torch.empty(N, 256, device=dev)
     g = gb.c_struct()
-    conv = table.det.conv[0]
+    conv, conv_next = table.det.conv[0], table.det.conv[1]
     s = stream_ptr()
     reps = max(steps, 3)
 
@@ -366,60 +406,178 @@ def measure_roofline(det, bf, dev, steps):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms_layer = timed_ms(lambda: check(lib().rgnn_conv_block_fwd(C.byref(conv), C.byref(g), ptr(x), ptr(e), ptr(out), ptr(agg), ptr(proj), s), 'conv'))
-    # the edge kernel alone (its launch also zero-fills agg with a memset node, counted in its time)
-    ms_edge = timed_ms(lambda: check(lib().rgnn_conv_edges_fwd(C.byref(conv), C.byref(g), ptr(e), ptr(proj), ptr(agg), s), 'edges'))
-    bytes_edge = 260.0 * E + 1280.0 * N
-    bytes_layer = 512.0 * N + 260.0 * E
-    flops_alg = 65536.0 * E + 16384.0 * N
-    return {'kernel': 'mp_edge_tc_kernel (tcgen05 3xTF32: message function + segmented-sum aggregation of one conv block)',
-            'bound': 'hbm',
-            'achieved': bytes_edge / (ms_edge * 1e-3) / 1e9, 'unit': 'GB/s', 'traffic': _traffic_from_profile(E, N),
-            'ms_per_launch': ms_edge, 'algorithmic_bytes': bytes_edge,
-            'algorithmic_tflops': 65536.0 * E / (ms_edge * 1e-3) / 1e12,
-            'executed_tf32_tflops': 3 * 2 * 16384.0 * E / (ms_edge * 1e-3) / 1e12,
-            'note': 'fp32-parity mode executes 3 TF32 MMAs per product and is bound by the tensor pipe + CUDA-core epilogue, not by HBM',
-            'layer': {'ms': ms_layer, 'algorithmic_bytes': bytes_layer, 'achieved_GBps': bytes_layer / (ms_layer * 1e-3) / 1e9,
-                      'algorithmic_tflops': flops_alg / (ms_layer * 1e-3) / 1e12}}
+    L = lib()
+    edges = lambda: check(L.rgnn_conv_edges_f16_fwd(C.byref(conv), C.byref(g), ptr(es), ptr(proj), ptr(agg), s), 'edges')
+    layer = lambda: check(L.rgnn_conv_layer_f16_fwd(C.byref(conv), C.byref(conv_next), C.byref(g), ptr(x), ptr(es), ptr(proj), ptr(out),
+                                                    ptr(agg), ptr(proj2), s), 'layer')
+    ms_edge = timed_ms(edges)        # its launch also zero-fills agg with a memset node, counted in its time
+    ms_layer = timed_ms(layer)
+    check(L.rgnn_set_option(b'f16_passes', 1), 'opt')
+    try:
+        ms_edge_1p = timed_ms(edges)
+        ms_layer_1p = timed_ms(layer)
+    finally:
+        check(L.rgnn_set_option(b'f16_passes', 3), 'opt')
+    # edge encoder
+    ef = bf.edge_features
+    ms_enc = timed_ms(lambda: check(L.rgnn_edge_encoder_f16_fwd(C.byref(table.det.edge_enc), ptr(ef), ptr(gb.perm), E, ptr(es), None, s), 'enc'))
+    # message backward of one layer (dgrad kernel + the two weight-gradient GEMMs + the projection-gradient gather)
+    nb = L.rgnn_conv_msg_bwd_workspace_bytes(C.byref(conv), C.byref(g))
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    dagg, dproj, de = torch.randn(N, 64, device=dev) * 1e-3, torch.empty(N, 256, device=dev), torch.empty(E, 64, device=dev)
+    ms_bwd = timed_ms(lambda: check(L.rgnn_conv_msg_bwd(C.byref(conv), C.byref(g), ptr(e), ptr(proj), ptr(dagg), ptr(dproj), ptr(de),
+                                                        ptr(ws), nb, s), 'bwd'))
+    B_f, B_b = 512.0 * N + 260.0 * E, 768.0 * N + 772.0 * E
+    F_msg, F_f = 65536.0 * E, 65536.0 * E + 16384.0 * N
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
+    tfs = lambda f, ms: f / (ms * 1e-3) / 1e12
+    main = {'kernel': 'mp_edge_f16_kernel (tcgen05 kind::f16, fp16-split operands x 3 passes = fp32 parity: message function + '
+                      'segmented-sum aggregation of one conv block)',
+            'bound': 'tensor', 'achieved': tfs(F_msg, ms_edge), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(F_msg, ms_edge) / tf,
+            'traffic': _traffic_from_profile(E, N), 'ms_per_launch': ms_edge,
+            'algorithmic_flop': F_msg, 'executed_f16_tflops': tfs(3 * 2 * 16384.0 * E, ms_edge),
+            'hbm_view': {'algorithmic_bytes': B_f, 'kernel_GBps': gbs(B_f, ms_edge), 'kernel_frac_of_hbm': gbs(B_f, ms_edge) / hbm,
+                         'layer_ms': ms_layer, 'layer_GBps': gbs(B_f, ms_layer), 'layer_frac_of_hbm': gbs(B_f, ms_layer) / hbm,
+                         'layer_algorithmic_tflops': tfs(F_f, ms_layer)},
+            'note': 'three fp16 MMAs per product (fp32 parity) put the tensor floor above the HBM floor; the single-pass entry is HBM-bound'}
+    extra = {
+        'roofline_reduced': {'kernel': 'mp_edge_f16_kernel, single pass (fp16 operands, fp32 accumulate; rgnn_set_option f16_passes=1)',
+                             'bound': 'hbm', 'achieved': gbs(B_f, ms_edge_1p), 'peak': hbm, 'unit': 'GB/s', 'frac': gbs(B_f, ms_edge_1p) / hbm,
+                             'ms_per_launch': ms_edge_1p, 'layer_ms': ms_layer_1p, 'layer_frac': gbs(B_f, ms_layer_1p) / hbm, 'traffic': None},
+        'roofline_rowmlp': {'kernel': 'edge_enc_f16_kernel (graph_feature_encoding of the edges, 7-256-128-128-64)', 'bound': 'tensor',
+                            'achieved': tfs(2 * 59136.0 * E, ms_enc), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * 59136.0 * E, ms_enc) / tf,
+                            'ms_per_launch': ms_enc, 'algorithmic_bytes': 284.0 * E, 'traffic': None},
+        'roofline_bwd': {'kernel': 'message backward of one conv block: mp_edge_bwd_tc_kernel + 2 x wgrad_tma_kernel + dproj_gather_kernel (3xTF32)',
+                         'bound': 'tensor', 'achieved': tfs(2 * F_msg, ms_bwd), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * F_msg, ms_bwd) / tf,
+                         'ms': ms_bwd, 'hbm_view': {'algorithmic_bytes': B_b, 'GBps': gbs(B_b, ms_bwd), 'frac_of_hbm': gbs(B_b, ms_bwd) / hbm},
+                         'traffic': None},
+    }
+    return main, extra
+
+
+def measure_c1(det, model, dev):
+    """The reference's own calling convention (one frame at a time, modules/inference/output.py:88-94; lists of small frames
+    in Model_Training.forward): host + device latency in ms, median of 20 calls, everything a caller pays included
+    (int64 edge_index -> CSR, cluster lists, weight images cached).  C1 = BASELINE.json configs[0]'s frame shape."""
+    from graph_neural_network_for_radar_perception_b200 import graph_features as gf
+    out = {}
+
+    def lat(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        return float(np.median(ts))
+    # 1 frame x 1000 points through Model_Inference.forward(node_features, edge_features, edge_index, adj, clusters)
+    d, src = synth.make_frame(4242, 1000, knn=KNN)
+    pts, fp = gf.frames_to_device([d], dev)
+    bf = gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+    ei = bf.edge_index()
+    blob = src['blob_of']
+    cl = [torch.from_numpy(np.nonzero(blob == b)[0]).to(dev) for b in np.unique(blob[blob >= 0])] + \
+         [torch.tensor([i], device=dev) for i in np.nonzero(blob < 0)[0]]
+    with torch.no_grad():
+        out['inference_1_frame_1000_points_ms'] = lat(lambda: det(bf.node_features, bf.edge_features, ei, None, cl))
+        out['graph_build_1_frame_1000_points_ms'] = lat(lambda: gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH))
+    # 8 frames x 100 points through Model_Training.forward with per-frame lists (forward + losses; eval mode, no backward)
+    nf_l, ef_l, ei_l = [], [], []
+    labels = {k: [] for k in ('cluster_node_idx', 'cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
+    for i in range(8):
+        d, src = synth.make_frame(4300 + i, 100, knn=KNN)
+        p1, f1 = gf.frames_to_device([d], dev)
+        b1 = gf.build_graph_batch(p1, f1, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+        e1 = b1.edge_index()
+        lab = synth.make_labels(d, src, e1.cpu().numpy())
+        nf_l.append(b1.node_features); ef_l.append(b1.edge_features); ei_l.append(e1)
+        labels['cluster_node_idx'].append([torch.from_numpy(c).to(dev) for c in lab['cluster_node_idx']])
+        for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets'):
+            labels[k].append(torch.from_numpy(lab[k]).to(dev))
+    with torch.no_grad():
+        out['training_forward_8_frames_100_points_ms'] = lat(lambda: model(nf_l, ef_l, ei_l, [None] * 8, labels))
+    return out
+
+
+def parity_check(det, bf, frames, fp, cl_lists, outs):
+    """CHECKER (outside every timed region; the one place the product arm touches oracle/): the four outputs of frame 0 of the
+    bench batch against the float32 oracle of the reference.  Returns the largest |got - want| / (1e-4 |want| + 1e-5 max|want|)
+    (<= 1 means inside the tolerance of tests/test_model_gpu.py) and the raw maxima."""
+    from oracle import graph_np, model_torch
+    sd = torch.load(CKPT, map_location='cpu', weights_only=True)
+    d = frames[0][0]
+    adj = graph_np.adjacency_information(d, EPS2, KNN)
+    nf = torch.from_numpy(graph_np.node_features(d, adj['degree'], True, 0, GRID_MAX_R, 0, GRID_MAX_TH).astype(np.float32))
+    ef = torch.from_numpy(graph_np.edge_features(d, adj['adj_list']).astype(np.float32))
+    with torch.no_grad():
+        want = model_torch.detector_forward(sd, nf, ef, torch.from_numpy(adj['adj_list']), [c for c in cl_lists[0]])
+    n0, eu0, c0 = fp[1], adj['adj_list'].shape[1] // 2, len(cl_lists[0])
+    got = (outs[0][:n0], outs[1][:n0], outs[2][:eu0], outs[3][:c0])
+    worst, raw = 0.0, {}
+    for name, gt, w in zip(('node_cls', 'node_off', 'link_cls', 'obj_cls'), got, want):
+        w = w.numpy().astype(np.float64)
+        err = np.abs(gt.cpu().numpy().astype(np.float64) - w)
+        tol = 1e-4 * np.abs(w) + max(1e-5 * np.abs(w).max(), 2e-6)
+        worst = max(worst, float((err / tol).max()))
+        raw[name] = float(err.max())
+    return worst, raw
 
 
 def measure_train(dev, args, timed, rank, world):
-    """BASELINE.json configs[2]: full multi-task training step (forward, 4 losses, backward, gradient all-reduce
-    over NCCL when world > 1, fused SGD) on `--train-frames` frames per GPU (weak scaling)."""
+    """BASELINE.json configs[2] / [3]: full multi-task training step (forward, 4 losses, backward, ONE gradient all-reduce over
+    NCCL when world > 1 -- the counts are all-reduced on the stream, nothing is read back by the host -- fused SGD).
+    weak: `--train-frames` frames per GPU; strong (world > 1): the SAME global batch of `--train-frames` frames split over
+    the ranks."""
     from graph_neural_network_for_radar_perception_b200 import config, Model_Training
     from graph_neural_network_for_radar_perception_b200 import graph_features as gf
-    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
-    model = Model_Training(config(), dev)
-    model.load_state_dict(torch.load(CKPT, map_location='cpu', weights_only=True))
-    model = model.to(dev).train()
-    trainer = DataParallelTrainer(model)
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer, shard_range
+
+    def case(frames):
+        model = Model_Training(config(), dev)
+        model.load_state_dict(torch.load(CKPT, map_location='cpu', weights_only=True))
+        model = model.to(dev).train()
+        trainer = DataParallelTrainer(model)
+        pts, fp = gf.frames_to_device([f[0] for f in frames], dev)
+        bf = gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+        gb = bf.gb
+        # synthetic labels (synth.make_labels needs the edge list of each frame: take it from the GPU graph)
+        ei = bf.edge_index().cpu().numpy()
+        row_ptr = gb.row_ptr.cpu().numpy()
+        labs, cl_lists = [], []
+        for i, (d, src) in enumerate(frames):
+            e0, e1 = int(row_ptr[fp[i]]), int(row_ptr[fp[i + 1]])
+            lab = synth.make_labels(d, src, ei[:, e0:e1] - fp[i])
+            labs.append(lab)
+            cl_lists.append([torch.from_numpy(c) for c in lab['cluster_node_idx']])
+        gb.set_clusters(cl_lists, fp[:-1], dev)
+        labels = {k: torch.cat([torch.from_numpy(l[k]) for l in labs]).to(dev)
+                  for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
+        step = lambda: trainer.step(gb, bf.node_features, bf.edge_features, labels)
+        for _ in range(max(args.warmup, 3)):
+            step()
+        ms = timed(step, args.steps) / args.steps
+        loss, _ = step()
+        return ms, gb.n_edges, float(sum(v.item() for v in loss.values()))
+
     nfr = args.train_frames
-    frames = make_frames(nfr, args.points, seed0=5000 + 1000 * rank)
-    pts, fp = gf.frames_to_device([f[0] for f in frames], dev)
-    bf = gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
-    gb = bf.gb
-    # synthetic labels (synth.make_labels needs the edge list of each frame: take it from the GPU graph)
-    ei = bf.edge_index().cpu().numpy()
-    row_ptr = gb.row_ptr.cpu().numpy()
-    labs, cl_lists = [], []
-    for i, (d, src) in enumerate(frames):
-        e0, e1 = int(row_ptr[fp[i]]), int(row_ptr[fp[i + 1]])
-        lab = synth.make_labels(d, src, ei[:, e0:e1] - fp[i])
-        labs.append(lab)
-        cl_lists.append([torch.from_numpy(c) for c in lab['cluster_node_idx']])
-    gb.set_clusters(cl_lists, fp[:-1], dev)
-    labels = {k: torch.cat([torch.from_numpy(l[k]) for l in labs]).to(dev)
-              for k in ('cluster_labels', 'edge_class', 'node_class', 'node_offsets')}
-    step = lambda: trainer.step(gb, bf.node_features, bf.edge_features, labels)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    ms = timed(step, args.steps) / args.steps
-    loss, _ = step()
-    return {'metric': 'radar_frames_per_s_gnn_fwd_bwd', 'value': nfr * world / (ms * 1e-3), 'unit': 'frames/s',
-            'ms_per_step': ms, 'frames_per_gpu': nfr, 'edges_per_s': gb.n_edges * world / (ms * 1e-3),
-            'directed_edges_per_gpu': gb.n_edges, 'collective': 'nccl all-reduce of 463144 fp32 gradients + 3 counts' if world > 1 else 'none (1 GPU)',
-            'includes': 'forward + 4 losses + backward + SGD(momentum, weight decay) update; graph prebuilt',
-            'loss_after': float(sum(v.item() for v in loss.values()))}
+    ms, n_edges, loss = case(make_frames(nfr, args.points, seed0=5000 + 1000 * rank))
+    out = {'metric': 'radar_frames_per_s_gnn_fwd_bwd', 'value': nfr * world / (ms * 1e-3), 'unit': 'frames/s',
+           'ms_per_step': ms, 'frames_per_gpu': nfr, 'edges_per_s': n_edges * world / (ms * 1e-3),
+           'directed_edges_per_gpu': n_edges, 'scaling': 'weak',
+           'collective': 'nccl: all-reduce of 3 counts (on the stream) + ONE all-reduce of 463144 fp32 gradients with the NaN flag '
+                         'and the four loss shares behind them' if world > 1 else 'none (1 GPU)',
+           'includes': 'forward + 4 losses + backward + SGD(momentum, weight decay) update; graph prebuilt; no host read in the step',
+           'loss_after_global_batch': loss}
+    if world > 1:
+        allf = make_frames(nfr, args.points, seed0=5000)
+        mine = [allf[i] for i in shard_range(nfr, rank, world)]
+        ms_s, _, loss_s = case(mine)
+        out['strong'] = {'scaling': 'strong', 'global_frames': nfr, 'frames_per_gpu': len(mine), 'ms_per_step': ms_s,
+                         'value': nfr / (ms_s * 1e-3), 'unit': 'frames/s', 'loss_after_global_batch': loss_s}
+    return out
 
 
 def cpu_baseline(args):

@@ -253,6 +253,7 @@ int plan_detector(const rgnn_detector& net, const rgnn_graph& g, int training, v
     }
     RGNN_REQUIRE(stack_out(net.node_enc) == d.cn && stack_out(net.edge_enc) == d.ce, "encoder widths do not match conv");
     pl->d = d;
+    pl->training = training != 0;
     pl->link_w = stack_out(net.link_node);
     pl->cls_w = stack_out(net.class_node);
     RGNN_REQUIRE(stack_in(net.head_link) == pl->link_w && stack_in(net.head_class) == pl->cls_w &&
@@ -332,8 +333,9 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     }
     bool emb_split_done = false;
     if (E > 0 && !pl.enc_tc_bwd && pl.emb_hl != nullptr && edge_enc_f16_supported(net.edge_enc)) {
-        // inference: the fixed-shape encoder writes the pre-split rows of the message kernel directly (no fp32 embedding)
-        if ((rc = run_edge_enc_f16(net.edge_enc, edge_features, g.perm, E, pl.emb_hl, nullptr, stream))) return rc;
+        // the fixed-shape encoder writes the pre-split rows of the message kernel directly; the fp32 embedding is written as well
+        // only when a backward will read it (a training step whose backward recomputes the encoder on the CUDA cores)
+        if ((rc = run_edge_enc_f16(net.edge_enc, edge_features, g.perm, E, pl.emb_hl, pl.training ? pl.emb : nullptr, stream))) return rc;
         emb_split_done = true;
     } else if (E > 0 && tc_stack_supported(net.edge_enc)) {
         if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream, pl.enc_tc_bwd ? &pl.enc_save : nullptr))) return rc;
@@ -457,6 +459,45 @@ extern "C" int rgnn_conv_edges_f16_fwd(const rgnn_conv* blk, const rgnn_graph* g
     if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
     RGNN_REQUIRE(mp_f16_supported(d), "conv_edges_f16: channel plan %d / %d / %d is not instantiated (64 / 64 / 128)", d.cn, d.ce, d.h);
     return run_conv_edges(*blk, *g, nullptr, proj, agg, static_cast<cudaStream_t>(stream), static_cast<const uint32_t*>(e_split));
+}
+
+extern "C" int rgnn_edge_encoder_f16_fwd(const rgnn_stack* enc, const float* edge_features, const int32_t* perm, int n_edges,
+                                         void* e_split, float* e_f32, void* stream) {
+    RGNN_REQUIRE(edge_enc_f16_supported(*enc), "edge_encoder_f16: only the reference plan (<= 7 -> 256 -> 128 -> 128 -> 64) is instantiated");
+    return run_edge_enc_f16(*enc, edge_features, perm, n_edges, static_cast<uint32_t*>(e_split), e_f32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rgnn_conv_layer_f16_fwd(const rgnn_conv* blk, const rgnn_conv* next, const rgnn_graph* g, const float* x,
+                                       const void* e_split, const float* proj, float* out, float* agg, float* proj_next, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(mp_f16_supported(d), "conv_layer_f16: channel plan %d / %d / %d is not instantiated (64 / 64 / 128)", d.cn, d.ce, d.h);
+    int rc = run_conv_edges(*blk, *g, nullptr, proj, agg, s, static_cast<const uint32_t*>(e_split));
+    if (rc) return rc;
+    return run_conv_nodes(*blk, g->n_nodes, x, agg, out, next, next != nullptr ? proj_next : nullptr, s);
+}
+
+extern "C" size_t rgnn_conv_msg_bwd_workspace_bytes(const rgnn_conv* blk, const rgnn_graph* g) {
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return 0;
+    return align256(mp_bwd_tc_scratch_floats(d, g->n_edges) * sizeof(float)) + align256(src_index_ints(g->n_nodes, g->n_edges) * sizeof(int));
+}
+
+extern "C" int rgnn_conv_msg_bwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, const float* dagg,
+                                 float* dproj, float* de, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(mp_bwd_tc_supported(d), "conv_msg_bwd: channel plan %d / %d / %d is not instantiated (64 / 64 / 128)", d.cn, d.ce, d.h);
+    RGNN_REQUIRE(workspace_bytes >= rgnn_conv_msg_bwd_workspace_bytes(blk, g), "conv_msg_bwd: workspace too small");
+    float* scratch = static_cast<float*>(workspace);
+    int* sidx = reinterpret_cast<int*>(static_cast<char*>(workspace) + align256(mp_bwd_tc_scratch_floats(d, g->n_edges) * sizeof(float)));
+    const int* sptr = nullptr;
+    const int* slist = nullptr;
+    int rc = build_src_index(*g, sidx, &sptr, &slist, s);
+    if (rc) return rc;
+    return run_conv_edges_bwd_tc(*blk, d, *g, e, proj, dagg, dproj, de, true, scratch, sptr, slist, s);
 }
 
 extern "C" size_t rgnn_detector_workspace_bytes(const rgnn_detector* net, const rgnn_graph* g, int training) {

@@ -17,6 +17,7 @@ struct TcSave {
 // Where everything lives inside the caller-provided detector workspace.
 struct DetPlan {
     ConvDims d;
+    bool training;
     int link_w, cls_w;
     float* x[RGNN_MAX_CONV + 1];   // node embeddings entering conv l (x[L] feeds the heads)
     float* P[RGNN_MAX_CONV];       // per-node projections of msg.0: [x W1_target^T | x W1_source^T]

@@ -193,12 +193,16 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             // sweep 2 (this group's chunks g and g + 2): y1 x 16 = act(k (z - mean) + sh) -> fp16 hi | lo, IN PLACE: the 32 fp32
             // columns [c, c + 32) become 16 packed hi columns [c, c + 16) and 16 packed lo columns [c + 16, c + 32) (the MMA
             // warp addresses the K steps of GEMM2 accordingly)
+            long long q0 = 0, q1 = 0, q2 = 0;
 #pragma unroll 1
             for (int c = 32 * g; c < H; c += 64) {
                 float2 v[16];
+                long long ta = 0;
+                if (PROFILE) ta = clock64();
                 tc::tmem_ld16(d1 + c, v);
                 tc::tmem_ld16(d1 + c + 16, v + 8);
                 tc::tmem_wait_ld();
+                if (PROFILE) { const long long tb = clock64(); q0 += tb - ta; ta = tb; }
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -210,8 +214,15 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                     }
                     f16::split(y, hi[i], lo[i]);
                 }
+                if (PROFILE) { const long long tb = clock64(); q1 += tb - ta; ta = tb; }
                 f16::tmem_st16u(d1 + c, hi);
                 if (np != 1) f16::tmem_st16u(d1 + c + 16, lo);
+                if (PROFILE) { tc::tmem_wait_st(); const long long tb = clock64(); q2 += tb - ta; }
+            }
+            if (PROFILE && lane == 0 && a.prof != nullptr && warp == 0) {
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 0], (unsigned long long)q0);
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 1], (unsigned long long)q1);
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 2], (unsigned long long)q2);
             }
             tc::tmem_wait_st();
             tc::tc_fence_before();
@@ -658,8 +669,8 @@ int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& 
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
         long long* h = new long long[n];
         RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * n, cudaMemcpyDeviceToHost));
-        static const char* role[20] = {"E1a", "", "", "", "E1b", "", "", "", "E2", "", "", "", "F", "", "", "", "MMA idle", "", "", ""};
-        for (int w = 0; w < 20; w += 4) {
+        static const char* role[20] = {"E1a", "", "", "", "E1b", "", "", "", "E2", "", "", "", "F", "", "", "", "MMA idle", "E1a sweep2: ld+wait | math | st+wait", "", ""};
+        for (int w = 0; w < 20; w += (w == 16 ? 1 : (w == 17 ? 3 : 4))) {
             double tot[4] = {0, 0, 0, 0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 4; ++i) tot[i] += (double)h[((size_t)b * 20 + w) * 4 + i];
             fprintf(stderr, "[mp_edge_f16 profile] %s warp %d cycles per tile: p0=%.0f p1=%.0f p2=%.0f\n", role[w], w, tot[0] / n_tiles,

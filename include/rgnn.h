@@ -203,6 +203,22 @@ int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* 
 int rgnn_split_edge_embedding(const float* e, int n_edges, void* e_split, void* stream);
 int rgnn_conv_edges_f16_fwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj, float* agg,
                             void* stream);
+/* graph_feature_encoding of the edges (reference plan <= 7 -> 256 -> 128 -> 128 -> 64) as ONE fixed-shape fp16-split kernel
+ * (csrc/rgnn_edge_enc_f16.cu): row k of the output is the embedding of feature row perm[k] (perm nullable), written in the
+ * pre-split format above (e_split) and optionally also as fp32 (e_f32, nullable). */
+int rgnn_edge_encoder_f16_fwd(const rgnn_stack* enc, const float* edge_features, const int32_t* perm, int n_edges, void* e_split,
+                              float* e_f32, void* stream);
+/* One whole layer as the detector forward runs it: message function + aggregation on the split rows, then the node update
+ * out = x + upd(cat(x, agg)) and -- when `next` is given -- the hoisted projection of the next block into proj_next. */
+int rgnn_conv_layer_f16_fwd(const rgnn_conv* blk, const rgnn_conv* next, const rgnn_graph* g, const float* x, const void* e_split,
+                            const float* proj, float* out, float* agg, float* proj_next, void* stream);
+/* Backward of the message function + aggregation of one block (autograd of gnn_blocks.py:106-113): given d(agg) it
+ * recomputes the edge activations and produces d(proj) (N, 2h), d(e) (E, ce, overwritten) and -- through the grad_* fields
+ * of blk->msg -- the weight / bias / norm-scalar gradients of msg.0 (edge columns) and msg.1 (accumulated).
+ * e is the fp32 edge embedding (target-major).  Used by rgnn_detector_bwd; exported for measurement and tests. */
+size_t rgnn_conv_msg_bwd_workspace_bytes(const rgnn_conv* blk, const rgnn_graph* g);
+int rgnn_conv_msg_bwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, const float* dagg,
+                      float* dproj, float* de, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Model_Inference.forward with cluster_node_idx given (gnn_detector.py:141-162).
  * edge_features rows are in the caller's order (g->perm maps them).  Outputs: node_cls (N,7), node_off (N,2),
