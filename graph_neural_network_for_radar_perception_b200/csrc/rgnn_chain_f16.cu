@@ -365,3 +365,310 @@ int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, con
 }
 
 }  // namespace rgnn
+
+// =====================================================================================================================
+// Node update of residual_graph_conv_block (reference gnn_blocks.py:96-111) + the hoisted projection of the NEXT block:
+//   out = x + ffn_block(128 -> 64)(cat(x, agg))                          (identity residual, reference plan)
+//   P_next = [out W_t^T + b | out W_s^T]   (N, 256), W_t / W_s = node columns of the next block's msg.0
+// Same structure as chain64_f16_kernel with TWO tiles in flight (256 TMEM columns per group: X = 128 columns for the
+// cat(x, agg) operand and later the two projection halves, Y = 64 columns for the update accumulator / `out` operand).
+// HBM-bound: 512 B read + 256 B + 1 KB written per node.
+// =====================================================================================================================
+namespace rgnn {
+
+struct ConvNodesArgs {
+    int n_rows;
+    const float* x;             // (N, 64)
+    const float* agg;           // (N, 64)
+    const uint32_t* w_upd;      // [hi | lo] image K = 128, N = 64
+    const float* b_upd; const float* s_upd; const float* m_upd;
+    int act;
+    float* out;                 // (N, 64)
+    int has_next;
+    const uint32_t* w_pt;       // next block: target half, [hi | lo] image K = 64, N = 128
+    const uint32_t* w_ps;       // source half
+    const float* b_p;           // msg.0 bias of the next block (rides on the target half) or nullptr
+    float* P;                   // (N, 256)
+    int passes;
+};
+
+namespace cnn {
+constexpr int TM = 128, NGROUPS = 2;
+constexpr int NTHREADS = 128 * NGROUPS + 128;
+constexpr int WU_WORDS = 128 * 64;          // hi + lo of the update layer (32 KB)
+constexpr int WP_WORDS = 64 * 128;          // hi + lo of one projection half (32 KB)
+constexpr int OFF_WU = 0, OFF_WPT = OFF_WU + WU_WORDS, OFF_WPS = OFF_WPT + WP_WORDS;
+constexpr int OFF_CST = OFF_WPS + WP_WORDS;             // b_upd[64] | gain | shift | pad | b_p[128]
+constexpr int OFF_BAR = OFF_CST + 64 + 8 + 128;
+constexpr int OFF_SLOT = OFF_BAR + 2 * 2 * NGROUPS;
+constexpr int WORDS = OFF_SLOT + 2;
+constexpr size_t SMEM = (size_t)WORDS * 4;
+static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+}  // namespace cnn
+
+__global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const __grid_constant__ ConvNodesArgs a) {
+    using namespace cnn;
+    extern __shared__ __align__(1024) uint32_t smem_u[];
+    float* cst = reinterpret_cast<float*>(smem_u) + OFF_CST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_u + OFF_BAR);
+    uint64_t* a_full = bars;
+    uint64_t* d_full = bars + NGROUPS;
+    uint32_t* slot = smem_u + OFF_SLOT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = warp >> 2, w4 = warp & 3, row = tid & 127;
+    const int G = (int)gridDim.x;
+    const int n_tiles = (a.n_rows + TM - 1) / TM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int np = a.passes == 1 ? 1 : 3;
+    {
+        auto copy = [&](uint32_t* dst, const uint32_t* src, int words) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (int i = tid; i < words / 4; i += NTHREADS) d4[i] = __ldg(s4 + i);
+        };
+        copy(smem_u + OFF_WU, a.w_upd, WU_WORDS);
+        if (a.has_next) {
+            copy(smem_u + OFF_WPT, a.w_pt, WP_WORDS);
+            copy(smem_u + OFF_WPS, a.w_ps, WP_WORDS);
+        }
+        for (int i = tid; i < 64 + 8 + 128; i += NTHREADS) {
+            float v = 0.f;
+            if (i < 64) v = a.b_upd ? __ldg(a.b_upd + i) : 0.f;
+            else if (i == 64) v = a.s_upd ? __ldg(a.s_upd) : 1.f;
+            else if (i == 65) v = a.m_upd ? __ldg(a.m_upd) : 0.f;
+            else if (i >= 72) v = (a.has_next && a.b_p) ? __ldg(a.b_p + (i - 72)) : 0.f;
+            cst[i] = v;
+        }
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NGROUPS; ++i) { tc::mbar_init(&a_full[i], 4); tc::mbar_init(&d_full[i], 1); }
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(slot, 512);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *slot;
+    const int n_mma = a.has_next ? 3 : 1;
+
+    if (g < NGROUPS) {
+        const uint32_t xr = tmem + ((uint32_t)w4 << 21) + (uint32_t)g * 256, yr = xr + 128;
+        uint32_t uses = 0;
+        const float2 s16 = make_float2(f16::A_SCALE, f16::A_SCALE), us = make_float2(f16::D_UNSCALE, f16::D_UNSCALE);
+        for (int j = g; j < my_tiles; j += NGROUPS) {
+            const int tile = (int)blockIdx.x + j * G;
+            const int r = tile * TM + row;
+            const bool valid = r < a.n_rows;
+            const size_t rr = valid ? (size_t)r : 0;
+            // ---- cat(x, agg) -> A operand (x 16, hi | lo per 32 columns) ----
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                const float* p = (c < 64 ? a.x + rr * 64 + c : a.agg + rr * 64 + (c - 64));
+                float2 v[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ldg256(p + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f16::split(valid ? __fmul2_rn(v[i], s16) : make_float2(0.f, 0.f), hi[i], lo[i]);
+                f16::tmem_st16u(xr + c, hi);
+                if (np != 1) f16::tmem_st16u(xr + c + 16, lo);
+            }
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            warp_arrive(&a_full[g], lane);
+            // ---- update layer epilogue: norm, act, + x, store, next operand ----
+            float2 xa[16], xb[16];          // the residual row, requested before the wait
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ldg256(a.x + rr * 64 + 8 * i, xa[4 * i], xa[4 * i + 1], xa[4 * i + 2], xa[4 * i + 3]);
+                ldg256(a.x + rr * 64 + 32 + 8 * i, xb[4 * i], xb[4 * i + 1], xb[4 * i + 2], xb[4 * i + 3]);
+            }
+            tc::mbar_wait(&d_full[g], uses & 1u);
+            ++uses;
+            tc::tc_fence_after();
+            float2 va[16], vb[16];
+            tc::tmem_ld16(yr, va);
+            tc::tmem_ld16(yr + 16, va + 8);
+            tc::tmem_ld16(yr + 32, vb);
+            tc::tmem_ld16(yr + 48, vb + 8);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                va[c] = __ffma2_rn(va[c], us, *reinterpret_cast<const float2*>(cst + 2 * c));
+                vb[c] = __ffma2_rn(vb[c], us, *reinterpret_cast<const float2*>(cst + 32 + 2 * c));
+            }
+            float k = 1.f, sh = 0.f, mean = 0.f;
+            if (a.s_upd != nullptr) {
+                RowStats st;
+                st.init();
+                st.add_chunk(va);
+                st.add_chunk(vb);
+                k = cst[64] * __frcp_rn(st.sigma(64) + NORM_EPS);
+                sh = cst[65];
+                mean = st.mean;
+            }
+            const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean, -mean);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                va[c] = __ffma2_rn(__fadd2_rn(va[c], nm), k2, sh2);
+                vb[c] = __ffma2_rn(__fadd2_rn(vb[c], nm), k2, sh2);
+                if (a.act) {
+                    const float2 ta = __fmul2_rn(va[c], sl), tb = __fmul2_rn(vb[c], sl);
+                    va[c].x = fmaxf(va[c].x, ta.x); va[c].y = fmaxf(va[c].y, ta.y);
+                    vb[c].x = fmaxf(vb[c].x, tb.x); vb[c].y = fmaxf(vb[c].y, tb.y);
+                }
+                va[c] = __fadd2_rn(va[c], xa[c]);       // identity residual
+                vb[c] = __fadd2_rn(vb[c], xb[c]);
+            }
+            if (valid) {
+                float* o = a.out + (size_t)r * 64;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    stg256(o + 8 * i, va[4 * i], va[4 * i + 1], va[4 * i + 2], va[4 * i + 3]);
+                    stg256(o + 32 + 8 * i, vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
+                }
+            }
+            if (a.has_next) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f16::split(__fmul2_rn(va[i], s16), hi[i], lo[i]);
+                f16::tmem_st16u(yr, hi);
+                if (np != 1) f16::tmem_st16u(yr + 16, lo);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f16::split(__fmul2_rn(vb[i], s16), hi[i], lo[i]);
+                f16::tmem_st16u(yr + 32, hi);
+                if (np != 1) f16::tmem_st16u(yr + 48, lo);
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                warp_arrive(&a_full[g], lane);
+                // ---- the two projection halves, 128 columns each, through the X region ----
+                for (int half = 0; half < 2; ++half) {
+                    tc::mbar_wait(&d_full[g], uses & 1u);
+                    ++uses;
+                    tc::tc_fence_after();
+                    float* o = a.P + (size_t)rr * 256 + half * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 128; c += 32) {
+                        float2 v[16];
+                        tc::tmem_ld16(xr + c, v);
+                        tc::tmem_ld16(xr + c + 16, v + 8);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            v[i] = half == 0 ? __ffma2_rn(v[i], us, *reinterpret_cast<const float2*>(cst + 72 + c + 2 * i)) : __fmul2_rn(v[i], us);
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) stg256(o + c + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        }
+                    }
+                    if (half == 0) {        // the X region has been read: the source half may overwrite it
+                        tc::tc_fence_before();
+                        warp_arrive(&a_full[g], lane);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+        }
+    } else if (warp == 4 * NGROUPS) {
+        if (lane == 0) {
+            constexpr uint32_t ID64 = f16::idesc(TM, 64), ID128 = f16::idesc(TM, 128);
+            const uint32_t sWU = tc::smem_u32(smem_u + OFF_WU), sWPT = tc::smem_u32(smem_u + OFF_WPT), sWPS = tc::smem_u32(smem_u + OFF_WPS);
+            int tile_j[NGROUPS], step[NGROUPS];
+            uint32_t uses[NGROUPS];
+            int remaining = 0;
+            for (int i = 0; i < NGROUPS; ++i) {
+                tile_j[i] = i; step[i] = 0; uses[i] = 0;
+                if (i < my_tiles) ++remaining;
+            }
+            auto gemm_ts = [&](uint32_t dcol, uint32_t acol, uint32_t sB, int K, int N, uint32_t idesc_) {
+                const uint32_t lbo = (uint32_t)N * 16, img = (uint32_t)K * N * 2;
+                bool acc = false;
+                for (int p = 0; p < np; ++p) {
+                    const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                    const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                    const uint64_t bd0 = tc::smem_desc(sB + pb * img, lbo, 128);
+                    for (int ks = 0; ks < K / 16; ++ks) {
+                        f16::mma_ts(dcol, acol + (ks >> 1) * 32 + (ks & 1) * 8 + (pa ? 16u : 0u), bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc_, acc);
+                        acc = true;
+                    }
+                }
+            };
+            while (remaining > 0) {
+                bool did = false;
+#pragma unroll
+                for (int i = 0; i < NGROUPS; ++i) {
+                    if (tile_j[i] >= my_tiles) continue;
+                    if (!f16::mbar_test(&a_full[i], uses[i] & 1u)) continue;
+                    tc::tc_fence_after();
+                    const uint32_t xr = tmem + (uint32_t)i * 256, yr = xr + 128;
+                    if (step[i] == 0) gemm_ts(yr, xr, sWU, 128, 64, ID64);            // update layer: Y = cat(x, agg) W_upd^T
+                    else if (step[i] == 1) gemm_ts(xr, yr, sWPT, 64, 128, ID128);      // target half of the projection
+                    else gemm_ts(xr, yr, sWPS, 64, 128, ID128);                        // source half
+                    tc::mma_commit(&d_full[i]);
+                    ++uses[i];
+                    if (++step[i] == n_mma) {
+                        step[i] = 0;
+                        tile_j[i] += NGROUPS;
+                        if (tile_j[i] >= my_tiles) --remaining;
+                    }
+                    did = true;
+                }
+                if (!did) __nanosleep(20);
+            }
+        }
+        __syncwarp();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// images of the hoisted projection of a block (node columns of msg.0): target half | source half, each K = 64 x N = 128 [hi | lo]
+size_t conv_proj_f16_floats(const ConvDims& d) { return (d.cn == 64 && d.h == 128) ? (size_t)2 * cnn::WP_WORDS : 0; }
+
+int conv_proj_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream) {
+    if (conv_proj_f16_floats(d) == 0) return RGNN_OK;
+    const rgnn_linear& m0 = c.msg.layer[0];
+    uint32_t* w = reinterpret_cast<uint32_t*>(dst);
+    int rc = pack_f16_image(m0.weight, m0.in_features, d.cn, d.h, d.h, d.cn, w, stream);
+    if (rc) return rc;
+    return pack_f16_image(m0.weight + d.cn, m0.in_features, d.cn, d.h, d.h, d.cn, w + cnn::WP_WORDS, stream);
+}
+
+bool conv_nodes_f16_supported(const rgnn_conv& c, const ConvDims& d) {
+    const rgnn_linear& L = c.upd.layer[0];
+    return g_chain_f16 && c.upd.n == 1 && d.cn == 64 && d.h == 128 && L.in_features == 128 && L.out_features == 64 && L.weight_t != nullptr;
+}
+
+int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
+                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream) {
+    if (n_nodes <= 0) return RGNN_OK;
+    (void)d;
+    const rgnn_linear& L = c.upd.layer[0];
+    ConvNodesArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = n_nodes; a.x = x; a.agg = agg;
+    a.w_upd = reinterpret_cast<const uint32_t*>(f16_weights(L));
+    a.b_upd = L.bias; a.s_upd = L.norm_scale; a.m_upd = L.norm_shift; a.act = L.activation;
+    a.out = out;
+    a.has_next = next != nullptr;
+    if (next != nullptr) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(next_proj_images);
+        a.w_pt = w; a.w_ps = w + cnn::WP_WORDS;
+        a.b_p = next->msg.layer[0].bias;
+        a.P = P_next;
+    }
+    a.passes = mp_f16_passes();
+    static PerDeviceOnce once;
+    if (once.needed()) {
+        RGNN_CHECK_CUDA(cudaFuncSetAttribute(conv_nodes_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn::SMEM));
+        once.mark();
+    }
+    const int n_tiles = (n_nodes + cnn::TM - 1) / cnn::TM;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    conv_nodes_f16_kernel<<<grid, cnn::NTHREADS, cnn::SMEM, stream>>>(a);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+}  // namespace rgnn

@@ -88,6 +88,7 @@ struct Packer {
             int r = mp_tc_pack(c, d, wp + conv_msg0_tc_offset(d), stream);
             if (r == RGNN_OK) r = tc_pack_projection(c, d, stream);
             if (r == RGNN_OK) r = mp_f16_pack(c, d, wp + conv_msg0_f16_offset(d), stream);
+            if (r == RGNN_OK) r = conv_proj_f16_pack(c, d, wp + conv_msg0_proj16_offset(d), stream);
             if (r != RGNN_OK) rc = r;
         }
     }
@@ -214,6 +215,15 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
                    const rgnn_conv* next, float* P_next, cudaStream_t stream, float* u_save = nullptr, float* sd_save = nullptr) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
+    if (u_save == nullptr && sd_save == nullptr && conv_nodes_f16_supported(c, d)) {       // inference: fixed-shape fp16-split kernel
+        if (next != nullptr) {
+            ConvDims dn;
+            if (!conv_dims(*next, &dn)) return RGNN_ERR_INVALID;
+            RGNN_REQUIRE(dn.cn == d.cn && dn.h == d.h && dn.ce == d.ce, "conv blocks with different channel plans");
+        }
+        return run_conv_nodes_f16(c, d, n_nodes, x, agg, out, next,
+                                  next != nullptr ? next->msg.layer[0].weight_t + conv_msg0_proj16_offset(d) : nullptr, P_next, stream);
+    }
     if (tc_stack_supported(c.upd) && c.upd.n == 1 && (next == nullptr || tc_proj_supported(d))) {
         if (next != nullptr) {
             ConvDims dn;
@@ -534,5 +544,5 @@ extern "C" int rgnn_detector_obj_head(const rgnn_detector* net, const rgnn_graph
 
 extern "C" size_t rgnn_packed_conv_msg0_floats(int node_channels, int edge_channels, int hidden) {
     ConvDims d{node_channels, edge_channels, hidden};
-    return conv_msg0_f16_offset(d) + mp_f16_pack_floats(d);
+    return conv_msg0_proj16_offset(d) + conv_proj_f16_floats(d);
 }

@@ -83,6 +83,12 @@ size_t f16_image_floats(int in_features, int out_features);
 int f16_pack_linear(const rgnn_linear& L, float* dst, cudaStream_t stream);
 bool chain64_supported(const rgnn_stack& s);
 int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream);
+size_t conv_proj_f16_floats(const ConvDims& d);
+int conv_proj_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
+bool conv_nodes_f16_supported(const rgnn_conv& c, const ConvDims& d);
+int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
+                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream);
+inline size_t conv_msg0_proj16_offset(const ConvDims& d);
 int chain_f16_set_option(const char* name, int value);
 int chain_f16_get_option(const char* name);
 
@@ -115,6 +121,7 @@ size_t tc_proj_pack_floats(const ConvDims& d);
 int tc_pack_linear(const rgnn_linear& L, cudaStream_t stream);
 int tc_pack_projection(const rgnn_conv& c, const ConvDims& d, cudaStream_t stream);
 inline size_t conv_msg0_f16_offset(const ConvDims& d) { return conv_msg0_tc_offset(d) + mp_tc_pack_floats(d) + tc_proj_pack_floats(d); }
+inline size_t conv_msg0_proj16_offset(const ConvDims& d) { return conv_msg0_f16_offset(d) + mp_f16_pack_floats(d); }
 int tc_run_stack(const rgnn_stack& s, const float* x, const int* ridx, int n_rows, float* y, cudaStream_t stream,
                  const TcSave* save = nullptr);
 bool tc_stack_bwd_supported(const rgnn_stack& s);

@@ -32,7 +32,8 @@ def test_pure_host_size_queries():
     assert lib.rgnn_packed_weight_floats(7, 256) == 8 * 256 + 2 * 8 * 256 + 16 * 256       # + fp16 image pair, K zero padded to 16
     assert lib.rgnn_packed_weight_floats(64, 7) == 64 * 64 + 2 * 64 * 32 + 2 * 8 * 64 + 64 * 16      # + transposed image (backward) + fp16 image pair
     assert lib.rgnn_packed_conv_msg0_floats(64, 64, 128) == 64 * 256 + 64 * 128 + 256 * 64 + 256 + 2 * (2 * 64 * 128 + 2 * 128 * 64) + 2 * 64 * 256 + 2 * (2 * 128 * 64) \
-        + (2 * 64 * 128 + 2 * 128 * 64) // 2          # fp16 hi / lo images of W_e and W_2 (rgnn_mp_f16.cu)
+        + (2 * 64 * 128 + 2 * 128 * 64) // 2 \
+        + 2 * 64 * 128         # fp16 hi / lo images of W_e and W_2 (rgnn_mp_f16.cu) and of the two projection halves
     assert lib.rgnn_packed_conv_msg0_floats(32, 32, 64) == 32 * 128 + 32 * 64 + 128 * 64 + 128
     assert lib.rgnn_graph_build_workspace_bytes(1000, 1, 10) > 1000 * 11 * 4
 
