@@ -7,7 +7,7 @@ UditBhaskar19/GRAPH_NEURAL_NETWORK_FOR_RADAR_PERCEPTION behind the reference's P
 All arithmetic runs in csrc/librgnn.so (C-ABI in include/rgnn.h); there is no CPU fallback.
 """
 from .config import config                                                   # noqa: F401
-from .gnn_detector import (Model_Inference, Model_Training,                 # noqa: F401
+from .gnn_detector import (Model_Inference, Model_Inference_v1, Model_Training,     # noqa: F401
                            Model_Object_Classifier_Finetuning, compute_accuracy)
 
-__all__ = ['config', 'Model_Inference', 'Model_Training', 'Model_Object_Classifier_Finetuning', 'compute_accuracy']
+__all__ = ['config', 'Model_Inference', 'Model_Inference_v1', 'Model_Training', 'Model_Object_Classifier_Finetuning', 'compute_accuracy']

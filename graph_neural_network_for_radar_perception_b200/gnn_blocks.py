@@ -192,7 +192,12 @@ class node_offset_predictions(nn.Module):
 
 def _undirected_pairs(adj_matrix: torch.Tensor):
     """nonzero(triu(adj,1)) in row-major order (reference :295-296) -- API-compatibility path on a dense
-    matrix; the detector-level forward derives the same list from edge_index instead."""
+    matrix; the detector-level forward derives the same list from edge_index instead.  A (2, E) int64 `edge_index`
+    (reference convention, source-sorted) is accepted in place of the dense matrix: its columns with source < target ARE
+    that list, in the same order."""
+    if adj_matrix.dtype == torch.int64 and adj_matrix.dim() == 2 and adj_matrix.shape[0] == 2:
+        und = adj_matrix[0] < adj_matrix[1]
+        return adj_matrix[0][und], adj_matrix[1][und]
     r, c = torch.nonzero(torch.triu(adj_matrix, diagonal=1), as_tuple=True)
     return r, c
 

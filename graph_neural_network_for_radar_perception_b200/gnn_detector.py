@@ -22,7 +22,7 @@ from ._engine import GraphBatch, run_detector
 from .clustering import Simple_DBSCAN
 from .compute_offsets import normalize_gt_offsets, unnormalize_gt_offsets
 from .gnn_blocks import (graph_convolution, graph_feature_encoding, link_predictions, node_offset_predictions,
-                         node_segmentation, object_classification)
+                         node_predictions, node_segmentation, object_classification)
 from .loss import Loss_Graph, Loss_Object_Class
 
 
@@ -115,6 +115,47 @@ class Model_Inference(nn.Module):
             node_cls, node_off, link_cls, obj_cls = run_detector(self, gb, node_features, edge_features)
         if self.extract_proposals:
             return node_cls, node_off, link_cls, obj_cls, cluster_members_list
+        return node_cls, node_off, link_cls, obj_cls
+
+
+class Model_Inference_v1(nn.Module):
+    """The reference's variant with ONE stem for the node-class and offset heads (`node_predictions`; reference
+    gnn_detector.py:204-312).  Composed from the block-level modules, each of which runs its fused kernel (inference forward;
+    the reference ships no checkpoint or training loop for this variant).  `adj_matrix` may be the dense (N, N) bool matrix
+    of the reference or None, in which case the undirected links are taken from `edge_index`."""
+
+    def __init__(self, net_config):
+        super().__init__()
+        c = net_config
+        common = dict(activation=c.activation, norm_layer=c.norm_layer, num_groups=c.num_groups)
+        conv_out = c.graph_convolution_stem_channels[-1]
+        self.encode_node_feat = graph_feature_encoding(in_channels=c.input_node_feat_dim,
+                                                       stem_channels=c.node_feat_enc_stem_channels, **common)
+        self.encode_edge_feat = graph_feature_encoding(in_channels=c.input_edge_feat_dim,
+                                                       stem_channels=c.edge_feat_enc_stem_channels, **common)
+        self.pass_messages = graph_convolution(in_node_channels=c.node_feat_enc_stem_channels[-1],
+                                               in_edge_channels=c.edge_feat_enc_stem_channels[-1],
+                                               stem_channels=c.graph_convolution_stem_channels,
+                                               msg_mlp_hidden_dim=c.msg_mlp_hidden_dim,
+                                               aggregation=c.aggregation, **common)
+        self.predict_node = node_predictions(in_channels=conv_out, stem_channels=c.node_pred_stem_channels,
+                                             num_classes=c.num_classes, reg_offset_dim=c.reg_offset_dim, **common)
+        self.predict_link = link_predictions(in_channels=conv_out, num_blks_for_edges=c.num_blocks_to_compute_edge,
+                                             stem_channels=c.link_pred_stem_channels, num_classes=c.num_edge_classes, **common)
+        self.predict_class = object_classification(in_channels=conv_out, stem_channels=c.node_pred_stem_channels,
+                                                   num_classes=c.num_classes, **common)
+
+    def forward(self, node_features: torch.Tensor, edge_features: torch.Tensor, edge_index: torch.Tensor,
+                adj_matrix: Optional[torch.Tensor], cluster_node_idx: List[torch.Tensor],
+                augmented_features: Optional[torch.Tensor] = None):
+        if augmented_features is not None:
+            raise NotImplementedError('augmented_features are not used by the reference model')
+        x = self.encode_node_feat(node_features)
+        e = self.encode_edge_feat(edge_features)
+        x = self.pass_messages(x, e, edge_index)
+        node_cls, node_off = self.predict_node(x)
+        link_cls = self.predict_link(x, adj_matrix if adj_matrix is not None else edge_index)
+        obj_cls = self.predict_class(x, cluster_node_idx)
         return node_cls, node_off, link_cls, obj_cls
 
 
