@@ -507,6 +507,14 @@ extern "C" int rgnn_conv_msg_bwd(const rgnn_conv* blk, const rgnn_graph* g, cons
     const int* slist = nullptr;
     int rc = build_src_index(*g, sidx, &sptr, &slist, s);
     if (rc) return rc;
+    if (g->n_edges > 0 && mp_bwd_f16_supported(d)) {       // fused fp16-split kernel on pre-split rows (stream-ordered temporary)
+        uint32_t* tmp = nullptr;
+        RGNN_CHECK_CUDA(cudaMallocAsync(&tmp, mp_f16_emb_words(g->n_edges) * sizeof(uint32_t), s));
+        rc = mp_f16_split_emb(e, g->n_edges, tmp, s);
+        if (rc == RGNN_OK) rc = run_conv_edges_bwd_f16(*blk, d, *g, tmp, proj, dagg, dproj, de, true, scratch, sptr, slist, s);
+        cudaFreeAsync(tmp, s);
+        return rc;
+    }
     return run_conv_edges_bwd_tc(*blk, d, *g, e, proj, dagg, dproj, de, true, scratch, sptr, slist, s);
 }
 

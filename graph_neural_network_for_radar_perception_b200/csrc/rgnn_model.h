@@ -105,6 +105,13 @@ size_t mp_bwd_tc_scratch_floats(const ConvDims& d, int n_edges);
 int run_conv_edges_bwd_tc(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const float* emb, const float* P,
                           const float* dagg, float* dP, float* demb, bool first_demb, float* scratch, const int* sptr,
                           const int* slist, cudaStream_t stream);
+// fused fp16-split backward of the message function (rgnn_mp_bwd_f16.cu): dgrad + both weight gradients in one kernel
+bool mp_bwd_f16_supported(const ConvDims& d);
+int run_conv_edges_bwd_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& g, const uint32_t* emb_hl, const float* P,
+                           const float* dagg, float* dP, float* demb, bool first_demb, float* scratch, const int* sptr,
+                           const int* slist, cudaStream_t stream);
+int mp_bwd_f16_set_option(const char* name, int value);
+int mp_bwd_f16_get_option(const char* name);
 // source-major index of the target-major edge list (edge positions grouped by source node), built once per backward call
 size_t src_index_ints(int n_nodes, int n_edges);
 int build_src_index(const rgnn_graph& g, int* ws, const int** sptr_out, const int** slist_out, cudaStream_t stream);

@@ -300,7 +300,9 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
                                 has_next ? pl.x[l + 1] : nullptr, has_next ? pl.dP : nullptr, pl.dx, pl.dagg, stream);
         }
         if (rc) return rc;
-        if (tc_edges && net.conv[l].msg.n == 2)
+        if (tc_edges && net.conv[l].msg.n == 2 && pl.emb_hl != nullptr && mp_bwd_f16_supported(d))
+            rc = run_conv_edges_bwd_f16(net.conv[l], d, g, pl.emb_hl, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, pl.escr, sptr, slist, stream);
+        else if (tc_edges && net.conv[l].msg.n == 2)
             rc = run_conv_edges_bwd_tc(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, pl.escr, sptr, slist, stream);
         else
             rc = conv_edges_bwd(net.conv[l], d, g, pl.emb, pl.P[l], pl.dagg, pl.dP, pl.demb, l == L - 1, stream);
