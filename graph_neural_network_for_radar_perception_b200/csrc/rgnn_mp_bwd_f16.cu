@@ -63,7 +63,7 @@ struct MpBwdF16Args {
     int act1, act2;
     int demb_accumulate;
     int passes;
-    long long* prof;        // PROFILE builds: [grid][12] cycle counters of worker thread 0
+    long long* prof;        // PROFILE builds: [grid][24] cycle counters: worker thread 0 [0,12), F thread 0 [12,18), MMA lane [18,24)
 };
 
 namespace mbf {
@@ -77,19 +77,21 @@ constexpr int OFF_Y = OFF_W + 2 * W1_WORDS + 2 * W2_WORDS;
 constexpr int Z_WORDS = TM * CN / 2;                         // dz2: 16 KB
 constexpr int OFF_Z = OFF_Y + 2 * Y_WORDS;
 constexpr int E_WORDS = TM * NE / 2;                         // emb (+ ones): 20 KB
-constexpr int OFF_E = OFF_Z + 2 * Z_WORDS;
+constexpr int STAGE_PITCH = CE + 4;                          // words per row of the d(emb) staging tile that shares the dz2 image's region (+ 2 KB)
+static_assert(TM * STAGE_PITCH <= 2 * Z_WORDS + 512, "staging tile");
+constexpr int OFF_E = OFF_Z + 2 * Z_WORDS + 512;
 constexpr int OFF_XCH = OFF_E + 2 * E_WORDS;                 // [2 phases][TM][2 q] float2
 constexpr int OFF_BIAS = OFF_XCH + 2 * TM * 2 * 2;
 constexpr int OFF_RED = OFF_BIAS + CN;                       // 4 x 8 doubles
 constexpr int OFF_BAR = OFF_RED + 64;                        // 10 mbarriers
-constexpr int OFF_SLOT = OFF_BAR + 2 * 10;
+constexpr int OFF_SLOT = OFF_BAR + 2 * 16;
 constexpr int WORDS = OFF_SLOT + 2;
 constexpr size_t SMEM = (size_t)WORDS * 4;
 static_assert((OFF_BAR % 2) == 0 && (OFF_RED % 2) == 0 && (OFF_XCH % 2) == 0 && (OFF_Y % 4) == 0 && (OFF_Z % 4) == 0 && (OFF_E % 4) == 0,
               "alignment");
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t COL_R1 = 0, COL_X0 = 128, COL_R3 = 192, COL_ACC2 = 256, COL_ACCE = 320, COL_X1 = 400;
-enum { B_A_FULL = 0, B_D1_FULL, B_Y1_FULL, B_D2_FULL, B_Z2_FULL, B_D3_FULL, B_W2_DONE, B_Z1_FULL, B_D4_FULL, B_WE_DONE };
+enum { B_A_FULL = 0, B_D1_FULL, B_Y1_FULL, B_D2_FULL, B_Z2_FULL, B_D3_FULL, B_W2_DONE, B_Z1_FULL, B_D4_FULL, B_WE_DONE, B_D4_READ, B_STAGE_FREE, B_YIMG_READ };
 constexpr int REG_W = 152, REG_F = 168, REG_AUX = 40;
 static_assert(NW * REG_W + 128 * REG_F + 128 * REG_AUX <= 65536, "setmaxnreg pool");
 __host__ __device__ constexpr uint32_t idesc_mn(int M, int N, int a_mn, int b_mn) {
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
     uint4* yimg = reinterpret_cast<uint4*>(smem_u + OFF_Y);          // [hi | lo][H/8][TM] 16-byte chunks
     uint4* zimg = reinterpret_cast<uint4*>(smem_u + OFF_Z);          // [hi | lo][CN/8][TM]
     uint4* eimg = reinterpret_cast<uint4*>(smem_u + OFF_E);          // [hi | lo][NE/8][TM]
+    float* stage = smem_f + OFF_Z;                                   // [TM][STAGE_PITCH] fp32, alias of the dz2 image (E4)
     float2* xch = reinterpret_cast<float2*>(smem_u + OFF_XCH);
     float* bias_s = smem_f + OFF_BIAS;
     double* red = reinterpret_cast<double*>(smem_u + OFF_RED);
@@ -159,6 +162,9 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
         tc::mbar_init(&bars[B_Z1_FULL], 8);
         tc::mbar_init(&bars[B_D4_FULL], 1);
         tc::mbar_init(&bars[B_WE_DONE], 1);
+        tc::mbar_init(&bars[B_D4_READ], 4);
+        tc::mbar_init(&bars[B_STAGE_FREE], 4);
+        tc::mbar_init(&bars[B_YIMG_READ], 3);
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(slot, 512);
@@ -209,55 +215,63 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
             const uint32_t xcol = t_row + ((j & 1) ? COL_X1 : COL_X0);
             const uint32_t r1 = t_row + COL_R1, r3 = t_row + COL_R3;
             const int t_my = valid ? __ldg(a.tgt + e_my) : 0;
+            float2 g2[16];          // own 32 columns of d(message) = dagg[target]: requested now, used in E2
+            {
+                const float* dg = a.dagg + (size_t)t_my * CN + 32 * q;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    g2[4 * c8] = g2[4 * c8 + 1] = g2[4 * c8 + 2] = g2[4 * c8 + 3] = make_float2(0.f, 0.f);
+                    if (valid) ldg256(dg + 8 * c8, g2[4 * c8], g2[4 * c8 + 1], g2[4 * c8 + 2], g2[4 * c8 + 3]);
+                }
+            }
 
             // ---------------- E1: z1 (x 4096) -> statistics -> y1 = act(norm(z1)) -> fp16 hi | lo: tensor memory + image ----------------
             tc::mbar_wait(&bars[B_D1_FULL], ph);
             tc::tc_fence_after();
             tick(0);
             float k1, sh1, mean1, sd1 = 0.f;
-            if (norm1) {
+            // the statistics sweep visits the PARTNER's two 32-column chunks first and this thread's own two last, so that the own
+            // chunks are still in registers (va, vb) when the row's mean and sigma are known: no second read of D1
+            float2 va[16], vb[16];
+            {
+                const int co = 64 * (q ^ 1), cm = 64 * q;
                 RowStats st;
                 st.init();
-                float2 va[16], vb[16];
-                tc::tmem_ld16(r1, va);
-                tc::tmem_ld16(r1 + 16, va + 8);
+                tc::tmem_ld16(r1 + co, va);
+                tc::tmem_ld16(r1 + co + 16, va + 8);
+                tc::tmem_ld16(r1 + co + 32, vb);
+                tc::tmem_ld16(r1 + co + 48, vb + 8);
                 tc::tmem_wait_ld();
-#pragma unroll 1
-                for (int c = 0; c < H; c += 64) {
-                    tc::tmem_ld16(r1 + c + 32, vb);
-                    tc::tmem_ld16(r1 + c + 48, vb + 8);
+                if (norm1) { st.add_chunk(va); st.add_chunk(vb); }
+                tc::tmem_ld16(r1 + cm, va);
+                tc::tmem_ld16(r1 + cm + 16, va + 8);
+                tc::tmem_ld16(r1 + cm + 32, vb);
+                tc::tmem_ld16(r1 + cm + 48, vb + 8);
+                tc::tmem_wait_ld();
+                if (norm1) {
                     st.add_chunk(va);
-                    tc::tmem_wait_ld();
-                    if (c + 64 < H) {
-                        tc::tmem_ld16(r1 + c + 64, va);
-                        tc::tmem_ld16(r1 + c + 80, va + 8);
-                    }
                     st.add_chunk(vb);
-                    tc::tmem_wait_ld();
+                    const float sds = st.sigma(H);
+                    k1 = f16::A_SCALE * s1v * __frcp_rn(sds + eps_s);
+                    sh1 = f16::A_SCALE * m1v;
+                    mean1 = st.mean;
+                    sd1 = sds * f16::D_UNSCALE;
+                } else {
+                    k1 = f16::A_SCALE * f16::D_UNSCALE;
+                    sh1 = 0.f;
+                    mean1 = 0.f;
                 }
-                const float sds = st.sigma(H);
-                k1 = f16::A_SCALE * s1v * __frcp_rn(sds + eps_s);
-                sh1 = f16::A_SCALE * m1v;
-                mean1 = st.mean;
-                sd1 = sds * f16::D_UNSCALE;
-            } else {
-                k1 = f16::A_SCALE * f16::D_UNSCALE;
-                sh1 = 0.f;
-                mean1 = 0.f;
             }
             tc::tc_fence_before();
             group_sync(bar_id, 64);            // the row partner has read every column: in-place stores may begin
             tc::tc_fence_after();
-            if (j > 0) tc::mbar_wait(&bars[B_WE_DONE], ph ^ 1u);      // the previous tile's dWe MMAs have read the y1/dz1 and emb images
+            if (j > 0) {
+                tc::mbar_wait(&bars[B_WE_DONE], ph ^ 1u);      // the previous tile's dWe MMAs have read the y1/dz1 and emb images
+                tc::mbar_wait(&bars[B_YIMG_READ], ph ^ 1u);    // and the copy warps have written its dz1 rows out
+            }
             {
                 const float2 k2 = make_float2(k1, k1), sh2 = make_float2(sh1, sh1), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean1, -mean1);
-#pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = 64 * q + 32 * cc;
-                    float2 v[16];
-                    tc::tmem_ld16(r1 + c, v);
-                    tc::tmem_ld16(r1 + c + 16, v + 8);
-                    tc::tmem_wait_ld();
+                auto emit = [&](float2 (&v)[16], int c) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -269,16 +283,15 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                         }
                         f16::split(y, hi[i], lo[i]);
                     }
-                    f16::tmem_st16u(r1 + c, hi);
-                    f16::tmem_st16u(r1 + c + 16, lo);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         yimg[(c / 8 + k) * TM + row] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
                         yimg[YI + (c / 8 + k) * TM + row] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
                     }
-                }
+                };
+                emit(va, 64 * q);
+                emit(vb, 64 * q + 32);
             }
-            tc::tmem_wait_st();
             tc::tc_fence_before();
             tc::fence_async_smem();
             warp_arrive(&bars[B_Y1_FULL], lane);
@@ -299,15 +312,6 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
 #pragma unroll
                 for (int k = 0; k < 8; ++k) eimg[q * EI + k * TM + row] = make_uint4(ev[4 * k], ev[4 * k + 1], ev[4 * k + 2], ev[4 * k + 3]);
             }
-            float2 g2[16];          // own 32 columns of d(message)
-            {
-                const float* dg = a.dagg + (size_t)t_my * CN + 32 * q;
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    g2[4 * c8] = g2[4 * c8 + 1] = g2[4 * c8 + 2] = g2[4 * c8 + 3] = make_float2(0.f, 0.f);
-                    if (valid) ldg256(dg + 8 * c8, g2[4 * c8], g2[4 * c8 + 1], g2[4 * c8 + 2], g2[4 * c8 + 3]);
-                }
-            }
 
             // ---------------- E2: statistics and mask of z2; dz2 = norm'(act'(d message)), x S -> hi | lo: tensor memory + image ----------------
             tc::mbar_wait(&bars[B_D2_FULL], ph);
@@ -316,34 +320,33 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
             {
                 float mean2 = 0.f, sd2 = 0.f, inv_den = 1.f;
                 const float2 us = make_float2(f16::D_UNSCALE, f16::D_UNSCALE);
-                if (norm2) {
-                    float2 va[16], vb[16];
-                    tc::tmem_ld16(r3, va);
-                    tc::tmem_ld16(r3 + 16, va + 8);
-                    tc::tmem_ld16(r3 + 32, vb);
-                    tc::tmem_ld16(r3 + 48, vb + 8);
+                float2 c2[16];          // own 32 columns of z2 (centred)
+                {
+                    float2 vo[16];      // the partner's 32 columns (statistics only)
+                    const int co = 32 * (q ^ 1), cm = 32 * q;
+                    tc::tmem_ld16(r3 + co, vo);
+                    tc::tmem_ld16(r3 + co + 16, vo + 8);
+                    tc::tmem_ld16(r3 + cm, c2);
+                    tc::tmem_ld16(r3 + cm + 16, c2 + 8);
                     tc::tmem_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        va[c] = __ffma2_rn(va[c], us, *reinterpret_cast<const float2*>(bias_s + 2 * c));
-                        vb[c] = __ffma2_rn(vb[c], us, *reinterpret_cast<const float2*>(bias_s + 32 + 2 * c));
+                        vo[c] = __ffma2_rn(vo[c], us, *reinterpret_cast<const float2*>(bias_s + co + 2 * c));
+                        c2[c] = __ffma2_rn(c2[c], us, *reinterpret_cast<const float2*>(bias_s + cm + 2 * c));
                     }
-                    RowStats st;
-                    st.init();
-                    st.add_chunk(va);
-                    st.add_chunk(vb);
-                    mean2 = st.mean;
-                    sd2 = st.sigma(CN);
-                    inv_den = 1.f / (sd2 + NORM_EPS);
+                    if (norm2) {
+                        RowStats st;
+                        st.init();
+                        st.add_chunk(vo);
+                        st.add_chunk(c2);
+                        mean2 = st.mean;
+                        sd2 = st.sigma(CN);
+                        inv_den = 1.f / (sd2 + NORM_EPS);
+                    }
                 }
-                float2 c2[16];          // own 32 columns of z2 (centred)
-                tc::tmem_ld16(r3 + 32 * q, c2);
-                tc::tmem_ld16(r3 + 32 * q + 16, c2 + 8);
-                tc::tmem_wait_ld();
                 const float2 nm = make_float2(-mean2, -mean2);
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    c2[c] = __fadd2_rn(__ffma2_rn(c2[c], us, *reinterpret_cast<const float2*>(bias_s + 32 * q + 2 * c)), nm);
+                for (int c = 0; c < 16; ++c) c2[c] = __fadd2_rn(c2[c], nm);
                 const float k = s2v * inv_den;
                 const float2 k2 = make_float2(k, k), m22 = make_float2(m2v, m2v), id2 = make_float2(inv_den, inv_den);
                 const float2 s22 = make_float2(s2v, s2v);
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                 }
                 f16::tmem_st16u(xcol + 16 * q, hi);
                 f16::tmem_st16u(xcol + 32 + 16 * q, lo);
+                if (j > 0) tc::mbar_wait(&bars[B_STAGE_FREE], ph ^ 1u);       // E4 of the previous tile has drained its staging tile (same region)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     zimg[(4 * q + k) * TM + row] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
@@ -411,12 +415,14 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                 const float2 s12 = make_float2(s1v, s1v);
                 const float2 ua = make_float2(1.f / f16::A_SCALE, 1.f / f16::A_SCALE), uw = make_float2(1.f / f16::W_SCALE, 1.f / f16::W_SCALE);
                 float2 ps2 = make_float2(0.f, 0.f), pm2 = ps2, sum2 = ps2, dot2 = ps2;
+                tc::tmem_ld16(r1 + 64 * q, dn);
+                tc::tmem_ld16(r1 + 64 * q + 16, dn + 8);
+                tc::tmem_ld16(r1 + 64 * q + 32, dn + 16);
+                tc::tmem_ld16(r1 + 64 * q + 48, dn + 24);
+                tc::tmem_wait_ld();
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int c = 64 * q + 32 * cc;
-                    tc::tmem_ld16(r1 + c, dn + 16 * cc);
-                    tc::tmem_ld16(r1 + c + 16, dn + 16 * cc + 8);
-                    tc::tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint4 yh = yimg[(c / 8 + k) * TM + row], yl = yimg[YI + (c / 8 + k) * TM + row];
@@ -453,7 +459,6 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                 tc::mbar_wait(&bars[B_W2_DONE], ph);        // the dW2 MMAs have read the y1 image: dz1 may replace it
                 tick(6);
                 const float2 nm2 = make_float2(-mean_dn, -mean_dn), id2 = make_float2(inv_den, inv_den), nc2 = make_float2(-coef, -coef);
-                const float2 iS2 = make_float2(inv_S, inv_S);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int c = 64 * q + 32 * cc;
@@ -474,58 +479,22 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                             f16::split(g, hi[4 * k + i], lo[4 * k + i]);
                         }
                     }
-                    f16::tmem_st16u(r1 + c, hi);
-                    f16::tmem_st16u(r1 + c + 16, lo);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         yimg[(c / 8 + k) * TM + row] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
                         yimg[YI + (c / 8 + k) * TM + row] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
                     }
                 }
-                tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::fence_async_smem();
                 warp_arrive(&bars[B_Z1_FULL], lane);
-                if (valid) {
-                    float* o = a.dz1_out + (size_t)e_my * H + 64 * q;
-#pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8)
-                        stg256(o + 8 * c8, __fmul2_rn(dn[4 * c8], iS2), __fmul2_rn(dn[4 * c8 + 1], iS2), __fmul2_rn(dn[4 * c8 + 2], iS2),
-                               __fmul2_rn(dn[4 * c8 + 3], iS2));
-                }
+                tick(8);
+                // (the fp32 copy of dz1 for dproj_gather_kernel is written by the copy warps from the dz1 image)
             }
-            tick(7);
-
-            // ---------------- E4: d(emb) (+)= D4 / (256 S) ----------------
-            float2 de[16];
-            if (a.demb_accumulate && valid) {
-                const float* o = a.demb + (size_t)e_my * CE + 32 * q;
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) ldg256(o + 8 * c8, de[4 * c8], de[4 * c8 + 1], de[4 * c8 + 2], de[4 * c8 + 3]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) de[c] = make_float2(0.f, 0.f);
-            }
-            tc::mbar_wait(&bars[B_D4_FULL], ph);
-            tc::tc_fence_after();
-            tick(8);
-            {
-                float2 d[16];
-                tc::tmem_ld16(r3 + 32 * q, d);
-                tc::tmem_ld16(r3 + 32 * q + 16, d + 8);
-                tc::tmem_wait_ld();
-                const float u = inv_S * (1.f / f16::W_SCALE);
-                const float2 u2 = make_float2(u, u);
-                if (valid) {
-                    float* o = a.demb + (size_t)e_my * CE + 32 * q;
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8)
-                        stg256(o + 8 * c8, __ffma2_rn(d[4 * c8], u2, de[4 * c8]), __ffma2_rn(d[4 * c8 + 1], u2, de[4 * c8 + 1]),
-                               __ffma2_rn(d[4 * c8 + 2], u2, de[4 * c8 + 2]), __ffma2_rn(d[4 * c8 + 3], u2, de[4 * c8 + 3]));
-                }
-            }
-            tc::tc_fence_before();
             tick(9);
+
+            // (E4, d(emb) (+)= D4, runs in the F role: global read-modify-write off the workers' chain)
+            tc::tc_fence_before();
         }
 
         // ---------------- flush: weight-gradient accumulators, bias gradients, norm-scalar gradients ----------------
@@ -564,7 +533,7 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
             if (a.gb2 != nullptr) atomicAdd(a.gb2 + 32 * q + lane, acc_b2 * inv_S);
         }
         if (PROFILE && tid == 0 && a.prof != nullptr)
-            for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 12 + i] = pt[i];
+            for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 24 + i] = pt[i];
         {
             double v[4] = {acc_s1 * (double)inv_S, acc_m1 * (double)inv_S, acc_s2, acc_m2};
 #pragma unroll
@@ -585,6 +554,49 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
         // =========================== F: emb operand and accumulator pre-load, one tile ahead ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_F));
         const float2 sc = make_float2(f16::D_SCALE, f16::D_SCALE);
+        long long ft[6] = {0, 0, 0, 0, 0, 0}, fl = 0;
+        auto ftick = [&](int i) {
+            if (PROFILE && tid == NW) { const long long n = clock64(); ft[i] += n - fl; fl = n; }
+        };
+        if (PROFILE) fl = clock64();
+        // E4 of tile jj: d(emb) (+)= D4 / (256 S), this thread's whole row (D4_FULL of tile jj has been observed by the caller);
+        // the arrive tells the MMA lane that R3 may be overwritten by G2 of the next tile
+        auto e4 = [&](int jj) {
+            const int e = ((int)blockIdx.x + jj * G) * TM + row;
+            const bool valid = e < a.n_edges;
+            float2 d[32];
+            tc::tmem_ld16(t_row + COL_R3, d);
+            tc::tmem_ld16(t_row + COL_R3 + 16, d + 8);
+            tc::tmem_ld16(t_row + COL_R3 + 32, d + 16);
+            tc::tmem_ld16(t_row + COL_R3 + 48, d + 24);
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            warp_arrive(&bars[B_D4_READ], lane);
+            // the row goes through a staging tile in shared memory (the dz2 image's region: its last reader, the dW2 MMAs of this
+            // tile, completed before D4_FULL) and from there to global memory with ONE bulk reduce-add per row: no global load,
+            // no per-thread sector stores on the load/store pipe
+            const float u = inv_S * (1.f / f16::W_SCALE);
+            const float2 u2 = make_float2(u, u);
+            float* st = stage + row * STAGE_PITCH;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float2 v0 = __fmul2_rn(d[2 * c4], u2), v1 = __fmul2_rn(d[2 * c4 + 1], u2);
+                *reinterpret_cast<float4*>(st + 4 * c4) = make_float4(v0.x, v0.y, v1.x, v1.y);
+            }
+            tc::fence_async_smem();
+            if (valid) {
+                float* o = a.demb + (size_t)e * CE;
+                if (a.demb_accumulate)
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(o), "r"(tc::smem_u32(st)), "n"(CE * 4) : "memory");
+                else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(o), "r"(tc::smem_u32(st)), "n"(CE * 4) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            warp_arrive(&bars[B_STAGE_FREE], lane);
+        };
         for (int j = 0; j < my_tiles; ++j) {
             const int tile = (int)blockIdx.x + j * G;
             const int e = tile * TM + row;
@@ -622,19 +634,65 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                     pre[4 * i + 3] = valid ? __fmul2_rn(__fadd2_rn(pre[4 * i + 3], p3), sc) : make_float2(0.f, 0.f);
                 }
             }
-            if (j > 0) {        // R1 is free once G4 of the previous tile has read dz1 out of it
-                tc::mbar_wait(&bars[B_D4_FULL], (uint32_t)(j - 1) & 1u);
+            ftick(0);           // loads issued and consumed
+            if (j > 0) {        // R1 is free once the workers' E3 of the previous tile has read D3 out of it (y1 / dz1 reach the MMAs as images)
+                tc::mbar_wait(&bars[B_Z1_FULL], (uint32_t)(j - 1) & 1u);
                 tc::tc_fence_after();
             }
+            ftick(1);           // idle: waiting for the workers
 #pragma unroll
             for (int c = 0; c < 8; ++c) tc::tmem_st16(t_row + COL_R1 + 16 * c, pre + 8 * c);
             tc::tmem_wait_st();
             tc::tc_fence_before();
             warp_arrive(&bars[B_A_FULL], lane);
+            ftick(2);           // pre-load stored
+            if (j > 0) {
+                tc::mbar_wait(&bars[B_D4_FULL], (uint32_t)(j - 1) & 1u);
+                tc::tc_fence_after();
+                ftick(3);       // rest of G4
+                e4(j - 1);
+                ftick(4);       // E4
+            }
         }
+        if (PROFILE && tid == NW && a.prof != nullptr)
+            for (int i = 0; i < 6; ++i) a.prof[blockIdx.x * 24 + 12 + i] = ft[i];
+        if (my_tiles > 0) {
+            tc::mbar_wait(&bars[B_D4_FULL], (uint32_t)(my_tiles - 1) & 1u);
+            tc::tc_fence_after();
+            e4(my_tiles - 1);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_AUX));
-        if (warp == (NW + 128) / 32 && lane == 0) {
+        if (warp > (NW + 128) / 32) {
+            // =========================== copy warps: dz1 image -> fp32 rows of the scratch buffer (input of dproj_gather_kernel) ===========================
+            // lane = edge row of a 32-row group: 16-byte reads of consecutive rows are conflict free; every lane writes the eight
+            // channels of a chunk as one 32-byte sector.  Off the workers' chain: the stores only have to leave before E1 of the
+            // next tile overwrites the image.
+            const int cw = warp - (NW + 128) / 32 - 1;      // 0..2; row groups: 0 -> {0, 3}, 1 -> {1}, 2 -> {2}
+            const float2 iS2 = make_float2(inv_S, inv_S);
+            for (int j = 0; j < my_tiles; ++j) {
+                const int tile = (int)blockIdx.x + j * G;
+                tc::mbar_wait(&bars[B_Z1_FULL], (uint32_t)j & 1u);
+                for (int grp = cw; grp < 4; grp += 3) {
+                    const int r = 32 * grp + lane;
+                    const long long e = (long long)tile * TM + r;
+                    if (e < a.n_edges) {
+                        float* o = a.dz1_out + (size_t)e * H;
+#pragma unroll 4
+                        for (int c8 = 0; c8 < H / 8; ++c8) {
+                            const uint4 yh = yimg[c8 * TM + r], yl = yimg[YI + c8 * TM + r];
+                            const float2 v0 = __fmul2_rn(__fadd2_rn(f16::unpack(yh.x), f16::unpack(yl.x)), iS2);
+                            const float2 v1 = __fmul2_rn(__fadd2_rn(f16::unpack(yh.y), f16::unpack(yl.y)), iS2);
+                            const float2 v2 = __fmul2_rn(__fadd2_rn(f16::unpack(yh.z), f16::unpack(yl.z)), iS2);
+                            const float2 v3 = __fmul2_rn(__fadd2_rn(f16::unpack(yh.w), f16::unpack(yl.w)), iS2);
+                            stg256(o + 8 * c8, v0, v1, v2, v3);
+                        }
+                    }
+                }
+                warp_arrive(&bars[B_YIMG_READ], lane);
+            }
+        } else if (warp == (NW + 128) / 32 && lane == 0) {
             // =========================== MMA issue ===========================
             constexpr uint32_t ID_G1 = f16::idesc(TM, H), ID_G2 = f16::idesc(TM, CN);
             constexpr uint32_t ID_G3 = idesc_mn(TM, H, 0, 1), ID_G4 = idesc_mn(TM, CE, 0, 1);
@@ -642,39 +700,54 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
             const uint32_t sWe = tc::smem_u32(wsm), sW2 = tc::smem_u32(wsm + 2 * W1_WORDS);
             const uint32_t sY = tc::smem_u32(yimg), sZ = tc::smem_u32(zimg), sE = tc::smem_u32(eimg);
             bool wacc = false;
-            for (int j = 0; j < my_tiles; ++j) {
-                const uint32_t ph = (uint32_t)j & 1u;
-                const uint32_t xcol = tmem + ((j & 1) ? COL_X1 : COL_X0);
-                // ---- G1: R1 += emb W_e^T ----
-                tc::mbar_wait(&bars[B_A_FULL], ph);
+            long long mt[6] = {0, 0, 0, 0, 0, 0};
+            auto mwait = [&](int slot_i, uint64_t* bar, uint32_t par) {
+                if (PROFILE) {
+                    const long long t0 = clock64();
+                    tc::mbar_wait(bar, par);
+                    mt[slot_i] += clock64() - t0;
+                } else {
+                    tc::mbar_wait(bar, par);
+                }
+            };
+            // ---- G1 of tile jj: R1 (pre-loaded by the F role) += emb W_e^T ----
+            auto g1 = [&](int jj) {
+                const uint32_t xc = tmem + ((jj & 1) ? COL_X1 : COL_X0);
+                mwait(0, &bars[B_A_FULL], (uint32_t)jj & 1u);
                 tc::tc_fence_after();
                 for (int p = 0; p < np; ++p) {      // small terms first: lo*hi, hi*lo, then hi*hi
                     const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0), pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
                     const uint64_t bd = tc::smem_desc(sWe + pb * (W1_WORDS * 4), H * 16, 128);
 #pragma unroll
                     for (int ks = 0; ks < CE / 16; ++ks)
-                        f16::mma_ts(tmem + COL_R1, xcol + (pa ? 32u : 0u) + ks * 8, bd + (uint64_t)((ks * 2 * H * 16) >> 4), ID_G1, true);
+                        f16::mma_ts(tmem + COL_R1, xc + (pa ? 32u : 0u) + ks * 8, bd + (uint64_t)((ks * 2 * H * 16) >> 4), ID_G1, true);
                 }
                 tc::mma_commit(&bars[B_D1_FULL]);
+            };
+            if (my_tiles > 0) g1(0);
+            for (int j = 0; j < my_tiles; ++j) {
+                const uint32_t ph = (uint32_t)j & 1u;
+                const uint32_t xcol = tmem + ((j & 1) ? COL_X1 : COL_X0);
                 // ---- G2: R3 = y1 W_2^T ----
-                tc::mbar_wait(&bars[B_Y1_FULL], ph);
+                mwait(1, &bars[B_Y1_FULL], ph);
+                if (j > 0) mwait(2, &bars[B_D4_READ], ph ^ 1u);      // the F role has read D4 of the previous tile out of R3
                 tc::tc_fence_after();
                 {
                     bool acc = false;
                     for (int p = 0; p < np; ++p) {
                         const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0), pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
                         const uint64_t bd = tc::smem_desc(sW2 + pb * (W2_WORDS * 4), CN * 16, 128);
+                        const uint64_t ad = tc::smem_desc(sY + pa * (Y_WORDS * 4), TM * 16, 128);      // the y1 image read K-major (rows = edges)
 #pragma unroll
                         for (int ks = 0; ks < H / 16; ++ks) {
-                            f16::mma_ts(tmem + COL_R3, tmem + COL_R1 + (pa ? 16u : 0u) + (ks >> 1) * 32 + (ks & 1) * 8,
-                                        bd + (uint64_t)((ks * 2 * CN * 16) >> 4), ID_G2, acc);
+                            f16::mma_ss(tmem + COL_R3, ad + (uint64_t)((ks * 2 * TM * 16) >> 4), bd + (uint64_t)((ks * 2 * CN * 16) >> 4), ID_G2, acc);
                             acc = true;
                         }
                     }
                 }
                 tc::mma_commit(&bars[B_D2_FULL]);
                 // ---- G3: R1 = dz2 W_2 (W_2's forward image read MN-major: N = H, K = CN) ----
-                tc::mbar_wait(&bars[B_Z2_FULL], ph);
+                mwait(3, &bars[B_Z2_FULL], ph);
                 tc::tc_fence_after();
                 {
                     bool acc = false;
@@ -701,22 +774,25 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                 }
                 tc::mma_commit(&bars[B_W2_DONE]);
                 // ---- G4: R3 = dz1 W_e (W_e's forward image read MN-major: N = CE, K = H) ----
-                tc::mbar_wait(&bars[B_Z1_FULL], ph);
+                mwait(4, &bars[B_Z1_FULL], ph);
                 tc::tc_fence_after();
                 {
                     bool acc = false;
                     for (int p = 0; p < np; ++p) {
                         const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0), pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
                         const uint64_t bd = tc::smem_desc(sWe + pb * (W1_WORDS * 4), 128, H * 16);
+                        const uint64_t ad = tc::smem_desc(sY + pa * (Y_WORDS * 4), TM * 16, 128);      // the dz1 image read K-major
 #pragma unroll
                         for (int ks = 0; ks < H / 16; ++ks) {
-                            f16::mma_ts(tmem + COL_R3, tmem + COL_R1 + (pa ? 16u : 0u) + (ks >> 1) * 32 + (ks & 1) * 8,
-                                        bd + (uint64_t)((ks * 256) >> 4), ID_G4, acc);
+                            f16::mma_ss(tmem + COL_R3, ad + (uint64_t)((ks * 2 * TM * 16) >> 4), bd + (uint64_t)((ks * 256) >> 4), ID_G4, acc);
                             acc = true;
                         }
                     }
                 }
                 tc::mma_commit(&bars[B_D4_FULL]);
+                // G1 of the NEXT tile goes in front of this tile's dWe: the workers' chain continues with its result, dWe only
+                // has to be complete before E1 of the next tile writes the y1 image
+                if (j + 1 < my_tiles) g1(j + 1);
                 // ---- dWe += dz1^T [emb | 1] ----
                 for (int p = 0; p < np; ++p) {
                     const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0), pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
@@ -730,6 +806,8 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
                 tc::mma_commit(&bars[B_WE_DONE]);
                 wacc = true;
             }
+            if (PROFILE && a.prof != nullptr)
+                for (int i = 0; i < 6; ++i) a.prof[blockIdx.x * 24 + 18 + i] = mt[i];
         }
         __syncwarp();
     }
@@ -803,18 +881,20 @@ int run_conv_edges_bwd_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_gra
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (g_f16_bwd_profile) {     // developer aid (rgnn_set_option("debug", 8)): per-phase cycles of worker thread 0; synchronises
         long long* prof = nullptr;
-        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 12 * grid));
-        RGNN_CHECK_CUDA(cudaMemsetAsync(prof, 0, sizeof(long long) * 12 * grid, stream));
+        RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * 24 * grid));
+        RGNN_CHECK_CUDA(cudaMemsetAsync(prof, 0, sizeof(long long) * 24 * grid, stream));
         a.prof = prof;
         mp_edge_bwd_f16_kernel<true><<<grid, mbf::NTHREADS, mbf::SMEM, stream>>>(a);
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
-        std::vector<long long> h(12 * grid);
-        RGNN_CHECK_CUDA(cudaMemcpy(h.data(), prof, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost));
-        double tot[12] = {0};
-        for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) tot[i] += (double)h[b * 12 + i];
-        static const char* nm[10] = {"waitG1", "E1", "waitG2", "E2", "waitG3", "E3a", "wait_dW2", "E3b", "waitG4", "E4"};
-        fprintf(stderr, "[mp_edge_bwd_f16 profile] cycles per tile (thread 0):");
-        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], tot[i] / (double)n_tiles);
+        std::vector<long long> h(24 * grid);
+        RGNN_CHECK_CUDA(cudaMemcpy(h.data(), prof, sizeof(long long) * 24 * grid, cudaMemcpyDeviceToHost));
+        double tot[24] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) tot[i] += (double)h[b * 24 + i];
+        static const char* nm[24] = {"waitG1", "E1", "waitG2", "E2", "waitG3", "E3a", "wait_dW2", "-", "E3b", "dz1 stores", "-", "-",
+                                     "F:loads", "F:idle", "F:preload", "F:waitG4", "F:E4", "-",
+                                     "MMA:wait A", "MMA:wait y1", "MMA:wait D4 read", "MMA:wait dz2", "MMA:wait dz1", "-"};
+        fprintf(stderr, "[mp_edge_bwd_f16 profile] cycles per tile:");
+        for (int i = 0; i < 24; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], tot[i] / (double)n_tiles);
         fprintf(stderr, "\n");
         cudaFree(prof);
     } else {
