@@ -425,8 +425,8 @@ def measure_roofline(det, bf, dev, steps, hbm, tf):
     nb = L.rgnn_conv_msg_bwd_workspace_bytes(C.byref(conv), C.byref(g))
     ws = torch.empty(nb, dtype=torch.uint8, device=dev)
     dagg, dproj, de = torch.randn(N, 64, device=dev) * 1e-3, torch.empty(N, 256, device=dev), torch.empty(E, 64, device=dev)
-    ms_bwd = timed_ms(lambda: check(L.rgnn_conv_msg_bwd(C.byref(conv), C.byref(g), ptr(e), ptr(proj), ptr(dagg), ptr(dproj), ptr(de),
-                                                        ptr(ws), nb, s), 'bwd'))
+    ms_bwd = timed_ms(lambda: check(L.rgnn_conv_msg_f16_bwd(C.byref(conv), C.byref(g), ptr(es), ptr(proj), ptr(dagg), ptr(dproj), ptr(de),
+                                                            ptr(ws), nb, s), 'bwd'))
     B_f, B_b = 512.0 * N + 260.0 * E, 768.0 * N + 772.0 * E
     F_msg, F_f = 65536.0 * E, 65536.0 * E + 16384.0 * N
     gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
@@ -447,7 +447,8 @@ def measure_roofline(det, bf, dev, steps, hbm, tf):
         'roofline_rowmlp': {'kernel': 'edge_enc_f16_kernel (graph_feature_encoding of the edges, 7-256-128-128-64)', 'bound': 'tensor',
                             'achieved': tfs(2 * 59136.0 * E, ms_enc), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * 59136.0 * E, ms_enc) / tf,
                             'ms_per_launch': ms_enc, 'algorithmic_bytes': 284.0 * E, 'traffic': None},
-        'roofline_bwd': {'kernel': 'message backward of one conv block: mp_edge_bwd_tc_kernel + 2 x wgrad_tma_kernel + dproj_gather_kernel (3xTF32)',
+        'roofline_bwd': {'kernel': 'message backward of one conv block: absmax_kernel + mp_edge_bwd_f16_kernel (recompute + dgrad + both weight gradients fused, '
+                                   'fp16-split x 3 passes) + dproj_gather_kernel',
                          'bound': 'tensor', 'achieved': tfs(2 * F_msg, ms_bwd), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * F_msg, ms_bwd) / tf,
                          'ms': ms_bwd, 'hbm_view': {'algorithmic_bytes': B_b, 'GBps': gbs(B_b, ms_bwd), 'frac_of_hbm': gbs(B_b, ms_bwd) / hbm},
                          'traffic': None},

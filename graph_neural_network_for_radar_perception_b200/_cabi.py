@@ -92,6 +92,7 @@ SIGNATURES = {
     'rgnn_conv_layer_f16_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V]),
     'rgnn_conv_msg_bwd_workspace_bytes': (_SZ, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph)]),
     'rgnn_conv_msg_bwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    'rgnn_conv_msg_f16_bwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_detector_workspace_bytes': (_SZ, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _I]),
     'rgnn_detector_fwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _I, _V]),
     'rgnn_cluster_workspace_bytes': (_SZ, [_I]),

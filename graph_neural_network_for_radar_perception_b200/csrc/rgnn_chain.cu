@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(NT, 2) tile_program_kernel(const __grid_consta
                 case OP_LOAD_SEGMAX: op_load_segmax<TR>(t, st); break;
                 case OP_LINEAR:
                     tile_gemm<TR>(t.reg(st.ra), t.ld(st.ra), st.i0, st.i3, static_cast<const float*>(st.p0), st.i4, st.i2,
-                                  static_cast<const float*>(st.p1), st.i1, t.reg(st.rb), t.ld(st.rb), t.wst);
+                                  static_cast<const float*>(st.p1), st.i1, t.reg(st.rb), t.ld(st.rb), t.wst, st.i5 > 0 ? st.i5 : st.i2);
                     break;
                 case OP_ADD_GATHER2: op_add_gather2<TR>(t, st); break;
                 case OP_NORM_ACT:
@@ -618,8 +618,8 @@ Step* ProgBuilder::add(int op, int ra, int rb) {
 }
 
 bool check_linear(const rgnn_linear& L) {
-    if (L.in_features <= 0 || L.in_features > 256 || L.out_features <= 0 || L.out_features > 256) {
-        set_error("linear %dx%d outside the supported widths (<=256)", L.out_features, L.in_features);
+    if (L.in_features <= 0 || L.in_features > 512 || L.out_features <= 0 || L.out_features > 512) {
+        set_error("linear %dx%d outside the supported widths (<=512)", L.out_features, L.in_features);
         return false;
     }
     if (L.norm_scale != nullptr && (L.out_features % 32 != 0 || L.out_features < 2)) {
@@ -639,10 +639,10 @@ void ProgBuilder::load_rows(int ra, const float* src, int ld, int w, int dcol, i
     s->i0 = ld; s->i1 = w; s->i2 = dcol; s->i3 = padto < w ? w : padto; s->i4 = scol;
 }
 
-void ProgBuilder::gemm(int ra, int rb, const float* Wt, int ldw, int K, int k_valid, int C, int Cpad, const float* bias) {
+void ProgBuilder::gemm(int ra, int rb, const float* Wt, int ldw, int K, int k_valid, int C, int Cpad, const float* bias, int c_exist) {
     Step* s = add(OP_LINEAR, ra, rb);
     s->p0 = Wt; s->p1 = bias;
-    s->i0 = K; s->i1 = C; s->i2 = Cpad; s->i3 = k_valid; s->i4 = ldw;
+    s->i0 = K; s->i1 = C; s->i2 = Cpad; s->i3 = k_valid; s->i4 = ldw; s->i5 = c_exist;
 }
 
 void ProgBuilder::norm_act(int ra, const rgnn_linear& L, int slot) {

@@ -108,7 +108,7 @@ bool conv_dims(const rgnn_conv& c, ConvDims* d) {
                   "identity-residual form in==out is implemented", m0.in_features, ml.out_features, u0.in_features, ul.out_features);
         return false;
     }
-    if ((d->cn % 8) || (d->ce % 8) || (d->h % 32) || 2 * d->h > 256 || 2 * d->cn > 256) {
+    if ((d->cn % 8) || (d->ce % 8) || (d->h % 32) || d->h > 512 || d->cn > 256 || d->ce > 256) {
         set_error("conv block: widths cn=%d ce=%d h=%d outside the supported range", d->cn, d->ce, d->h);
         return false;
     }
@@ -121,21 +121,40 @@ bool conv_dims(const rgnn_conv& c, ConvDims* d) {
 int stack_in(const rgnn_stack& s) { return s.layer[0].in_features; }
 int stack_out(const rgnn_stack& s) { return s.layer[s.n - 1].out_features; }
 
+// widest activation row of a stack / a conv block (sizes the two ping-pong regions)
+static int stack_maxw(const rgnn_stack& s) {
+    int w = 64;
+    for (int i = 0; i < s.n; ++i) {
+        w = w > s.layer[i].in_features ? w : s.layer[i].in_features;
+        w = w > s.layer[i].out_features ? w : s.layer[i].out_features;
+    }
+    return w;
+}
+static int conv_maxw(const ConvDims& d) { return d.h > 2 * d.cn ? (d.h > d.ce ? d.h : d.ce) : (2 * d.cn > d.ce ? 2 * d.cn : d.ce); }
+
+// Two ping-pong regions.  The reference plan (every row <= 256 wide) runs 64-row tiles; wider channel plans (hidden width 128 / 256
+// of BASELINE.json's sweep: rows of up to 512 values) run 32-row tiles with regions of the width they need.
 struct FwdBuilder : ProgBuilder {
-    int cur, nxt;
-    explicit FwdBuilder(int n_rows) : ProgBuilder(n_rows, TR_FWD) {
-        cur = region(256);
-        nxt = region(256);
+    int cur, nxt, width;
+    explicit FwdBuilder(int n_rows, int maxw = 256) : ProgBuilder(n_rows, maxw > 256 ? 32 : TR_FWD) {
+        width = maxw > 256 ? round_up(maxw, 64) : 256;
+        cur = region(width);
+        nxt = region(width);
     }
     void swap() { int t = cur; cur = nxt; nxt = t; }
     void lin(const rgnn_linear& L) { linear(cur, nxt, L); swap(); }
     void stack(const rgnn_stack& s, int first = 0) { for (int i = first; i < s.n; ++i) lin(s.layer[i]); }
+    // hoisted node half of msg.0: P = [x W_t^T + b | x W_s^T], 2h columns, produced and stored in pieces of at most `width` columns
     void proj(const rgnn_conv& c, const ConvDims& d, float* P) {
         const int Cp = round_up(2 * d.h, 64), Kp = round_up(d.cn, 8);
         const float* bias2h = c.msg.layer[0].weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d) + conv_msg0_projnat_floats(d);
-        gemm(cur, nxt, c.msg.layer[0].weight_t, Cp, Kp, Kp, 2 * d.h, Cp, bias2h);
-        swap();
-        store_rows(cur, P, 2 * d.h, 2 * d.h);
+        const int src = cur;
+        for (int c0 = 0; c0 < Cp; c0 += width) {
+            const int cw = Cp - c0 < width ? Cp - c0 : width;
+            const int valid = 2 * d.h - c0 < cw ? 2 * d.h - c0 : cw;
+            gemm(src, nxt, c.msg.layer[0].weight_t + c0, Cp, Kp, Kp, valid, cw, bias2h + c0);
+            store_rows(nxt, P, 2 * d.h, valid, c0);
+        }
     }
 };
 
@@ -144,7 +163,7 @@ int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cud
     // inference (nothing to save for a backward): the fixed-shape fp16-split chain kernel
     if (save == nullptr && chain64_supported(s)) return run_chain64(s, x, stack_in(s), nullptr, nullptr, n_rows, y, stream);
     if (tc_stack_supported(s)) return tc_run_stack(s, x, nullptr, n_rows, y, stream, save);
-    FwdBuilder b(n_rows);
+    FwdBuilder b(n_rows, stack_maxw(s));
     b.load_rows(b.cur, x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
     b.stack(s);
     b.store_rows(b.cur, y, stack_out(s), stack_out(s));
@@ -156,7 +175,7 @@ int run_proj(const rgnn_conv& c, const float* x, int n_nodes, float* P, cudaStre
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
     RGNN_REQUIRE(c.msg.layer[0].weight_t != nullptr, "conv msg.0 not packed");
-    FwdBuilder b(n_nodes);
+    FwdBuilder b(n_nodes, conv_maxw(d));
     b.load_rows(b.cur, x, d.cn, d.cn, 0, round_up(d.cn, 8));
     b.proj(c, d, P);
     if (!b.ok) return RGNN_ERR_INVALID;
@@ -200,7 +219,7 @@ int run_conv_edges(const rgnn_conv& c, const rgnn_graph& g, const float* emb, co
         const float* wpack = c.msg.layer[0].weight_t + conv_msg0_tc_offset(d);
         return run_conv_edges_tc(c, d, g, emb, P, wpack, agg, stream);
     }
-    FwdBuilder b(g.n_edges);
+    FwdBuilder b(g.n_edges, conv_maxw(d));
     b.load_rows(b.cur, emb, d.ce, d.ce, 0, round_up(d.ce, 8));
     add_message_layers(b, c, d, g, P, b.cur, b.nxt, b.cur, -1, -1);
     Step* s = b.add(OP_SEGSUM, b.cur);
@@ -232,7 +251,7 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
         }
         return tc_run_conv_nodes(c, d, n_nodes, x, agg, out, next, P_next, stream, u_save, sd_save);
     }
-    FwdBuilder b(n_nodes);
+    FwdBuilder b(n_nodes, conv_maxw(d));
     b.load_rows(b.cur, x, d.cn, d.cn, 0);
     b.load_rows(b.cur, agg, d.cn, d.cn, d.cn);
     b.stack(c.upd);
@@ -310,7 +329,7 @@ static int run_obj_head(const rgnn_detector& net, const rgnn_graph& g, const Det
     if (g.n_clusters > 0 && tc_stack_supported(net.head_class)) {
         if ((rc = tc_run_segmax_stack(net.head_class, pl.gcls, pl.cls_w, g.cl_ptr, g.cl_members, g.n_clusters, obj_cls, stream))) return rc;
     } else if (g.n_clusters > 0) {
-        FwdBuilder b(g.n_clusters);
+        FwdBuilder b(g.n_clusters, stack_maxw(net.head_class));
         Step* s = b.add(OP_LOAD_SEGMAX, b.cur);
         s->p0 = pl.gcls; s->p1 = g.cl_ptr; s->p2 = g.cl_members; s->i0 = pl.cls_w; s->i1 = pl.cls_w;
         b.stack(net.head_class);
@@ -332,7 +351,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
                                       pl.node_tc_bwd[0] ? &pl.node_save[0] : nullptr)))
             return rc;
     } else {   // node encoder (+ first layer's projections)
-        FwdBuilder b(N);
+        FwdBuilder b(N, stack_maxw(net.node_enc) > conv_maxw(d) ? stack_maxw(net.node_enc) : conv_maxw(d));
         const int in = stack_in(net.node_enc);
         b.load_rows(b.cur, node_features, in, in, 0, round_up(in, 8));
         b.stack(net.node_enc);
@@ -350,7 +369,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     } else if (E > 0 && tc_stack_supported(net.edge_enc)) {
         if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream, pl.enc_tc_bwd ? &pl.enc_save : nullptr))) return rc;
     } else if (E > 0) {   // edge encoder, rows gathered into target-major order
-        FwdBuilder b(E);
+        FwdBuilder b(E, stack_maxw(net.edge_enc));
         const int in = stack_in(net.edge_enc);
         b.load_rows(b.cur, edge_features, in, in, 0, round_up(in, 8), g.perm);
         b.stack(net.edge_enc);
@@ -378,7 +397,7 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
                                        pl.link_tc_bwd ? &pl.link_save : nullptr)))
             return rc;
     } else if (g.n_und > 0) {
-        FwdBuilder b(g.n_und);
+        FwdBuilder b(g.n_und, stack_maxw(net.head_link));
         Step* s = b.add(OP_LOAD_PAIRSUM, b.cur);
         s->p0 = pl.hlink; s->p1 = g.und_a; s->p2 = g.und_b; s->i0 = pl.link_w; s->i1 = pl.link_w;
         b.stack(net.head_link);
@@ -516,6 +535,23 @@ extern "C" int rgnn_conv_msg_bwd(const rgnn_conv* blk, const rgnn_graph* g, cons
         return rc;
     }
     return run_conv_edges_bwd_tc(*blk, d, *g, e, proj, dagg, dproj, de, true, scratch, sptr, slist, s);
+}
+
+extern "C" int rgnn_conv_msg_f16_bwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj, const float* dagg,
+                                     float* dproj, float* de, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(mp_bwd_f16_supported(d), "conv_msg_f16_bwd: channel plan %d / %d / %d is not instantiated (64 / 64 / 128)", d.cn, d.ce, d.h);
+    RGNN_REQUIRE(workspace_bytes >= rgnn_conv_msg_bwd_workspace_bytes(blk, g), "conv_msg_f16_bwd: workspace too small");
+    float* scratch = static_cast<float*>(workspace);
+    int* sidx = reinterpret_cast<int*>(static_cast<char*>(workspace) + align256(mp_bwd_tc_scratch_floats(d, g->n_edges) * sizeof(float)));
+    const int* sptr = nullptr;
+    const int* slist = nullptr;
+    int rc = build_src_index(*g, sidx, &sptr, &slist, s);
+    if (rc) return rc;
+    if (g->n_edges == 0) return cudaMemsetAsync(dproj, 0, (size_t)g->n_nodes * 2 * d.h * sizeof(float), s) == cudaSuccess ? RGNN_OK : RGNN_ERR_CUDA;
+    return run_conv_edges_bwd_f16(*blk, d, *g, static_cast<const uint32_t*>(e_split), proj, dagg, dproj, de, true, scratch, sptr, slist, s);
 }
 
 extern "C" size_t rgnn_detector_workspace_bytes(const rgnn_detector* net, const rgnn_graph* g, int training) {

@@ -36,6 +36,11 @@ struct BwdBuilder : ProgBuilder {
 
     void actnorm_bwd(const rgnn_linear& L, int r_y, int slot) {
         if (L.norm_scale == nullptr && !L.activation) return;
+        if (L.out_features > 256) {
+            set_error("backward: layers wider than 256 channels (%d) are outside the training envelope", L.out_features);
+            ok = false;
+            return;
+        }
         Step* st = add(OP_ACTNORM_BWD, wcur, r_y);
         st->i0 = L.out_features; st->i1 = L.activation; st->i2 = slot < 0 ? 0 : slot;
         st->p0 = L.norm_scale; st->p1 = L.norm_shift; st->p2 = L.grad_norm_scale; st->p3 = L.grad_norm_shift;
@@ -48,14 +53,14 @@ struct BwdBuilder : ProgBuilder {
         st->p0 = dW; st->p1 = db;
     }
 
-    // dX = dZ * W with W in its natural (out, in) layout: rows = reduction index
+    // dX = dZ * W with W in its natural (out, in) layout: rows = reduction index, in_features columns (not padded)
     bool dgrad(const float* W, int ldw, int n_out_rows, int n_in_cols) {
-        if (n_in_cols % 64 != 0) {
-            set_error("backward: input width %d of a differentiated Linear must be a multiple of 64", n_in_cols);
+        if (n_in_cols % 8 != 0) {
+            set_error("backward: input width %d of a differentiated Linear must be a multiple of 8", n_in_cols);
             ok = false;
             return false;
         }
-        gemm(wcur, wnxt, W, ldw, round_up(n_out_rows, 8), n_out_rows, n_in_cols, n_in_cols, nullptr);
+        gemm(wcur, wnxt, W, ldw, round_up(n_out_rows, 8), n_out_rows, n_in_cols, round_up(n_in_cols, 64), nullptr, n_in_cols);
         swap();
         return true;
     }
@@ -166,8 +171,7 @@ static int conv_edges_bwd(const rgnn_conv& c, const ConvDims& d, const rgnn_grap
     b.actnorm_bwd(m0, r_1, s0);                                               // wcur = dz1 (E_tile, h)
     b.wgrad(b.wcur, r_e, d.h, d.ce, m0.grad_weight, m0.in_features, 2 * d.cn, 0, m0.grad_bias);
     const int r_dz1 = b.wcur;
-    if (d.ce % 64 != 0) { set_error("backward: edge width must be a multiple of 64"); return RGNN_ERR_INVALID; }
-    b.gemm(b.wcur, b.wnxt, m0.weight + 2 * d.cn, m0.in_features, round_up(d.h, 8), d.h, d.ce, d.ce, nullptr);
+    b.gemm(b.wcur, b.wnxt, m0.weight + 2 * d.cn, m0.in_features, round_up(d.h, 8), d.h, d.ce, round_up(d.ce, 64), nullptr, d.ce);
     b.store_rows(b.wnxt, demb, d.ce, d.ce, 0, !first_demb);
     Step* s = b.add(OP_SEGSUM, r_dz1);
     s->p0 = dP; s->p1 = g.tgt; s->p2 = g.row_ptr;

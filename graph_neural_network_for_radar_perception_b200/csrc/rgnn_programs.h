@@ -18,7 +18,8 @@ struct ProgBuilder {
     Step* add(int op, int ra = 0, int rb = 0);
     void load_rows(int ra, const float* src, int ld, int w, int dcol = 0, int padto = 0, const int* ridx = nullptr,
                    int scol = 0);
-    void gemm(int ra, int rb, const float* Wt, int ldw, int K, int k_valid, int C, int Cpad, const float* bias);
+    // c_exist: columns of Wt that exist in memory (0: all Cpad; natural-layout operands of a backward are not padded)
+    void gemm(int ra, int rb, const float* Wt, int ldw, int K, int k_valid, int C, int Cpad, const float* bias, int c_exist = 0);
     void norm_act(int ra, const rgnn_linear& L, int slot = -1);
     void linear(int ra, int rb, const rgnn_linear& L, int slot = -1);   // OP_LINEAR (+ OP_NORM_ACT on rb)
     void store_rows(int ra, float* dst, int ld, int w, int dcol = 0, bool accumulate = false, int scol = 0);

@@ -27,15 +27,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Copy rows [k0, k0+kn) x cols [cb, cb+bw) of the k-major operand Wt (row stride ldw) into a stage buffer laid
-// out [KC][CBMAX].  Rows at or beyond k_valid do not exist in memory and are zero-filled.
+// out [KC][CBMAX].  Rows at or beyond k_valid and columns at or beyond c_exist (a multiple of 4) do not exist in memory and
+// are zero-filled.
 __device__ __forceinline__ void stage_weights(float* ws, const float* __restrict__ Wt, int ldw, int k0, int kn,
-                                              int k_valid, int cb, int bw) {
+                                              int k_valid, int cb, int bw, int c_exist) {
     const int per_row = bw >> 2;
     const int tot = kn * per_row;
     for (int i = threadIdx.x; i < tot; i += NT) {
         const int r = i / per_row, c4 = i - r * per_row;
         float* d = ws + r * CBMAX + 4 * c4;
-        if (k0 + r < k_valid)
+        if (k0 + r < k_valid && cb + 4 * c4 < c_exist)
             cp_async16(d, Wt + (size_t)(k0 + r) * ldw + cb + 4 * c4);
         else
             *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -49,7 +50,7 @@ template <int TR, bool TWO>
 __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, int ldx, int K, int k_valid,
                                                 const float* __restrict__ Wt, int ldw, int cb, int bw,
                                                 const float* __restrict__ bias, int C, float* __restrict__ Ys, int ldy,
-                                                float* __restrict__ wstage) {
+                                                float* __restrict__ wstage, int c_exist) {
     constexpr int RPT = TR / 16;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     float acc[RPT][TWO ? 8 : 4];
@@ -59,12 +60,12 @@ __device__ __forceinline__ void tile_gemm_block(const float* __restrict__ Xs, in
         for (int j = 0; j < (TWO ? 8 : 4); ++j) acc[i][j] = 0.f;
 
     const int nch = (K + KC - 1) / KC;
-    stage_weights(wstage, Wt, ldw, 0, min(KC, K), k_valid, cb, bw);
+    stage_weights(wstage, Wt, ldw, 0, min(KC, K), k_valid, cb, bw, c_exist);
     cp_async_commit();
     for (int ch = 0; ch < nch; ++ch) {
         if (ch + 1 < nch) {
             stage_weights(wstage + ((ch + 1) & 1) * KC * CBMAX, Wt, ldw, (ch + 1) * KC, min(KC, K - (ch + 1) * KC),
-                          k_valid, cb, bw);
+                          k_valid, cb, bw, c_exist);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -125,13 +126,13 @@ template <int TR>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ Xs, int ldx, int K, int k_valid,
                                           const float* __restrict__ Wt, int ldw, int Cpad,
                                           const float* __restrict__ bias, int C, float* __restrict__ Ys, int ldy,
-                                          float* __restrict__ wstage) {
+                                          float* __restrict__ wstage, int c_exist) {
     for (int cb = 0; cb < Cpad; cb += CBMAX) {
         const int bw = min(CBMAX, Cpad - cb);
         if (bw > 64)
-            tile_gemm_block<TR, true>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage);
+            tile_gemm_block<TR, true>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage, c_exist);
         else
-            tile_gemm_block<TR, false>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage);
+            tile_gemm_block<TR, false>(Xs, ldx, K, k_valid, Wt, ldw, cb, bw, bias, C, Ys, ldy, wstage, c_exist);
     }
     __syncthreads();
 }
@@ -149,17 +150,17 @@ __device__ __forceinline__ void tile_norm_act(float* __restrict__ Ys, int ld, in
         const int nq = C >> 5;
         for (int r = warp; r < TR; r += NT / 32) {
             float* y = Ys + r * ld;
-            float v[8];
+            float v[16];       // rows of up to 512 channels (hidden width 256: msg.0 is 512 wide)
             float s = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 16; ++q) {
                 v[q] = q < nq ? y[lane + 32 * q] : 0.f;
                 s += v[q];
             }
             const float mean = warp_sum(s) / (float)C;
             float ss = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 16; ++q) {
                 const float d = q < nq ? v[q] - mean : 0.f;
                 v[q] = d;
                 ss = fmaf(d, d, ss);
@@ -168,7 +169,7 @@ __device__ __forceinline__ void tile_norm_act(float* __restrict__ Ys, int ld, in
             const float den = sd + NORM_EPS;
             if (sigma_out != nullptr && lane == 0) sigma_out[r] = sd;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 16; ++q) {
                 if (q < nq) {
                     float o = fmaf(scale, __fdiv_rn(v[q], den), shift);
                     if (act) o = leaky(o);

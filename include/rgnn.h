@@ -219,6 +219,11 @@ int rgnn_conv_layer_f16_fwd(const rgnn_conv* blk, const rgnn_conv* next, const r
 size_t rgnn_conv_msg_bwd_workspace_bytes(const rgnn_conv* blk, const rgnn_graph* g);
 int rgnn_conv_msg_bwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, const float* dagg,
                       float* dproj, float* de, void* workspace, size_t workspace_bytes, void* stream);
+/* The same on the pre-split rows of rgnn_split_edge_embedding / rgnn_edge_encoder_f16_fwd (what the detector backward passes):
+ * ONE fused kernel (csrc/rgnn_mp_bwd_f16.cu: recompute, data gradients and both weight gradients on fp16-split operands)
+ * plus the gather of d(proj).  Reference plan only (64 / 64 / 128); same workspace as rgnn_conv_msg_bwd. */
+int rgnn_conv_msg_f16_bwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj, const float* dagg,
+                          float* dproj, float* de, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Model_Inference.forward with cluster_node_idx given (gnn_detector.py:141-162).
  * edge_features rows are in the caller's order (g->perm maps them).  Outputs: node_cls (N,7), node_off (N,2),

@@ -207,15 +207,10 @@ def test_trainer_step_equals_reference_sgd_step(golden_dir, ckpt_state_dict):
             assert_close(p.detach().cpu().numpy(), ref, 1e-5, 1e-4, n)
 
 
-def test_hidden_width_32_forward_matches_oracle_and_training_fails_loudly():
-    """BASELINE.json configs[4] (hidden width sweep).  Supported envelope of this library: forward for
-    node / edge widths that are multiples of 8 up to 128 with msg hidden <= 128; training additionally needs widths that are
-    multiples of 64.  Width 32: the forward (FFMA tile programs + the generic tensor-core row-MLP stages) is held to the
-    oracle; the training step must raise, not compute something else."""
-    from graph_neural_network_for_radar_perception_b200 import config, Model_Training, synth
-    from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
-    from oracle import graph_np, model_torch as mt
-    hidden = 32
+def _width_config(hidden):
+    """BASELINE.json configs[4] / SURVEY.md 8(d) C5: `hidden` scales graph_convolution_stem_channels, the encoder tails and the
+    head stems; msg_mlp_hidden_dim = 2 x hidden (reference set_config_gnn.py:48-72)."""
+    from graph_neural_network_for_radar_perception_b200 import config
     cfg = config()
     cfg.node_feat_enc_stem_channels = [256, 128, hidden]
     cfg.edge_feat_enc_stem_channels = [256, 128, 128, hidden]
@@ -223,8 +218,19 @@ def test_hidden_width_32_forward_matches_oracle_and_training_fails_loudly():
     cfg.msg_mlp_hidden_dim = 2 * hidden
     cfg.link_pred_stem_channels = [hidden] * 3
     cfg.node_pred_stem_channels = [hidden] * 3
+    return cfg
+
+
+@pytest.mark.parametrize('hidden', [32, 128, 256])
+def test_hidden_width_sweep_forward_matches_oracle(hidden):
+    """Hidden widths off the reference plan run the FFMA tile programs (csrc/rgnn_chain.cu: 32-row tiles and regions of up to
+    512 columns for hidden 256, whose msg.0 is 768 -> 512 with the node half hoisted) and, where a stack fits it, the generic
+    tensor-core row-MLP stages.  Random-init weights (seed 1234), one 150-point frame, all four outputs held to the oracle at
+    the forward tolerance of tests/test_model_gpu.py."""
+    from graph_neural_network_for_radar_perception_b200 import Model_Training, synth
+    from oracle import graph_np, model_torch as mt
     torch.manual_seed(1234)
-    m = Model_Training(cfg, 'cuda').to('cuda')
+    m = Model_Training(_width_config(hidden), 'cuda').to('cuda')
     sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
     d, src = synth.make_frame(900, 150)
@@ -239,13 +245,42 @@ def test_hidden_width_32_forward_matches_oracle_and_training_fails_loudly():
         got = m.pred.eval()(nf.cuda(), ef.cuda(), ei.cuda(), None, [c.cuda() for c in clusters])
     for g, w, name in zip(got, want, ('node_cls', 'node_off', 'link_cls', 'obj_cls')):
         w = w.detach().numpy()
-        assert_close(g.cpu().numpy(), w, 1e-4, 1e-5 * max(np.abs(w).max(), 1.0), name)
-    labels = {'cluster_node_idx': [[c.cuda() for c in clusters]],
-              'cluster_labels': [torch.from_numpy(lab['cluster_labels']).cuda()],
-              'edge_class': [torch.from_numpy(lab['edge_class']).cuda()],
-              'node_class': [torch.from_numpy(lab['node_class']).cuda()],
-              'node_offsets': [torch.from_numpy(lab['node_offsets']).cuda()]}
-    loss, _ = m.train()([nf.cuda()], [ef.cuda()], [ei.cuda()], [None], labels)
+        assert_close(g.cpu().numpy(), w, 1e-4, 1e-5 * max(np.abs(w).max(), 1.0), f'hidden {hidden}: {name}')
+
+
+def test_hidden_width_32_training_step_matches_oracle_autograd():
+    """Training at hidden width 32 (every gradient through the recompute tile programs on the CUDA cores; the natural-layout
+    weight operands of their dgrad steps are 32 / 96 columns wide, zero-filled to the 64-column blocks of the tile GEMM),
+    random-init weights, against the same yardstick as the reference plan."""
+    from graph_neural_network_for_radar_perception_b200 import Model_Training
+    torch.manual_seed(1234)
+    cfg = _width_config(32)
+    sd0 = {k: v.detach().clone() for k, v in Model_Training(cfg, 'cpu').state_dict().items()}
+    frames = synth_batch((150, 90), seed0=760)
+    ys = GradientYardstick(sd0, frames, members=5, flip_window=FLIP_WINDOW)
+    m = Model_Training(cfg, 'cuda')
+    m.load_state_dict(sd0, strict=True)
+    m = m.to('cuda').train()
+    loss, acc = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
+                  [None] * len(frames), batch_labels(frames, 'cuda'))
+    for k in loss:
+        assert_close(loss[k].item(), ys.loss32[k].item(), 1e-4, 1e-6, k)
+    sum(loss.values()).backward()
+    got = model_grads(m)
+    assert set(got) == set(ys.names)
+    ys.check(got, what='hidden width 32, random-init weights')
+
+
+def test_hidden_width_256_training_fails_loudly():
+    """Outside the training envelope: the backward tile programs hold rows of at most 256 channels; a wider
+    plan must raise, not compute something else."""
+    from graph_neural_network_for_radar_perception_b200 import Model_Training
+    from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
+    torch.manual_seed(1234)
+    m = Model_Training(_width_config(256), 'cuda').to('cuda').train()
+    frames = synth_batch((60,), seed0=770)
+    loss, _ = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
+                [None], batch_labels(frames, 'cuda'))
     with pytest.raises(RgnnError):
         sum(loss.values()).backward()
 
