@@ -385,7 +385,7 @@ def measure_roofline(det, bf, dev, steps, hbm, tf):
     N, E = gb.n_nodes, gb.n_edges
     x = torch.randn(N, 64, device=dev)
     e = torch.randn(E, 64, device=dev)
-    es = torch.empty(E * 64, dtype=torch.int32, device=dev)
+    es = torch.empty(lib().rgnn_split_edge_embedding_words(E), dtype=torch.int32, device=dev)
     check(lib().rgnn_split_edge_embedding(ptr(e), E, ptr(es), stream_ptr()), 'split')
     out, agg = torch.empty_like(x), torch.empty_like(x)
     proj, proj2 = torch.randn(N, 256, device=dev), torch.empty(N, 256, device=dev)

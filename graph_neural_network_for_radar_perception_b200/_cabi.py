@@ -86,6 +86,7 @@ SIGNATURES = {
     'rgnn_ffn_stack_bwd': (_I, [C.POINTER(rgnn_stack), _V, _V, _I, _V, _V, _SZ, _V]),
     'rgnn_conv_block_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V]),
     'rgnn_conv_edges_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V]),
+    'rgnn_split_edge_embedding_words': (_SZ, [_I]),
     'rgnn_split_edge_embedding': (_I, [_V, _I, _V, _V]),
     'rgnn_conv_edges_f16_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V]),
     'rgnn_edge_encoder_f16_fwd': (_I, [C.POINTER(rgnn_stack), _V, _V, _I, _V, _V, _V]),

@@ -31,7 +31,7 @@ struct EdgeEncArgs {
     const uint32_t* w3;         // K = 128 x N = 64
     const float* b0; const float* b1; const float* b2; const float* b3;
     const float* s1; const float* m1; const float* s2; const float* m2; const float* s3; const float* m3;
-    uint32_t* emb_hl;           // (E, 64 words): [hi 64 fp16 | lo 64 fp16] of 16 x the embedding
+    uint32_t* emb_hl;           // pre-split rows of 16 x the embedding, TILED (rgnn_f16.cuh: emb_tile_word)
     float* emb;                 // optional fp32 copy (E, 64) or nullptr
     int passes;
 };
@@ -301,16 +301,22 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                             stg256(o + 32 + 8 * i, vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
                         }
                     }
-                    uint32_t* o = a.emb_hl + (size_t)r * 64;
+                    // tiled rows (rgnn_f16.cuh: emb_tile_word): 16 bytes per chunk of 8 channels, the warp's 32 rows write 512 contiguous bytes
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f16::split(__fmul2_rn(va[i], s16), hi[i], lo[i]);
-                    f16::stg256u(o, hi); f16::stg256u(o + 8, hi + 8);
-                    f16::stg256u(o + 32, lo); f16::stg256u(o + 40, lo + 8);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        *reinterpret_cast<uint4*>(a.emb_hl + emb_tile_word(r, 0, k)) = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                        *reinterpret_cast<uint4*>(a.emb_hl + emb_tile_word(r, 1, k)) = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f16::split(__fmul2_rn(vb[i], s16), hi[i], lo[i]);
-                    f16::stg256u(o + 16, hi); f16::stg256u(o + 24, hi + 8);
-                    f16::stg256u(o + 48, lo); f16::stg256u(o + 56, lo + 8);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        *reinterpret_cast<uint4*>(a.emb_hl + emb_tile_word(r, 0, 4 + k)) = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                        *reinterpret_cast<uint4*>(a.emb_hl + emb_tile_word(r, 1, 4 + k)) = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+                    }
                 }
             }
         }

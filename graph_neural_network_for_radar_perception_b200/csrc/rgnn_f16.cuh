@@ -111,6 +111,20 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 
 }  // namespace f16
 
+// TILED layout of the pre-split edge rows (what the edge encoder writes and the message kernels read): per tile of 128 edges one
+// 32 KB block  [hi | lo][chunk of 8 channels: 8][edge: 128][8 fp16]  -- byte for byte the chunk-major operand image of a tile.
+// A thread that owns edge row r moves 16 bytes per chunk and the 32 lanes of a warp touch 512 CONTIGUOUS bytes (4 L1 wavefronts
+// per instruction instead of the 32 of a row-per-thread 32-byte access); a whole image is one bulk copy.
+constexpr int EMB_TILE_WORDS = 128 * 64;
+__host__ __device__ __forceinline__ size_t emb_tile_word(long long e, int img, int c8) {
+    return (size_t)(e >> 7) * EMB_TILE_WORDS + (size_t)img * (EMB_TILE_WORDS / 2) + ((size_t)c8 * 128 + (size_t)(e & 127)) * 4;
+}
+__device__ __forceinline__ uint4 ldg128u(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 // one elected lane per warp arrives for its 32 rows (the warp-collective tcgen05.wait / fences come first)
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     __syncwarp();

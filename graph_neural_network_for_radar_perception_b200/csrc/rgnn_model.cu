@@ -478,6 +478,8 @@ extern "C" int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, co
     return run_conv_edges(*blk, *g, e, proj, agg, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" size_t rgnn_split_edge_embedding_words(int n_edges) { return mp_f16_emb_words(n_edges); }
+
 extern "C" int rgnn_split_edge_embedding(const float* e, int n_edges, void* e_split, void* stream) {
     return mp_f16_split_emb(e, n_edges, static_cast<uint32_t*>(e_split), static_cast<cudaStream_t>(stream));
 }

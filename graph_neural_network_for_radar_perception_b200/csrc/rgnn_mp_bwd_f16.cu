@@ -42,7 +42,7 @@
 namespace rgnn {
 
 struct MpBwdF16Args {
-    const uint32_t* emb;    // (E, 64) words: per edge [hi: 64 fp16 | lo: 64 fp16], values x 16, target-major
+    const uint32_t* emb;    // pre-split edge rows, values x 16, target-major, TILED (rgnn_f16.cuh: emb_tile_word)
     const float* P;         // (N, 2H) fp32: [x W_t^T + b1 | x W_s^T]
     const float* dagg;      // (N, CN) gradient w.r.t. the aggregated messages
     const int* tgt;
@@ -606,9 +606,12 @@ __global__ void __launch_bounds__(mbf::NTHREADS, 1) mp_edge_bwd_f16_kernel(const
             if (valid) { t = __ldg(a.tgt + e); s = __ldg(a.src + e); }
             {   // emb hi | lo -> X (free: the dz2 operand of tile j - 2 was consumed by its G3, which this role has seen complete)
                 uint32_t ev[64];
-                const uint32_t* pe = a.emb + (size_t)(valid ? e : 0) * 64;
+                const long long el = valid ? e : 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f16::ldg256u(pe + 8 * i, ev + 8 * i);
+                for (int i = 0; i < 16; ++i) {      // tiled rows (rgnn_f16.cuh): 16 bytes per chunk, a warp reads 512 contiguous bytes
+                    const uint4 v = ldg128u(a.emb + emb_tile_word(el, i >> 3, i & 7));
+                    ev[4 * i] = v.x; ev[4 * i + 1] = v.y; ev[4 * i + 2] = v.z; ev[4 * i + 3] = v.w;
+                }
                 if (!valid) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) ev[i] = 0u;

@@ -34,7 +34,7 @@
 namespace rgnn {
 
 struct MpF16Args {
-    const uint32_t* emb;    // (E, 64) words: per edge [hi: 64 fp16 | lo: 64 fp16], values x 16, target-major
+    const uint32_t* emb;    // pre-split edge rows, values x 16, target-major, TILED (rgnn_f16.cuh: emb_tile_word)
     const float* P;         // (N, 2H) fp32: [x W_t^T + b1 | x W_s^T]
     const int* tgt;
     const int* src;
@@ -397,9 +397,12 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             load_pt(p1, 32);
             load_pt(p2, 64);
             uint32_t ev[32];
-            const uint32_t* pe = a.emb + (size_t)(valid ? e : 0) * 64;
+            const long long el = valid ? e : 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) f16::ldg256u(pe + 8 * i, ev + 8 * i);
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const uint4 v = ldg128u(a.emb + emb_tile_word(el, 0, c8));
+                ev[4 * c8] = v.x; ev[4 * c8 + 1] = v.y; ev[4 * c8 + 2] = v.z; ev[4 * c8 + 3] = v.w;
+            }
             {   // next tile: target index of this thread's row; its emb row two tiles ahead -> L2 (it streams from DRAM)
                 const int en = ((int)blockIdx.x + (j + 1) * G) * TM + row;
                 t_next = (j + 1 < my_tiles && en < a.n_edges) ? __ldg(a.tgt + en) : -1;
@@ -423,7 +426,10 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             f16::tmem_st16u(c_emb + 16, ev + 16);
             if (np != 1) {      // the lo half: requested now, stored after the accumulator pre-load below
 #pragma unroll
-                for (int i = 0; i < 4; ++i) f16::ldg256u(pe + 32 + 8 * i, ev + 8 * i);
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const uint4 v = ldg128u(a.emb + emb_tile_word(el, 1, c8));
+                    ev[4 * c8] = v.x; ev[4 * c8 + 1] = v.y; ev[4 * c8 + 2] = v.z; ev[4 * c8 + 3] = v.w;
+                }
             }
             // accumulator pre-load: 4096 (P_t[target] + P_s[source]); P_s from the staged rows
             const float* Ps = ps + (size_t)b * TM * H + row * H;
@@ -568,17 +574,20 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
 // fp32 edge embedding (E, 64) -> pre-split fp16 rows [hi 64 | lo 64], values x 16  (until the edge encoder writes them itself)
 // ---------------------------------------------------------------------------------------------
 __global__ void emb_split_f16_kernel(const float* __restrict__ emb, uint32_t* __restrict__ out, long long n_rows) {
-    const long long total = n_rows * 8;       // one thread per 8 values
+    const long long n_tiles = (n_rows + 127) >> 7;
+    const long long total = n_tiles * 1024;       // one thread per (edge, chunk of 8 values); the edge index runs fastest: coalesced image writes
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i >> 3;
-        const int c8 = (int)(i & 7);
-        float2 v[4];
-        ldg256(emb + r * 64 + c8 * 8, v[0], v[1], v[2], v[3]);
-        uint32_t hi[4], lo[4];
+        const long long r = (i >> 10) * 128 + (i & 127);
+        const int c8 = (int)((i >> 7) & 7);
+        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+        if (r < n_rows) {
+            float2 v[4];
+            ldg256(emb + r * 64 + c8 * 8, v[0], v[1], v[2], v[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) f16::split(make_float2(v[k].x * f16::A_SCALE, v[k].y * f16::A_SCALE), hi[k], lo[k]);
-        *reinterpret_cast<uint4*>(out + r * 64 + c8 * 4) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(out + r * 64 + 32 + c8 * 4) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int k = 0; k < 4; ++k) f16::split(make_float2(v[k].x * f16::A_SCALE, v[k].y * f16::A_SCALE), hi[k], lo[k]);
+        }
+        *reinterpret_cast<uint4*>(out + emb_tile_word(r, 0, c8)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(out + emb_tile_word(r, 1, c8)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -604,7 +613,7 @@ static int g_f16_profile = 0;
 bool mp_f16_supported(const ConvDims& d) { return g_f16_fwd && d.cn == 64 && d.ce == 64 && d.h == 128; }
 int mp_f16_passes() { return g_f16_passes; }
 size_t mp_f16_pack_floats(const ConvDims& d) { return (d.cn == 64 && d.ce == 64 && d.h == 128) ? (size_t)(2 * mpf::W1_WORDS + 2 * mpf::W2_WORDS) : 0; }
-size_t mp_f16_emb_words(int n_edges) { return (size_t)(n_edges > 0 ? n_edges : 1) * 64; }
+size_t mp_f16_emb_words(int n_edges) { return (size_t)((n_edges > 0 ? n_edges : 1) + 127) / 128 * EMB_TILE_WORDS; }     // whole tiles
 
 int mp_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream) {
     if (mp_f16_pack_floats(d) == 0) return RGNN_OK;
@@ -629,7 +638,7 @@ int pack_f16_image(const float* W, int ldw, int K, int N, int n_valid, int k_val
 
 int mp_f16_split_emb(const float* emb, int n_edges, uint32_t* out, cudaStream_t stream) {
     if (n_edges <= 0) return RGNN_OK;
-    const long long total = (long long)n_edges * 8;
+    const long long total = (((long long)n_edges + 127) / 128) * 1024;
     long long blocks = (total + 255) / 256;
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
     emb_split_f16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(emb, out, n_edges);

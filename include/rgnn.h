@@ -195,11 +195,14 @@ int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* 
  * agg[t] = sum over edges s->t of msg(x_t, x_s, e); proj = the hoisted node projections written by
  * rgnn_conv_block_fwd (or by the previous block).  This is the dominant kernel of the forward; bench.py times it. */
 int rgnn_conv_edges_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* e, const float* proj, float* agg, void* stream);
-/* The fp16-split message kernel (csrc/rgnn_mp_f16.cu) reads the edge embedding PRE-SPLIT: per edge 64 32-bit words
- * = [hi: 64 fp16 | lo: 64 fp16] of 16 x the embedding (hi = fp16(16 e), lo = fp16(16 e - hi); 256 bytes per edge like the
- * fp32 row).  The embedding is produced once per forward and read by every conv block, so it is split once.
- * rgnn_split_edge_embedding: e (n_edges, 64) fp32, target-major -> e_split (n_edges * 64 words).
+/* The fp16-split message kernels (csrc/rgnn_mp_f16.cu, rgnn_mp_bwd_f16.cu) read the edge embedding PRE-SPLIT and TILED: per
+ * edge 64 fp16 hi + 64 fp16 lo values of 16 x the embedding (hi = fp16(16 e), lo = fp16(16 e - hi); 256 bytes per edge like the
+ * fp32 row), stored per tile of 128 edges as one 32 KB block [hi | lo][chunk of 8 channels][edge][8 fp16] (the chunk-major operand
+ * image of the tile: coalesced for row-owning threads, one bulk copy per image).  The embedding is produced once per forward and
+ * read by every conv block, so it is split once.  The buffer holds WHOLE tiles: rgnn_split_edge_embedding_words(n_edges) 32-bit words.
+ * rgnn_split_edge_embedding: e (n_edges, 64) fp32, target-major -> e_split.
  * rgnn_conv_edges_f16_fwd: rgnn_conv_edges_fwd on the split rows (64 / 64 / 128 channel plan; other plans return an error). */
+size_t rgnn_split_edge_embedding_words(int n_edges);
 int rgnn_split_edge_embedding(const float* e, int n_edges, void* e_split, void* stream);
 int rgnn_conv_edges_f16_fwd(const rgnn_conv* blk, const rgnn_graph* g, const void* e_split, const float* proj, float* agg,
                             void* stream);

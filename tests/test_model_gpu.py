@@ -175,7 +175,7 @@ def test_conv_layer_entry_points_match_oracle(ckpt_state_dict):
     g = gb.c_struct()
     # the kernels work in target-major order: row k of the embedding belongs to edge perm[k] of the caller's list
     emb_tm = emb.cuda()[gb.perm.long()].contiguous()
-    es = torch.empty(e * 64, dtype=torch.int32, device='cuda')
+    es = torch.empty(lib().rgnn_split_edge_embedding_words(e), dtype=torch.int32, device='cuda')
     check(lib().rgnn_split_edge_embedding(ptr(emb_tm), e, ptr(es), stream_ptr()), 'split')
     # projection of layer 3 from x (through the stand-alone block API), then the layer entry
     proj = torch.empty(n, 256, device='cuda')

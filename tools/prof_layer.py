@@ -81,7 +81,7 @@ def main():
         table.refill(None)
         check(lib().rgnn_pack_detector(C.byref(table.det), stream_ptr()), 'pack')
         e = torch.randn(E, 64, device=dev)
-        es = torch.empty(E * 64, dtype=torch.int32, device=dev)
+        es = torch.empty(lib().rgnn_split_edge_embedding_words(E), dtype=torch.int32, device=dev)
         check(lib().rgnn_split_edge_embedding(ptr(e), E, ptr(es), stream_ptr()), 'split')
         agg = torch.empty(N, 64, device=dev)
         proj = torch.randn(N, 256, device=dev)
