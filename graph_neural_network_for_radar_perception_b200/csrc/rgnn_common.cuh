@@ -17,6 +17,8 @@ constexpr float LEAKY = 0.01f;        // reference modules/neural_net/constants.
 
 void set_error(const char* fmt, ...);
 int sm_count();          // of the CURRENT device
+int graph_set_option(const char* name, int value);     // rgnn_graph.cu ("knn_grid")
+int graph_get_option(const char* name);
 
 // Per-device one-time setup at a launch site (cudaFuncSetAttribute is a per-device setting): `needed()` is true until
 // `mark()` has run on the current device.  The attribute calls are idempotent, so two threads racing through the same

@@ -175,6 +175,189 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// phase A with a uniform grid: the same exact result (k + 1 nearest by (d2, index), radius count), candidates from the cells
+// around the query instead of the whole frame.
+//   cell_sort_kernel (one CTA per frame): bounding box -> square cells (about 8 points per cell, at most 32 x 32) -> counting
+//   sort of the frame's points by cell; a sorted entry is {x, y, local index} (16 bytes: one load per candidate).
+//   knn_grid_kernel: a thread owns a query (taken in SORTED order, so the lanes of a warp sit in the same or adjacent cells and
+//   read the same candidates: broadcast loads) and visits the cells ring by ring.  After ring r every point outside the
+//   (2r+1) x (2r+1) block is at least `bound` away (distance to the nearest side of the block that is not the grid's border); the
+//   search stops when the worst kept candidate and the radius both lie strictly inside bound (less 1e-4 of a cell, which covers the
+//   float rounding of the cell assignment and of d2).  The distance is the reference's fl(fl(dx^2) + fl(dy^2)) and the kept list is
+//   ordered by (d2, index) with an explicit index tie-break, so the result is bit-identical to the brute-force kernel whatever the
+//   order in which candidates are visited.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRID_MAXN = 32;
+constexpr int GRID_CELLS = GRID_MAXN * GRID_MAXN;
+struct FrameGrid { float x0, y0, cell, inv_cell; int nx, ny, pad0, pad1; };
+
+__device__ __forceinline__ int grid_coord(float v, float v0, float inv_cell, int n) {
+    const float t = (v - v0) * inv_cell;
+    int c = t > 0.f ? (t < (float)n ? (int)t : n - 1) : 0;      // (a NaN position lands in cell 0)
+    return c;
+}
+
+__global__ void __launch_bounds__(256) cell_sort_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                        const int* __restrict__ frame_ptr, FrameGrid* __restrict__ grids,
+                                                        int* __restrict__ cell_start, float4* __restrict__ sorted) {
+    __shared__ int cnt[GRID_CELLS + 1];
+    __shared__ int cur[GRID_CELLS];
+    __shared__ float red[4][8];
+    __shared__ FrameGrid gsh;
+    const int f = blockIdx.x;
+    const int f0 = frame_ptr[f], nf = frame_ptr[f + 1] - f0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
+    for (int i = tid; i < nf; i += 256) {
+        const float x = px[f0 + i], y = py[f0 + i];
+        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (lane == 0) { red[0][warp] = xmin; red[1][warp] = xmax; red[2][warp] = ymin; red[3][warp] = ymax; }
+    for (int i = tid; i <= GRID_CELLS; i += 256) cnt[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            xmin = fminf(xmin, red[0][w]); xmax = fmaxf(xmax, red[1][w]); ymin = fminf(ymin, red[2][w]); ymax = fmaxf(ymax, red[3][w]);
+        }
+        int n = (int)ceilf(sqrtf((float)nf * 0.125f));
+        n = n < 1 ? 1 : (n > GRID_MAXN ? GRID_MAXN : n);
+        const float w = xmax - xmin, h = ymax - ymin;
+        float cell = fmaxf(w, h) / (float)n;
+        if (!(cell > 1e-12f) || !(cell < 1e30f)) cell = 1.f;      // all points coincide (or non-finite input): one column of cells
+        cell *= 1.0001f;
+        FrameGrid g;
+        g.x0 = xmin; g.y0 = ymin; g.cell = cell; g.inv_cell = 1.f / cell;
+        g.nx = min(n, (int)(w * g.inv_cell) + 1);
+        g.ny = min(n, (int)(h * g.inv_cell) + 1);
+        if (g.nx < 1) g.nx = 1;
+        if (g.ny < 1) g.ny = 1;
+        g.pad0 = g.pad1 = 0;
+        gsh = g;
+        grids[f] = g;
+    }
+    __syncthreads();
+    const FrameGrid g = gsh;
+    const int ncell = g.nx * g.ny;
+    for (int i = tid; i < nf; i += 256) {
+        const int c = grid_coord(py[f0 + i], g.y0, g.inv_cell, g.ny) * g.nx + grid_coord(px[f0 + i], g.x0, g.inv_cell, g.nx);
+        atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {        // exclusive scan of <= 1024 counters by one warp: 32 per lane, then a warp scan of the lane totals
+        int base = lane * 32, tot = 0;
+        for (int k = 0; k < 32; ++k) tot += (base + k < ncell) ? cnt[base + k] : 0;
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - tot;
+        for (int k = 0; k < 32; ++k) {
+            if (base + k < ncell) {
+                const int c = cnt[base + k];
+                cnt[base + k] = run;
+                cur[base + k] = run;
+                run += c;
+            }
+        }
+        if (lane == 31) cnt[ncell] = nf;
+    }
+    __syncthreads();
+    for (int i = tid; i <= ncell; i += 256) cell_start[(size_t)f * (GRID_CELLS + 1) + i] = cnt[i];
+    for (int i = tid; i < nf; i += 256) {
+        const float x = px[f0 + i], y = py[f0 + i];
+        const int c = grid_coord(y, g.y0, g.inv_cell, g.ny) * g.nx + grid_coord(x, g.x0, g.inv_cell, g.nx);
+        const int pos = atomicAdd(&cur[c], 1);
+        sorted[f0 + pos] = make_float4(x, y, __int_as_float(i), 0.f);
+    }
+}
+
+template <int KCAP>
+__global__ void __launch_bounds__(KNN_THREADS) knn_grid_kernel(const float4* __restrict__ sorted, const int* __restrict__ frame_ptr,
+                                                               const FrameGrid* __restrict__ grids, const int* __restrict__ cell_start,
+                                                               float eps2, int knn, int ks, int* __restrict__ knn_idx,
+                                                               int* __restrict__ degree) {
+    const int f = blockIdx.y;
+    const int f0 = frame_ptr[f], nf = frame_ptr[f + 1] - f0;
+    const int sp = blockIdx.x * KNN_THREADS + threadIdx.x;
+    if (sp >= nf) return;
+    const FrameGrid g = grids[f];
+    const int* __restrict__ cs = cell_start + (size_t)f * (GRID_CELLS + 1);
+    const float4* __restrict__ pts = sorted + f0;
+    const float4 me = pts[sp];
+    const float xi = me.x, yi = me.y;
+    const int li = __float_as_int(me.z);
+    const int cx = grid_coord(xi, g.x0, g.inv_cell, g.nx), cy = grid_coord(yi, g.y0, g.inv_cell, g.ny);
+    float bd[KCAP];
+    int bj[KCAP];
+#pragma unroll
+    for (int q = 0; q < KCAP; ++q) { bd[q] = FLT_MAX; bj[q] = INT_MAX; }
+    int deg = -1;
+    auto before = [](float d, int j, float d2, int j2) { return d < d2 || (d == d2 && j < j2); };
+    auto visit_span = [&](int p0, int p1) {
+        for (int p = p0; p < p1; ++p) {
+            const float4 c = __ldg(pts + p);
+            const int j = __float_as_int(c.z);
+            const float d = dist2(xi, yi, c.x, c.y);
+            deg += d <= eps2 ? 1 : 0;
+            if (before(d, j, bd[KCAP - 1], bj[KCAP - 1])) {
+#pragma unroll
+                for (int q = KCAP - 1; q > 0; --q) {
+                    if (before(d, j, bd[q - 1], bj[q - 1])) { bd[q] = bd[q - 1]; bj[q] = bj[q - 1]; }
+                    else if (before(d, j, bd[q], bj[q])) { bd[q] = d; bj[q] = j; }
+                }
+                if (before(d, j, bd[0], bj[0])) { bd[0] = d; bj[0] = j; }
+            }
+        }
+    };
+    const float slack = 1e-4f * g.cell;
+    for (int r = 0;; ++r) {
+        const int xlo = max(cx - r, 0), xhi = min(cx + r, g.nx - 1);
+        for (int dy = -r; dy <= r; ++dy) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= g.ny) continue;
+            if (dy == -r || dy == r) {
+                visit_span(cs[yy * g.nx + xlo], cs[yy * g.nx + xhi + 1]);       // a whole row of the block: contiguous in the sorted order
+            } else {
+                if (cx - r >= 0) visit_span(cs[yy * g.nx + cx - r], cs[yy * g.nx + cx - r + 1]);
+                if (cx + r < g.nx) visit_span(cs[yy * g.nx + cx + r], cs[yy * g.nx + cx + r + 1]);
+            }
+        }
+        const bool open_l = cx - r > 0, open_r = cx + r < g.nx - 1, open_d = cy - r > 0, open_u = cy + r < g.ny - 1;
+        if (!(open_l || open_r || open_d || open_u)) break;         // the block covers the whole grid
+        float bound = FLT_MAX;
+        if (open_l) bound = fminf(bound, xi - (g.x0 + (float)(cx - r) * g.cell));
+        if (open_r) bound = fminf(bound, (g.x0 + (float)(cx + r + 1) * g.cell) - xi);
+        if (open_d) bound = fminf(bound, yi - (g.y0 + (float)(cy - r) * g.cell));
+        if (open_u) bound = fminf(bound, (g.y0 + (float)(cy + r + 1) * g.cell) - yi);
+        bound -= slack;
+        if (bound > 0.f) {
+            const float b2 = bound * bound * 0.9999f;
+            if (bd[KCAP - 1] < b2 && eps2 < b2) break;
+        }
+    }
+    const int gi = f0 + li;
+    degree[gi] = max(deg, 0);
+    const int kp1 = knn >= nf ? nf : knn + 1;
+#pragma unroll
+    for (int q = 0; q < KCAP; ++q)
+        if (q < ks) knn_idx[(size_t)gi * ks + q] = (q < kp1) ? f0 + bj[q] : -1;
+}
+
+static int g_knn_grid = 1;
+int graph_set_option(const char* name, int value) {
+    if (strcmp(name, "knn_grid") == 0 && (value == 0 || value == 1)) { g_knn_grid = value; return 1; }
+    return 0;
+}
+int graph_get_option(const char* name) { return strcmp(name, "knn_grid") == 0 ? g_knn_grid : -2; }
+
+// ---------------------------------------------------------------------------------------------
 // phase B: symmetrise.  row(i) = (kNN(i) \ {i})  U  {j : i in kNN(j)}   [U radius(i) for _v2]
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_list(const int* __restrict__ lst, int n, int v) {
@@ -426,11 +609,11 @@ static int knn_stride(int knn) { return knn + 1; }
 
 using namespace rgnn;
 
-// workspace: knn_idx (n*ks) | own (n) | extra (n) | total (n) | cursor (n) | scan ws
+// workspace: knn_idx (n*ks) | own (n) | extra (n) | total (n) | cursor (n) | scan ws | cell-sorted points (n) | frame grids | cell starts
 extern "C" size_t rgnn_graph_build_workspace_bytes(int n_points, int n_frames, int knn) {
-    (void)n_frames;
     const size_t n = (size_t)n_points;
-    return align256(n * knn_stride(knn) * 4) + 4 * align256(n * 4) + align256(scan_ws_ints(n_points) * 4) + 256;
+    return align256(n * knn_stride(knn) * 4) + 4 * align256(n * 4) + align256(scan_ws_ints(n_points) * 4) + 256 +
+           align256(n * sizeof(float4)) + align256((size_t)n_frames * sizeof(FrameGrid)) + align256((size_t)n_frames * (GRID_CELLS + 1) * 4);
 }
 
 extern "C" int rgnn_graph_build(const float* px, const float* py, const int32_t* frame_ptr_dev,
@@ -456,10 +639,20 @@ extern "C" int rgnn_graph_build(const float* px, const float* py, const int32_t*
     int* extra = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
     int* total = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
     int* cursor = reinterpret_cast<int*>(w); w += align256((size_t)n_points * 4);
-    int* scan_ws = reinterpret_cast<int*>(w);
+    int* scan_ws = reinterpret_cast<int*>(w); w += align256(scan_ws_ints(n_points) * 4) + 256;
+    float4* sorted = reinterpret_cast<float4*>(w); w += align256((size_t)n_points * sizeof(float4));
+    FrameGrid* grids = reinterpret_cast<FrameGrid*>(w); w += align256((size_t)n_frames * sizeof(FrameGrid));
+    int* cell_start = reinterpret_cast<int*>(w);
 
     const dim3 grid_a((max_nf + KNN_THREADS - 1) / KNN_THREADS, n_frames);
-    if (ks <= 12) knn_kernel<12><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
+    if (g_knn_grid && max_nf > 4 * (knn + 1)) {
+        // uniform grid per frame: the same result from ~10 x (k + 1) candidates per query instead of the whole frame
+        cell_sort_kernel<<<n_frames, 256, 0, stream>>>(px, py, frame_ptr_dev, grids, cell_start, sorted);
+        if (ks <= 12) knn_grid_kernel<12><<<grid_a, KNN_THREADS, 0, stream>>>(sorted, frame_ptr_dev, grids, cell_start, eps2, knn, ks, knn_idx, degree);
+        else if (ks <= 20) knn_grid_kernel<20><<<grid_a, KNN_THREADS, 0, stream>>>(sorted, frame_ptr_dev, grids, cell_start, eps2, knn, ks, knn_idx, degree);
+        else if (ks <= 36) knn_grid_kernel<36><<<grid_a, KNN_THREADS, 0, stream>>>(sorted, frame_ptr_dev, grids, cell_start, eps2, knn, ks, knn_idx, degree);
+        else knn_grid_kernel<68><<<grid_a, KNN_THREADS, 0, stream>>>(sorted, frame_ptr_dev, grids, cell_start, eps2, knn, ks, knn_idx, degree);
+    } else if (ks <= 12) knn_kernel<12><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
     else if (ks <= 20) knn_kernel<20><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
     else if (ks <= 36) knn_kernel<36><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);
     else knn_kernel<68><<<grid_a, KNN_THREADS, 0, stream>>>(px, py, frame_ptr_dev, eps2, knn, ks, knn_idx, degree);

@@ -526,7 +526,6 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                         if (!did) { if (t0 == 0) t0 = clock64(); }
                         else if (t0 != 0) { idle += clock64() - t0; t0 = 0; }
                     }
-                    if (!did) __nanosleep(20);
                 }
                 if (PROFILE && a.prof != nullptr) a.prof[(blockIdx.x * 20 + warp) * 4] = idle;
             }

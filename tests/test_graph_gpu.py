@@ -127,3 +127,45 @@ def test_large_frame_properties():
     assert perm.min() >= 0 and np.array_equal(ei[0][perm], ei[1])          # symmetric
     deg_out = np.bincount(ei[0], minlength=20000)
     assert deg_out.min() >= 10
+
+
+@pytest.mark.parametrize('kind', ['lattice', 'blobs', 'line', 'identical', 'mixed_sizes'])
+def test_grid_knn_is_bit_identical_to_brute_force(kind):
+    """The uniform-grid kNN (cell_sort_kernel + knn_grid_kernel) must give exactly the brute-force kernel's graph, including its
+    (d2, index) order among EXACT distance ties (integer lattice, coincident points), for points crowded into a few cells (tight
+    blobs, a line) and for a batch that mixes tiny and large frames; knn and the radius vary."""
+    from graph_neural_network_for_radar_perception_b200._cabi import check, lib
+    rng = np.random.default_rng(5)
+
+    def frame(x, y):
+        d, _ = synth.make_frame(1, len(x))
+        d = dict(d)
+        d['meas_px'] = np.asarray(x, dtype=np.float32)
+        d['meas_py'] = np.asarray(y, dtype=np.float32)
+        return d
+    if kind == 'lattice':
+        gx, gy = np.meshgrid(np.arange(40), np.arange(30))
+        frames = [frame(gx.ravel() * 2.5, gy.ravel() * 2.5 - 37.0), frame(gx.ravel()[:700] * 1.0, gy.ravel()[:700] * 1.0)]
+    elif kind == 'blobs':
+        c = rng.uniform(0, 100, size=(6, 2))
+        p = c[rng.integers(0, 6, 2500)] + rng.normal(0, 0.05, size=(2500, 2))
+        frames = [frame(p[:, 0], p[:, 1] - 50), frame(rng.uniform(0, 100, 1500), rng.uniform(-50, 50, 1500))]
+    elif kind == 'line':
+        t = rng.uniform(0, 100, 1800)
+        frames = [frame(t, np.full_like(t, 3.0)), frame(np.full_like(t, 7.0), t - 50)]
+    elif kind == 'identical':
+        frames = [frame(np.full(600, 12.5), np.full(600, -3.25)), frame(rng.uniform(0, 1e-3, 900), rng.uniform(0, 1e-3, 900))]
+    else:
+        frames = [frame(rng.uniform(0, 100, n), rng.uniform(-50, 50, n)) for n in (5, 3000, 47, 1, 900)]
+    pts, fp = gf.frames_to_device(frames)
+    for knn, eps, union in ((10, 25.0, False), (16, 4.0, True), (64, 100.0, False)):
+        out = {}
+        for mode in (1, 0):
+            check(lib().rgnn_set_option(b'knn_grid', mode), 'opt')
+            try:
+                bf = gf.build_graph_batch(pts, fp, eps, knn, union_radius=union, with_features=False)
+                out[mode] = (bf.edge_index().cpu().numpy(), bf.degree.cpu().numpy())
+            finally:
+                check(lib().rgnn_set_option(b'knn_grid', 1), 'opt')
+        assert np.array_equal(out[1][0], out[0][0]), (kind, knn)
+        assert np.array_equal(out[1][1], out[0][1]), (kind, knn)
