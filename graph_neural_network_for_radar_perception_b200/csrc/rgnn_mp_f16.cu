@@ -155,39 +155,45 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
             float k, sh, mean;
             if (norm1) {
-                // sweep 1: statistics on the 4096-fold values (power-of-two scaling is exact; sigma and eps scale along)
+                // sweep 1: statistics on the 4096-fold values (power-of-two scaling is exact; sigma and eps scale along).  Each group
+                // takes ITS two 32-column chunks (the ones it rewrites in sweep 2); the two partial (mean, M2) pairs meet in four
+                // columns of the emb operand's region -- dead since GEMM1 completed, rewritten by the F role only after GEMM2 of this
+                // tile -- and are merged with the exact pairwise update.  The barrier is the one the in-place stores need anyway.
                 RowStats st;
                 st.init();
                 float2 va[16], vb[16];
-                tc::tmem_ld16(d1, va);
-                tc::tmem_ld16(d1 + 16, va + 8);
+                tc::tmem_ld16(d1 + 32 * g, va);
+                tc::tmem_ld16(d1 + 32 * g + 16, va + 8);
+                tc::tmem_ld16(d1 + 32 * g + 64, vb);
+                tc::tmem_ld16(d1 + 32 * g + 80, vb + 8);
                 tc::tmem_wait_ld();
-#pragma unroll 1
-                for (int c = 0; c < H; c += 64) {
-                    tc::tmem_ld16(d1 + c + 32, vb);         // the next chunk's load runs under this chunk's arithmetic
-                    tc::tmem_ld16(d1 + c + 48, vb + 8);
-                    st.add_chunk(va);
-                    tc::tmem_wait_ld();
-                    if (c + 64 < H) {
-                        tc::tmem_ld16(d1 + c + 64, va);
-                        tc::tmem_ld16(d1 + c + 80, va + 8);
-                    }
-                    st.add_chunk(vb);
-                    tc::tmem_wait_ld();
-                }
-                const float sd = st.sigma(H);
+                st.add_chunk(va);
+                st.add_chunk(vb);
+                const uint32_t xc = t_row + COL_EMB + (uint32_t)b * 64;
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(xc + 2 * g), "f"(st.mean), "f"(st.m2) : "memory");
+                tc::tmem_wait_st();
+                if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
+                tc::tc_fence_before();
+                group_sync(BAR_E1, 256);           // the other group has read its columns: in-place stores may begin; partials are visible
+                tc::tc_fence_after();
+                float m0, q0s, m1, q1s;
+                tc::tmem_ld4(xc, m0, q0s, m1, q1s);
+                tc::tmem_wait_ld();
+                const float dm = m1 - m0;
+                mean = 0.5f * (m0 + m1);
+                const float m2 = (q0s + q1s) + dm * dm * (float)(H / 4);      // n_a n_b / n = 64 * 64 / 128
+                const float sd = __fsqrt_rn(m2 * (1.f / (float)(H - 1)));
                 k = f16::A_SCALE * s1v * __frcp_rn(sd + eps_s);
                 sh = f16::A_SCALE * m1v;
-                mean = st.mean;
             } else {
                 k = f16::A_SCALE * f16::D_UNSCALE;
                 sh = 0.f;
                 mean = 0.f;
+                if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
+                tc::tc_fence_before();
+                group_sync(BAR_E1, 256);
+                tc::tc_fence_after();
             }
-            if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
-            tc::tc_fence_before();
-            group_sync(BAR_E1, 256);           // the other group has read every column: in-place stores may begin
-            tc::tc_fence_after();
             const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean, -mean);
             const bool act = a.act1 != 0;
             // sweep 2 (this group's chunks g and g + 2): y1 x 16 = act(k (z - mean) + sh) -> fp16 hi | lo, IN PLACE: the 32 fp32
