@@ -112,6 +112,14 @@ int run_conv_edges_bwd_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_gra
                            const int* slist, cudaStream_t stream);
 int mp_bwd_f16_set_option(const char* name, int value);
 int mp_bwd_f16_get_option(const char* name);
+// fixed-shape fp16-split node-level backward with fused weight gradients (rgnn_node_bwd_f16.cu)
+bool node_bwd_f16_supported(const rgnn_conv& c, const ConvDims& d);
+int run_proj_bwd_f16(const rgnn_conv& c, const ConvDims& d, const float* dP, const float* x, int n_nodes, float* dx, float* scalar,
+                     cudaStream_t stream);
+int run_upd_bwd_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, const float* u, const float* sd,
+                    float* dx, float* dagg, float* scalar, cudaStream_t stream);
+int node_bwd_f16_set_option(const char* name, int value);
+int node_bwd_f16_get_option(const char* name);
 // source-major index of the target-major edge list (edge positions grouped by source node), built once per backward call
 size_t src_index_ints(int n_nodes, int n_edges);
 int build_src_index(const rgnn_graph& g, int* ws, const int** sptr_out, const int** slist_out, cudaStream_t stream);

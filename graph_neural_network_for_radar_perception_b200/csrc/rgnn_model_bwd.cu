@@ -296,7 +296,11 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     if (tc_edges && (rc = build_src_index(g, pl.sidx, &sptr, &slist, stream))) return rc;
     for (int l = L - 1; l >= 0; --l) {
         const bool has_next = l + 1 < L;
-        if (pl.conv_tc_bwd) {
+        if (pl.conv_tc_bwd && pl.cscr != nullptr && node_bwd_f16_supported(net.conv[l], d)) {
+            // fixed-shape fp16-split kernels with the weight gradients fused in (rgnn_node_bwd_f16.cu); cscr[0] holds max |gradient|
+            if (has_next && (rc = run_proj_bwd_f16(net.conv[l + 1], d, pl.dP, pl.x[l + 1], N, pl.dx, pl.cscr, stream))) return rc;
+            rc = run_upd_bwd_f16(net.conv[l], d, N, pl.x[l], pl.agg[l], pl.u_save[l], pl.usd_save[l], pl.dx, pl.dagg, pl.cscr, stream);
+        } else if (pl.conv_tc_bwd) {
             if (has_next && (rc = tc_proj_bwd(net.conv[l + 1], d, pl.dP, pl.x[l + 1], N, pl.dx, stream))) return rc;
             rc = tc_conv_nodes_bwd(net.conv[l], d, N, pl.x[l], pl.agg[l], pl.u_save[l], pl.usd_save[l], pl.dx, pl.dagg, pl.cscr, stream);
         } else {
@@ -314,7 +318,9 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     }
     // ---- node encoder (receives dL/dx_0 and the projection gradient of layer 0) ----
     if (pl.node_tc_bwd[0]) {
-        if ((rc = tc_proj_bwd(net.conv[0], d, pl.dP, pl.x[0], N, pl.dx, stream))) return rc;
+        if (pl.conv_tc_bwd && pl.cscr != nullptr && node_bwd_f16_supported(net.conv[0], d)) {
+            if ((rc = run_proj_bwd_f16(net.conv[0], d, pl.dP, pl.x[0], N, pl.dx, pl.cscr, stream))) return rc;
+        } else if ((rc = tc_proj_bwd(net.conv[0], d, pl.dP, pl.x[0], N, pl.dx, stream))) return rc;
         if ((rc = tc_stack_bwd(net.node_enc, pl.node_save[0], node_features, nullptr, pl.x[0], pl.dx, N, pl.cscr, nullptr, 0, nullptr,
                                nullptr, stream)))
             return rc;

@@ -696,6 +696,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     if (name != nullptr && mp_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && mp_bwd_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && graph_set_option(name, value)) return RGNN_OK;
+    if (name != nullptr && node_bwd_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && chain_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && edge_enc_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && strcmp(name, "debug") == 0) { g_debug = value; g_rowmlp_profile = (value & 8) != 0; return RGNN_OK; }
@@ -712,6 +713,7 @@ extern "C" int rgnn_get_option(const char* name) {
     if (name != nullptr && mp_f16_get_option(name) != -2) return mp_f16_get_option(name);
     if (name != nullptr && mp_bwd_f16_get_option(name) != -2) return mp_bwd_f16_get_option(name);
     if (name != nullptr && graph_get_option(name) != -2) return graph_get_option(name);
+    if (name != nullptr && node_bwd_f16_get_option(name) != -2) return node_bwd_f16_get_option(name);
     if (name != nullptr && chain_f16_get_option(name) != -2) return chain_f16_get_option(name);
     if (name != nullptr && edge_enc_f16_get_option(name) != -2) return edge_enc_f16_get_option(name);
     return -1;

@@ -103,6 +103,20 @@ def test_training_step_matches_oracle_autograd_all_parameters(ckpt_state_dict):
     ys.check(got, what='ragged 3-frame batch, trained checkpoint')
 
 
+def test_training_step_with_the_round1_backward_kernels(ckpt_state_dict):
+    """The kernels the fused fp16-split backward replaced stay selectable (rgnn_set_option f16_bwd / f16_node_bwd = 0: 3xTF32
+    message backward + weight-gradient GEMMs, row-MLP interpreter for the node-sized halves) and are held to the same yardstick."""
+    from graph_neural_network_for_radar_perception_b200._cabi import check, lib
+    try:
+        check(lib().rgnn_set_option(b'f16_bwd', 0), 'opt')
+        check(lib().rgnn_set_option(b'f16_node_bwd', 0), 'opt')
+        ys, got = _train_case(ckpt_state_dict, (90, 7, 161), 700)
+    finally:
+        check(lib().rgnn_set_option(b'f16_bwd', 1), 'opt')
+        check(lib().rgnn_set_option(b'f16_node_bwd', 1), 'opt')
+    ys.check(got, what='ragged 3-frame batch, round-1 backward kernels')
+
+
 def test_training_step_random_init_is_tight(ckpt_state_dict):
     """Random-init weights (seed 1234): gradients are not cancelling sums, the reference's noise floor is ~1e-6 of each
     tensor's maximum, so this case holds the CUDA backward to rtol 1e-4 almost everywhere and catches a systematic
