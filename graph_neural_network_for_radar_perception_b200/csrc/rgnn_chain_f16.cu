@@ -389,6 +389,8 @@ struct ConvNodesArgs {
     const uint32_t* w_ps;       // source half
     const float* b_p;           // msg.0 bias of the next block (rides on the target half) or nullptr
     float* P;                   // (N, 256)
+    float* u_save;              // training: the update's output before the residual (N, 64) and its sigma (N), or nullptr
+    float* sd_save;
     int passes;
 };
 
@@ -503,7 +505,9 @@ __global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const 
                 st.init();
                 st.add_chunk(va);
                 st.add_chunk(vb);
-                k = cst[64] * __frcp_rn(st.sigma(64) + NORM_EPS);
+                const float sd = st.sigma(64);
+                if (a.sd_save != nullptr && valid) a.sd_save[r] = sd;
+                k = cst[64] * __frcp_rn(sd + NORM_EPS);
                 sh = cst[65];
                 mean = st.mean;
             }
@@ -517,6 +521,17 @@ __global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const 
                     va[c].x = fmaxf(va[c].x, ta.x); va[c].y = fmaxf(va[c].y, ta.y);
                     vb[c].x = fmaxf(vb[c].x, tb.x); vb[c].y = fmaxf(vb[c].y, tb.y);
                 }
+            }
+            if (a.u_save != nullptr && valid) {        // a training step keeps the update's output for the backward (upd_bwd_f16_kernel)
+                float* o = a.u_save + (size_t)r * 64;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    stg256(o + 8 * i, va[4 * i], va[4 * i + 1], va[4 * i + 2], va[4 * i + 3]);
+                    stg256(o + 32 + 8 * i, vb[4 * i], vb[4 * i + 1], vb[4 * i + 2], vb[4 * i + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
                 va[c] = __fadd2_rn(va[c], xa[c]);       // identity residual
                 vb[c] = __fadd2_rn(vb[c], xb[c]);
             }
@@ -641,7 +656,7 @@ bool conv_nodes_f16_supported(const rgnn_conv& c, const ConvDims& d) {
 }
 
 int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
-                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream) {
+                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream, float* u_save, float* sd_save) {
     if (n_nodes <= 0) return RGNN_OK;
     (void)d;
     const rgnn_linear& L = c.upd.layer[0];
@@ -658,6 +673,7 @@ int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const
         a.b_p = next->msg.layer[0].bias;
         a.P = P_next;
     }
+    a.u_save = u_save; a.sd_save = sd_save;
     a.passes = mp_f16_passes();
     static PerDeviceOnce once;
     if (once.needed()) {

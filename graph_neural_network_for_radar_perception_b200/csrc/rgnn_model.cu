@@ -234,14 +234,17 @@ int run_conv_nodes(const rgnn_conv& c, int n_nodes, const float* x, const float*
                    const rgnn_conv* next, float* P_next, cudaStream_t stream, float* u_save = nullptr, float* sd_save = nullptr) {
     ConvDims d;
     if (!conv_dims(c, &d)) return RGNN_ERR_INVALID;
-    if (u_save == nullptr && sd_save == nullptr && conv_nodes_f16_supported(c, d)) {       // inference: fixed-shape fp16-split kernel
+    // fixed-shape fp16-split kernel; a training step has it leave the update's output and sigma behind when the fp16-split node
+    // backward will read them (the interpreter's backward wants the same two arrays, so either forward serves either backward)
+    if (conv_nodes_f16_supported(c, d) && ((u_save == nullptr && sd_save == nullptr) || node_bwd_f16_supported(c, d))) {
         if (next != nullptr) {
             ConvDims dn;
             if (!conv_dims(*next, &dn)) return RGNN_ERR_INVALID;
             RGNN_REQUIRE(dn.cn == d.cn && dn.h == d.h && dn.ce == d.ce, "conv blocks with different channel plans");
         }
         return run_conv_nodes_f16(c, d, n_nodes, x, agg, out, next,
-                                  next != nullptr ? next->msg.layer[0].weight_t + conv_msg0_proj16_offset(d) : nullptr, P_next, stream);
+                                  next != nullptr ? next->msg.layer[0].weight_t + conv_msg0_proj16_offset(d) : nullptr, P_next, stream,
+                                  u_save, sd_save);
     }
     if (tc_stack_supported(c.upd) && c.upd.n == 1 && (next == nullptr || tc_proj_supported(d))) {
         if (next != nullptr) {

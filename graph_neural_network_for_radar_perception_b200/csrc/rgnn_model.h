@@ -87,7 +87,8 @@ size_t conv_proj_f16_floats(const ConvDims& d);
 int conv_proj_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
 bool conv_nodes_f16_supported(const rgnn_conv& c, const ConvDims& d);
 int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, float* out,
-                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream);
+                       const rgnn_conv* next, const float* next_proj_images, float* P_next, cudaStream_t stream,
+                       float* u_save = nullptr, float* sd_save = nullptr);
 inline size_t conv_msg0_proj16_offset(const ConvDims& d);
 int chain_f16_set_option(const char* name, int value);
 int chain_f16_get_option(const char* name);
@@ -118,6 +119,9 @@ int run_proj_bwd_f16(const rgnn_conv& c, const ConvDims& d, const float* dP, con
                      cudaStream_t stream);
 int run_upd_bwd_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg, const float* u, const float* sd,
                     float* dx, float* dagg, float* scalar, cudaStream_t stream);
+bool chain64_bwd_f16_supported(const rgnn_stack& s);
+int run_chain64_bwd_f16(const rgnn_stack& s, const TcSave& save, const float* x_rows, const float* y_out, const float* g_top, int n_rows,
+                        float* dx, int dx_mode, const int* ia, const int* ib, float* scalar, cudaStream_t stream);
 int node_bwd_f16_set_option(const char* name, int value);
 int node_bwd_f16_get_option(const char* name);
 // source-major index of the target-major edge list (edge positions grouped by source node), built once per backward call

@@ -239,6 +239,8 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     // ---- heads: accumulate dL/dx_L in pl.dx ----
     // node-sized stack: tensor-core chain backward when the forward saved its activations, else the recompute tile program
     auto node_bwd = [&](int i, const rgnn_stack& s, const float* y_out, const float* g_top, bool accumulate) -> int {
+        if (pl.node_tc_bwd[i] && pl.cscr != nullptr && chain64_bwd_f16_supported(s))       // fixed-shape fp16-split chain with fused weight gradients
+            return run_chain64_bwd_f16(s, pl.node_save[i], xL, y_out, g_top, N, pl.dx, accumulate ? 1 : 0, nullptr, nullptr, pl.cscr, stream);
         if (pl.node_tc_bwd[i])
             return tc_stack_bwd(s, pl.node_save[i], xL, nullptr, y_out, g_top, N, pl.cscr, pl.dx, accumulate ? 1 : 0, nullptr, nullptr, stream);
         return stack_bwd(s, xL, nullptr, g_top, N, pl.dx, accumulate, stream);
@@ -246,7 +248,10 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     if ((rc = node_bwd(1, net.head_node, nullptr, g_node_cls, false))) return rc;
     if ((rc = node_bwd(2, net.head_offset, nullptr, g_node_off, true))) return rc;
     RGNN_CHECK_CUDA(cudaMemsetAsync(pl.dh, 0, (size_t)N * pl.link_w * sizeof(float), stream));
-    if (g.n_und > 0 && pl.link_tc_bwd) {
+    if (g.n_und > 0 && pl.link_tc_bwd && pl.cscr != nullptr && chain64_bwd_f16_supported(net.head_link)) {
+        if ((rc = run_chain64_bwd_f16(net.head_link, pl.link_save, nullptr, nullptr, g_link, g.n_und, pl.dh, 2, g.und_a, g.und_b, pl.cscr, stream)))
+            return rc;
+    } else if (g.n_und > 0 && pl.link_tc_bwd) {
         if ((rc = tc_stack_bwd(net.head_link, pl.link_save, nullptr, nullptr, nullptr, g_link, g.n_und, pl.cscr, pl.dh, 2, g.und_a,
                                g.und_b, stream)))
             return rc;
