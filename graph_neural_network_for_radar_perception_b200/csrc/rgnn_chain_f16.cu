@@ -38,6 +38,11 @@ struct Chain64Args {
     int act[C64_MAX_LAYERS];
     float* y;
     int ldy;
+    // a training step: what the backward (chain64_bwd_f16_kernel) reads back -- the assembled input rows (pair sums), the outputs of
+    // the hidden layers except the stack's own output, the sigmas (each nullable)
+    float* save_x;
+    float* save_y[C64_MAX_LAYERS];
+    float* save_sd[C64_MAX_LAYERS];
     int passes;
 };
 
@@ -133,6 +138,11 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __fadd2_rn(v[i], u[i]);
                     }
+                    if (a.save_x != nullptr && valid) {
+                        float* o = a.save_x + (size_t)r * W + c;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) stg256(o + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f16::split(valid ? __fmul2_rn(v[i], s16) : make_float2(0.f, 0.f), hi[i], lo[i]);
@@ -170,7 +180,9 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
                     st.init();
                     st.add_chunk(va);
                     st.add_chunk(vb);
-                    k = osc * cb[W] * __frcp_rn(st.sigma(W) + NORM_EPS);
+                    const float sd = st.sigma(W);
+                    if (a.save_sd[l] != nullptr && valid) a.save_sd[l][r] = sd;
+                    k = osc * cb[W] * __frcp_rn(sd + NORM_EPS);
                     sh = osc * cb[W + 1];
                     mean = st.mean;
                 }
@@ -196,6 +208,15 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
                         }
                     }
                 } else {
+                    if (a.save_y[l] != nullptr && valid) {      // the layer output at its true scale (the operand carries x 16)
+                        const float2 un = make_float2(1.f / f16::A_SCALE, 1.f / f16::A_SCALE);
+                        float* o = a.save_y[l] + (size_t)r * W;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            stg256(o + 8 * i, __fmul2_rn(va[4 * i], un), __fmul2_rn(va[4 * i + 1], un), __fmul2_rn(va[4 * i + 2], un), __fmul2_rn(va[4 * i + 3], un));
+                            stg256(o + 32 + 8 * i, __fmul2_rn(vb[4 * i], un), __fmul2_rn(vb[4 * i + 1], un), __fmul2_rn(vb[4 * i + 2], un), __fmul2_rn(vb[4 * i + 3], un));
+                        }
+                    }
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f16::split(va[i], hi[i], lo[i]);
@@ -334,7 +355,8 @@ bool chain64_supported(const rgnn_stack& s) {
 
 const float* f16_weights(const rgnn_linear& L);      // rgnn_model_tc.cu
 
-int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream) {
+int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream,
+                const TcSave* save) {
     if (n_rows <= 0) return RGNN_OK;
     Chain64Args a;
     memset(&a, 0, sizeof(a));
@@ -351,6 +373,10 @@ int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, con
         a.bias[l] = L.bias; a.scale[l] = L.norm_scale; a.shift[l] = L.norm_shift; a.act[l] = L.activation;
     }
     a.y = y; a.ldy = a.n_out;
+    if (save != nullptr) {
+        a.save_x = save->x_in;
+        for (int l = 0; l < a.n_hidden; ++l) { a.save_y[l] = (l + 1 < s.n) ? save->y[l] : nullptr; a.save_sd[l] = save->sd[l]; }
+    }
     a.passes = mp_f16_passes();
     static PerDeviceOnce once;
     if (once.needed()) {

@@ -161,7 +161,9 @@ struct FwdBuilder : ProgBuilder {
 int run_stack_fwd(const rgnn_stack& s, const float* x, int n_rows, float* y, cudaStream_t stream, const TcSave* save) {
     RGNN_REQUIRE(s.n >= 1 && s.n <= RGNN_MAX_STACK, "stack with %d layers", s.n);
     // inference (nothing to save for a backward): the fixed-shape fp16-split chain kernel
-    if (save == nullptr && chain64_supported(s)) return run_chain64(s, x, stack_in(s), nullptr, nullptr, n_rows, y, stream);
+    // (a training step passes `save`: the same kernel then leaves the layer outputs and sigmas behind for chain64_bwd_f16_kernel)
+    if (chain64_supported(s) && (save == nullptr || chain64_bwd_f16_supported(s)))
+        return run_chain64(s, x, stack_in(s), nullptr, nullptr, n_rows, y, stream, save);
     if (tc_stack_supported(s)) return tc_run_stack(s, x, nullptr, n_rows, y, stream, save);
     FwdBuilder b(n_rows, stack_maxw(s));
     b.load_rows(b.cur, x, stack_in(s), stack_in(s), 0, round_up(stack_in(s), 8));
@@ -393,8 +395,10 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
     if ((rc = run_stack_fwd(net.head_node, xL, N, node_cls, stream, sv(1)))) return rc;
     if ((rc = run_stack_fwd(net.head_offset, xL, N, node_off, stream, sv(2)))) return rc;
     if ((rc = run_stack_fwd(net.link_node, xL, N, pl.hlink, stream, sv(3)))) return rc;
-    if (g.n_und > 0 && !pl.link_tc_bwd && chain64_supported(net.head_link)) {
-        if ((rc = run_chain64(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream))) return rc;
+    if (g.n_und > 0 && chain64_supported(net.head_link) && (!pl.link_tc_bwd || chain64_bwd_f16_supported(net.head_link))) {
+        if ((rc = run_chain64(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream,
+                              pl.link_tc_bwd ? &pl.link_save : nullptr)))
+            return rc;
     } else if (g.n_und > 0 && tc_stack_supported(net.head_link)) {
         if ((rc = tc_run_pairsum_stack(net.head_link, pl.hlink, pl.link_w, g.und_a, g.und_b, g.n_und, link_cls, stream,
                                        pl.link_tc_bwd ? &pl.link_save : nullptr)))

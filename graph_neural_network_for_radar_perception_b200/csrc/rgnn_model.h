@@ -82,7 +82,8 @@ inline size_t conv_msg0_f16_offset(const ConvDims& d);
 size_t f16_image_floats(int in_features, int out_features);
 int f16_pack_linear(const rgnn_linear& L, float* dst, cudaStream_t stream);
 bool chain64_supported(const rgnn_stack& s);
-int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream);
+int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, const int* ib, int n_rows, float* y, cudaStream_t stream,
+                const TcSave* save = nullptr);
 size_t conv_proj_f16_floats(const ConvDims& d);
 int conv_proj_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t stream);
 bool conv_nodes_f16_supported(const rgnn_conv& c, const ConvDims& d);
