@@ -33,6 +33,8 @@ struct EdgeEncArgs {
     const float* s1; const float* m1; const float* s2; const float* m2; const float* s3; const float* m3;
     uint32_t* emb_hl;           // pre-split rows of 16 x the embedding, TILED (rgnn_f16.cuh: emb_tile_word)
     float* emb;                 // optional fp32 copy (E, 64) or nullptr
+    float* save_y1; float* save_y2;                         // training: outputs of layers 1 / 2 (E, 128) and the three sigmas (E), nullable
+    float* save_sd1; float* save_sd2; float* save_sd3;
     int passes;
 };
 
@@ -74,7 +76,8 @@ __device__ __forceinline__ void bulk_g2s_e(void* smem_dst, const void* gsrc, uin
 
 // norm + act + split of a 128- or 64-column accumulator that sits in TMEM at `dreg`, in place (A format), thread = row
 template <int C>
-__device__ __forceinline__ void enc_norm_epilogue(uint32_t dreg, const float* __restrict__ bias, bool has_norm, float gain, float shift, int np) {
+__device__ __forceinline__ void enc_norm_epilogue(uint32_t dreg, const float* __restrict__ bias, bool has_norm, float gain, float shift, int np,
+                                                  float* __restrict__ save_row = nullptr, float* __restrict__ save_sd = nullptr) {
     static_assert(C == 128 || C == 64, "chunks of 32 columns");
     const float2 us = make_float2(f16::D_UNSCALE, f16::D_UNSCALE);
     float k = f16::A_SCALE, sh = 0.f, mean = 0.f;
@@ -91,7 +94,9 @@ __device__ __forceinline__ void enc_norm_epilogue(uint32_t dreg, const float* __
             for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(v[i], us, *reinterpret_cast<const float2*>(bias + c + 2 * i));
             st.add_chunk(v);
         }
-        k = f16::A_SCALE * gain * __frcp_rn(st.sigma(C) + NORM_EPS);
+        const float sd = st.sigma(C);
+        if (save_sd != nullptr) *save_sd = sd;          // a training step keeps sigma and (below) the layer output for the backward
+        k = f16::A_SCALE * gain * __frcp_rn(sd + NORM_EPS);
         sh = f16::A_SCALE * shift;
         mean = st.mean;
     }
@@ -111,9 +116,16 @@ __device__ __forceinline__ void enc_norm_epilogue(uint32_t dreg, const float* __
             y.x = fmaxf(y.x, t.x);
             y.y = fmaxf(y.y, t.y);
             f16::split(y, hi[i], lo[i]);
+            v[i] = y;
         }
         f16::tmem_st16u(dreg + c, hi);
         if (np != 1) f16::tmem_st16u(dreg + c + 16, lo);
+        if (save_row != nullptr) {
+            const float2 un = make_float2(1.f / f16::A_SCALE, 1.f / f16::A_SCALE);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                stg256(save_row + c + 8 * i, __fmul2_rn(v[4 * i], un), __fmul2_rn(v[4 * i + 1], un), __fmul2_rn(v[4 * i + 2], un), __fmul2_rn(v[4 * i + 3], un));
+        }
     }
 }
 
@@ -244,7 +256,9 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
             tc::mbar_wait(&bars[B_D_FULL + g], n_d & 1u);
             ++n_d;
             tc::tc_fence_after();
-            enc_norm_epilogue<C1>(d1r, cst + CST_B1, n1, cst[CST_S], cst[CST_S + 1], np);
+            enc_norm_epilogue<C1>(d1r, cst + CST_B1, n1, cst[CST_S], cst[CST_S + 1], np,
+                                  (valid && a.save_y1 != nullptr) ? a.save_y1 + (size_t)r * C1 : nullptr,
+                                  (valid && a.save_sd1 != nullptr) ? a.save_sd1 + r : nullptr);
             tc::tmem_wait_st();
             tc::tc_fence_before();
             { warp_arrive(&bars[B_A_FULL + 2 * g + (n_arr & 1u)], lane); ++n_arr; }
@@ -252,7 +266,9 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
             tc::mbar_wait(&bars[B_D_FULL + g], n_d & 1u);
             ++n_d;
             tc::tc_fence_after();
-            enc_norm_epilogue<C2>(d0r[0], cst + CST_B2, n2, cst[CST_S + 2], cst[CST_S + 3], np);
+            enc_norm_epilogue<C2>(d0r[0], cst + CST_B2, n2, cst[CST_S + 2], cst[CST_S + 3], np,
+                                  (valid && a.save_y2 != nullptr) ? a.save_y2 + (size_t)r * C2 : nullptr,
+                                  (valid && a.save_sd2 != nullptr) ? a.save_sd2 + r : nullptr);
             tc::tmem_wait_st();
             tc::tc_fence_before();
             { warp_arrive(&bars[B_A_FULL + 2 * g + (n_arr & 1u)], lane); ++n_arr; }
@@ -279,7 +295,9 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                     st.init();
                     st.add_chunk(va);
                     st.add_chunk(vb);
-                    k = cst[CST_S + 4] * __frcp_rn(st.sigma(C3) + NORM_EPS);
+                    const float sd = st.sigma(C3);
+                    if (valid && a.save_sd3 != nullptr) a.save_sd3[r] = sd;
+                    k = cst[CST_S + 4] * __frcp_rn(sd + NORM_EPS);
                     sh = cst[CST_S + 5];
                     mean = st.mean;
                 }
@@ -460,7 +478,8 @@ int edge_enc_f16_pack(const rgnn_stack& s, cudaStream_t stream) {
     return RGNN_OK;
 }
 
-int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, int n_rows, uint32_t* emb_hl, float* emb, cudaStream_t stream) {
+int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, int n_rows, uint32_t* emb_hl, float* emb, cudaStream_t stream,
+                     const TcSave* save) {
     if (n_rows <= 0) return RGNN_OK;
     EdgeEncArgs a;
     memset(&a, 0, sizeof(a));
@@ -474,6 +493,10 @@ int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, in
     a.s2 = s.layer[2].norm_scale; a.m2 = s.layer[2].norm_shift;
     a.s3 = s.layer[3].norm_scale; a.m3 = s.layer[3].norm_shift;
     a.emb_hl = emb_hl; a.emb = emb;
+    if (save != nullptr) {
+        a.save_y1 = save->y[1]; a.save_y2 = save->y[2];
+        a.save_sd1 = save->sd[1]; a.save_sd2 = save->sd[2]; a.save_sd3 = save->sd[3];
+    }
     a.passes = mp_f16_passes();
     static PerDeviceOnce once;
     if (once.needed()) {

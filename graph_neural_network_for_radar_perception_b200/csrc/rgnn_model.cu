@@ -366,10 +366,13 @@ int detector_fwd(const rgnn_detector& net, const rgnn_graph& g, const float* nod
         if ((rc = launch_program(b.p, stream))) return rc;
     }
     bool emb_split_done = false;
-    if (E > 0 && !pl.enc_tc_bwd && pl.emb_hl != nullptr && edge_enc_f16_supported(net.edge_enc)) {
+    if (E > 0 && pl.emb_hl != nullptr && edge_enc_f16_supported(net.edge_enc)) {
         // the fixed-shape encoder writes the pre-split rows of the message kernel directly; the fp32 embedding is written as well
         // only when a backward will read it (a training step whose backward recomputes the encoder on the CUDA cores)
-        if ((rc = run_edge_enc_f16(net.edge_enc, edge_features, g.perm, E, pl.emb_hl, pl.training ? pl.emb : nullptr, stream))) return rc;
+        // (a training step with the chain backward also gets the layer outputs and sigmas that backward reads: enc_save)
+        if ((rc = run_edge_enc_f16(net.edge_enc, edge_features, g.perm, E, pl.emb_hl, pl.training ? pl.emb : nullptr, stream,
+                                   pl.enc_tc_bwd ? &pl.enc_save : nullptr)))
+            return rc;
         emb_split_done = true;
     } else if (E > 0 && tc_stack_supported(net.edge_enc)) {
         if ((rc = tc_run_stack(net.edge_enc, edge_features, g.perm, E, pl.emb, stream, pl.enc_tc_bwd ? &pl.enc_save : nullptr))) return rc;

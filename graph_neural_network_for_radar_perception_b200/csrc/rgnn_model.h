@@ -97,7 +97,8 @@ int chain_f16_get_option(const char* name);
 // fixed-shape edge encoder with fp16-split operands, rgnn_edge_enc_f16.cu
 bool edge_enc_f16_supported(const rgnn_stack& s);
 int edge_enc_f16_pack(const rgnn_stack& s, cudaStream_t stream);
-int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, int n_rows, uint32_t* emb_hl, float* emb, cudaStream_t stream);
+int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, int n_rows, uint32_t* emb_hl, float* emb, cudaStream_t stream,
+                     const TcSave* save = nullptr);
 int edge_enc_f16_set_option(const char* name, int value);
 int edge_enc_f16_get_option(const char* name);
 
