@@ -67,7 +67,8 @@ __device__ __forceinline__ float2 unpack(uint32_t h) {
 __device__ __forceinline__ void split(float2 x, uint32_t& hi, uint32_t& lo) {
     hi = pack_sat(x.x, x.y);
     const float2 h = unpack(hi);
-    lo = pack_sat(x.x - h.x, x.y - h.y);
+    const float2 d = __fadd2_rn(x, make_float2(-h.x, -h.y));       // one packed subtraction (same fp32 results as two FADDs)
+    lo = pack_sat(d.x, d.y);
 }
 
 // 16 packed columns (= 32 fp16 values of this lane's row) <-> tensor memory
@@ -122,6 +123,13 @@ __host__ __device__ __forceinline__ size_t emb_tile_word(long long e, int img, i
 __device__ __forceinline__ uint4 ldg128u(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// streaming variant: the data is used once and should not push re-used rows out of the (small) L1
+__device__ __forceinline__ uint4 ldg128u_na(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 

@@ -3,29 +3,35 @@
 //
 //   agg[t] = sum_{e: s->t} ffn2( ffn1( cat(x_t, x_s, emb_e) ) ),      z1 = emb_e W_e^T + P_t[tgt] + P_s[src]   (P hoisted per node)
 //
-// A CTA (one per SM, persistent) owns tiles of 128 target-major edges; thread = TMEM lane = edge row in every role, so no
-// row statistic ever crosses a thread.  Four roles work on DIFFERENT tiles at the same time:
+// A CTA (one per SM, persistent, 896 threads) owns tiles of 128 target-major edges; thread = TMEM lane = edge row in every
+// role, so no row statistic ever crosses a thread.  Roles work on DIFFERENT tiles at the same time:
 //
-//   F    (4 warps)  tile j   : emb rows (pre-split fp16 hi | lo, 256 B / edge) -> TMEM A operand;  4096 P_s (staged rows) -> D1[b]
-//   MMA  (1 lane)            : G1(j): D1[b] += emb W_e^T   |   G2(j): D2[b] = y1 W_2^T          (issues whatever is ready)
-//   E1   (2 x 4 warps, group g owns buffer g) : D1[b] -> mean / unbiased std / affine / LeakyReLU -> y1 as fp16 hi | lo, in
-//                              place over D1[b], 32 columns at a time (small loop bodies: the instruction cache holds all roles)
-//   E2   (4 warps)  tile j   : D2[b] -> + b2 -> norm -> act -> message tile in shared memory -> segment table
-//   stagers (4 warps) tile j+2: the 128 P_s[src] rows (512 B each) -> shared memory, whole rows per warp instruction (cp.async)
-//   segsum (2 warps) tile j  : segmented sum over equal consecutive targets -> agg (plain stores; atomics only for the <= 2
-//                              segments a tile boundary cuts, so the result is deterministic)
+//   F    (4 warps)  tile j   : emb rows (pre-split fp16 hi | lo, 256 B / edge) -> TMEM A operand;  4096 (P_t[tgt] + P_s[src]) -> D1[b].
+//                              Every tile passes through this role serially, so nothing it needs may cost a memory round trip
+//                              inside the tile: the emb row and the first half of the P_t row of tile j + 1 are requested while
+//                              tile j's pre-load runs (128 registers of loads in flight across the loop edge: 200 registers)
+//   MMA  (2 lanes in 2 warps): G1(j): D1[b] += emb W_e^T   |   G2(j): D2[b] = y1 W_2^T ; each lane BLOCKS on its own barrier sequence
+//   E1   (2 x 4 warps, both groups on every tile) : D1[b] -> mean / unbiased std / affine / LeakyReLU -> y1 as fp16 hi | lo, in
+//                              place over D1[b]; each group rewrites two of the four 32-column chunks
+//   E2   (2 x 4 warps, group g owns the tiles of parity g) : D2[b] -> + b2 -> norm -> act -> message tile in shared memory ->
+//                              segmented sum over equal consecutive targets -> agg (plain stores; atomics only for the <= 2 segments
+//                              a tile boundary cuts, so the result is deterministic).  The one message tile is handed from group
+//                              to group through the mbarrier B_STAGE
+//   stagers (6 warps) tile j+2: the 128 P_s[src] rows (512 B each) -> shared memory, whole rows per warp instruction (cp.async)
 //
-// with b = j & 1.  Tensor memory (512 columns): D1[2] 2 x 128 | D2[2] 2 x 64 | emb[2] 2 x (32 hi + 32 lo).  The node half
-// source half of msg.0's hoisted projection is PRE-LOADED into the accumulator (the MMAs of G1 accumulate onto it); E1 adds the
-// target half, whose rows repeat over consecutive edges, while it gathers the row statistics.
+// with b = j & 1.  Tensor memory (512 columns): D1[2] 2 x 128 | D2[2] 2 x 64 | emb[2] 2 x (32 hi + 32 lo).  The node half of
+// msg.0's hoisted projection is PRE-LOADED into the accumulator (the MMAs of G1 accumulate onto it).
 // Scales: the accumulators hold 4096 x the true values (rgnn_f16.cuh); E1's normalisation is scale invariant (sigma and
 // eps scale along), E2 multiplies by 2^-12 inside the FFMA that adds the bias.
 // Hand-over (mbarriers, phase = (j >> 1) & 1):
 //   ps_full[b]  stager -> F      ps_free[b]  F -> stager
 //   a_full[b]   F -> MMA         d1_full[b]  tcgen05.commit(G1) -> E1
 //   y1_full[b]  E1 -> MMA        d2_full[b]  tcgen05.commit(G2) -> E2, and -> F (D1[b] / emb[b] of tile j may be reused by j+2)
-//   d2_free[b]  E2 -> MMA (D2[b] has been read)
-// and two named barriers between E2 and the segsum warps for the single message tile (STAGE_FULL / STAGE_FREE).
+//   d2_free[b]  E2 -> MMA (D2[b] has been read)      stage (one): E2 group -> the other E2 group (completion k = tile k is summed)
+// Register budgets (setmaxnreg; 65536 / 896 -> 72 at launch): E1 64, E2 64, F 200, MMA + stagers 24.
+// What the measurements of round 2 say about this kernel (profiles/README.md): it is bound by the SM's issue
+// slots and load/store path, not by the tensor pipe (25 % active) or HBM; every role that was relieved (a second E2 group, more
+// stagers, blocking MMA lanes) only paid once the F role stopped waiting for its own loads.
 #include "rgnn_f16.cuh"
 #include "rgnn_model.h"
 #include "rgnn_tc_rows.cuh"
@@ -53,19 +59,19 @@ struct MpF16Args {
 
 namespace mpf {
 constexpr int CE = 64, H = 128, CN = 64, TM = 128;
-// warp groups (4 warps each): E1 x 2 (each owns half of the columns of every tile), E2 (+ segmented sum), F, aux (MMA issue + 3 stagers)
-constexpr int NTHREADS = 640;
-constexpr int WG_E1 = 0, WG_E2 = 2, WG_F = 3, WG_AUX = 4;
-constexpr int NSTAGER = 3;
+// warp groups (4 warps each): E1 x 2 (each owns half of the columns of every tile), E2 x 2 (+ segmented sum), F, aux x 2 (2 MMA issue warps + 6 stagers)
+constexpr int NTHREADS = 896;
+constexpr int WG_E1 = 0, WG_E2 = 2, WG_F = 4, WG_AUX = 5;      // E2 group g (warpgroup WG_E2 + g) owns the tiles of parity g
+constexpr int NSTAGER = 6;
 constexpr int W1_WORDS = CE * H / 2, W2_WORDS = H * CN / 2;         // 32-bit words per (hi or lo) image
 constexpr int OFF_W = 0;                                            // words: W_e hi | lo | W_2 hi | lo
 constexpr int OFF_PS = OFF_W + 2 * W1_WORDS + 2 * W2_WORDS;          // [2][TM][H] floats
 constexpr int OFF_STAGE = OFF_PS + 2 * TM * H;                      // [TM][CN] floats, 16-byte chunks XOR-swizzled
 constexpr int SEG = TM + 4;
-constexpr int OFF_SEG = OFF_STAGE + TM * CN;                        // [SEG] int2
-constexpr int OFF_MASK = OFF_SEG + 2 * SEG;                         // [4] ballots | nseg | cut | cut_first | cut_last
-constexpr int OFF_BAR = OFF_MASK + 8;                               // 14 mbarriers
-constexpr int OFF_BIAS = OFF_BAR + 2 * 14;                          // msg.1 bias (CN floats; broadcast reads)
+constexpr int OFF_SEG = OFF_STAGE + TM * CN;                        // [2 groups][SEG] int2
+constexpr int OFF_MASK = OFF_SEG + 2 * 2 * SEG;                     // [2 groups]([4] ballots | nseg | cut | cut_first | cut_last)
+constexpr int OFF_BAR = OFF_MASK + 2 * 8;                           // 15 mbarriers (+ 1 pad)
+constexpr int OFF_BIAS = OFF_BAR + 2 * 16;                          // msg.1 bias (CN floats; broadcast reads)
 constexpr int OFF_SLOT = OFF_BIAS + CN;
 constexpr int WORDS = OFF_SLOT + 2;
 constexpr size_t SMEM = (size_t)WORDS * 4;
@@ -73,14 +79,15 @@ static_assert((OFF_BAR % 2) == 0 && (OFF_SEG % 2) == 0, "mbarrier / int2 alignme
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 // tensor memory columns
 constexpr uint32_t COL_D1 = 0, COL_D2 = 256, COL_EMB = 384;
-// register budget per role (setmaxnreg; launch = 65536 / 640 -> 96).  setmaxnreg.inc only draws what .dec released.
-constexpr int REG_LAUNCH = 96, REG_E1 = 88, REG_E2 = 104, REG_F = 160, REG_AUX = 40;
-static_assert(256 * REG_E1 + 128 * (REG_E2 + REG_F + REG_AUX) <= 640 * REG_LAUNCH, "setmaxnreg pool");
+// register budget per role (setmaxnreg; launch = 65536 / 896 -> 72).  setmaxnreg.inc only draws what .dec released.
+constexpr int REG_LAUNCH = 72, REG_E1 = 64, REG_E2 = 64, REG_F = 200, REG_AUX = 24;
+static_assert(256 * REG_E1 + 256 * REG_E2 + 128 * REG_F + 256 * REG_AUX <= NTHREADS * REG_LAUNCH, "setmaxnreg pool");
 // named barriers
-constexpr int BAR_E2 = 12, BAR_E1 = 13;
-enum { B_PS_FULL = 0, B_PS_FREE = 2, B_A_FULL = 4, B_D1_FULL = 6, B_Y1_FULL = 8, B_D2_FULL = 10, B_D2_FREE = 12 };
+constexpr int BAR_E2 = 12 /* and 14 for group 1 */, BAR_E1 = 13;
+enum { B_PS_FULL = 0, B_PS_FREE = 2, B_A_FULL = 4, B_D1_FULL = 6, B_Y1_FULL = 8, B_D2_FULL = 10, B_D2_FREE = 12, B_STAGE = 14 };
 }  // namespace mpf
 
+#define MPF_EV(k) do { if (PROFILE && a.prof != nullptr && blockIdx.x == 0 && j >= 16 && j < 32) a.prof[(size_t)gridDim.x * 28 * 4 + (j - 16) * 16 + (k)] = clock64(); } while (0)
 template <bool PROFILE>
 __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __grid_constant__ MpF16Args a) {
     using namespace mpf;
@@ -89,12 +96,6 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
     uint32_t* wsm = smem_u + OFF_W;
     float* ps = smem_f + OFF_PS;
     float* stage = smem_f + OFF_STAGE;
-    int2* seg_s = reinterpret_cast<int2*>(smem_u + OFF_SEG);
-    unsigned* mask_s = smem_u + OFF_MASK;
-    int* nseg_s = reinterpret_cast<int*>(smem_u + OFF_MASK + 4);
-    int* cut_s = nseg_s + 1;
-    int* cut_first_s = nseg_s + 2;
-    int* cut_last_s = nseg_s + 3;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_u + OFF_BAR);
     uint32_t* slot = smem_u + OFF_SLOT;
     float* bias_s = smem_f + OFF_BIAS;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             tc::mbar_init(&bars[B_D2_FULL + i], 1);
             tc::mbar_init(&bars[B_D2_FREE + i], 4);
         }
+        tc::mbar_init(&bars[B_STAGE], 4);           // the segmented sum of a tile is complete: the message tile may be rewritten
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(slot, 512);
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             tc::mbar_wait(&bars[B_D1_FULL + b], ph);
             tc::tc_fence_after();
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
+            if (tid == 0) MPF_EV(5);
             float k, sh, mean;
             if (norm1) {
                 // sweep 1: statistics on the 4096-fold values (power-of-two scaling is exact; sigma and eps scale along).  Each group
@@ -161,14 +164,17 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 // tile -- and are merged with the exact pairwise update.  The barrier is the one the in-place stores need anyway.
                 RowStats st;
                 st.init();
-                float2 va[16], vb[16];
-                tc::tmem_ld16(d1 + 32 * g, va);
-                tc::tmem_ld16(d1 + 32 * g + 16, va + 8);
-                tc::tmem_ld16(d1 + 32 * g + 64, vb);
-                tc::tmem_ld16(d1 + 32 * g + 80, vb + 8);
-                tc::tmem_wait_ld();
-                st.add_chunk(va);
-                st.add_chunk(vb);
+                {
+                    float2 v[16];
+                    tc::tmem_ld16(d1 + 32 * g, v);
+                    tc::tmem_ld16(d1 + 32 * g + 16, v + 8);
+                    tc::tmem_wait_ld();
+                    st.add_chunk(v);
+                    tc::tmem_ld16(d1 + 32 * g + 64, v);
+                    tc::tmem_ld16(d1 + 32 * g + 80, v + 8);
+                    tc::tmem_wait_ld();
+                    st.add_chunk(v);
+                }
                 const uint32_t xc = t_row + COL_EMB + (uint32_t)b * 64;
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(xc + 2 * g), "f"(st.mean), "f"(st.m2) : "memory");
                 tc::tmem_wait_st();
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 group_sync(BAR_E1, 256);
                 tc::tc_fence_after();
             }
+            if (tid == 0) MPF_EV(6);
             const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean, -mean);
             const bool act = a.act1 != 0;
             // sweep 2 (this group's chunks g and g + 2): y1 x 16 = act(k (z - mean) + sh) -> fp16 hi | lo, IN PLACE: the 32 fp32
@@ -201,45 +208,65 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             // warp addresses the K steps of GEMM2 accordingly)
             long long q0 = 0, q1 = 0, q2 = 0;
 #pragma unroll 1
-            for (int c = 32 * g; c < H; c += 64) {
-                float2 v[16];
+            for (int cb = 32 * g; cb < H; cb += 64) {
+                // one 32-column chunk in two 16-column halves (register budget): the first half's lo pairs wait in registers until
+                // the second half's fp32 values have been read from the columns they overwrite
                 long long ta = 0;
                 if (PROFILE) ta = clock64();
-                tc::tmem_ld16(d1 + c, v);
-                tc::tmem_ld16(d1 + c + 16, v + 8);
-                tc::tmem_wait_ld();
-                if (PROFILE) { const long long tb = clock64(); q0 += tb - ta; ta = tb; }
-                uint32_t hi[16], lo[16];
+                uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
+                auto half = [&](int c, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+                    float2 v[8];
+                    tc::tmem_ld16(d1 + c, v);
+                    tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float2 y = __ffma2_rn(__fadd2_rn(v[i], nm), k2, sh2);
-                    if (act) {
-                        const float2 t = __fmul2_rn(y, sl);
-                        y.x = fmaxf(y.x, t.x);
-                        y.y = fmaxf(y.y, t.y);
+                    for (int i = 0; i < 8; ++i) {
+                        float2 y = __ffma2_rn(__fadd2_rn(v[i], nm), k2, sh2);
+                        if (act) {
+                            const float2 t = __fmul2_rn(y, sl);
+                            y.x = fmaxf(y.x, t.x);
+                            y.y = fmaxf(y.y, t.y);
+                        }
+                        f16::split(y, hi[i], lo[i]);
                     }
-                    f16::split(y, hi[i], lo[i]);
-                }
+                };
+                half(cb, hi0, lo0);
+                half(cb + 16, hi1, lo1);
                 if (PROFILE) { const long long tb = clock64(); q1 += tb - ta; ta = tb; }
-                f16::tmem_st16u(d1 + c, hi);
-                if (np != 1) f16::tmem_st16u(d1 + c + 16, lo);
+                f16::tmem_st8u(d1 + cb, hi0);
+                f16::tmem_st8u(d1 + cb + 8, hi1);
+                if (np != 1) {
+                    f16::tmem_st8u(d1 + cb + 16, lo0);
+                    f16::tmem_st8u(d1 + cb + 24, lo1);
+                }
                 if (PROFILE) { tc::tmem_wait_st(); const long long tb = clock64(); q2 += tb - ta; }
             }
             if (PROFILE && lane == 0 && a.prof != nullptr && warp == 0) {
-                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 0], (unsigned long long)q0);
-                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 1], (unsigned long long)q1);
-                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 20 + 17) * 4 + 2], (unsigned long long)q2);
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 28 + 21) * 4 + 0], (unsigned long long)q0);
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 28 + 21) * 4 + 1], (unsigned long long)q1);
+                atomicAdd((unsigned long long*)&a.prof[(blockIdx.x * 28 + 21) * 4 + 2], (unsigned long long)q2);
             }
             tc::tmem_wait_st();
             tc::tc_fence_before();
             warp_arrive(&bars[B_Y1_FULL + b], lane);
+            if (tid == 0) MPF_EV(7);
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[2] += n - tl; tl = n; }
         }
         if (PROFILE && lane == 0 && a.prof != nullptr)
-            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 20 + warp) * 4 + i] = pt[i];
-    } else if (wg == WG_E2) {
-        // =========================== E2: epilogue of GEMM2, message tile, segmented sum ===========================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_E2));
+            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 28 + warp) * 4 + i] = pt[i];
+    } else if (wg < WG_F) {
+        // =========================== E2 (two groups): epilogue of GEMM2, message tile, segmented sum ===========================
+        // Group g takes the tiles of parity g (= TMEM buffer g): this is the role with the most work per tile (epilogue + segmented
+        // sum), so two groups alternate.  The epilogue arithmetic of tile j + 1 overlaps the segmented sum of tile j; the ONE message
+        // tile in shared memory is handed from group to group through the mbarrier B_STAGE (completion k = the sum of tile k is done).
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_E2));
+        const int g = wg - WG_E2;
+        const int bar_e2 = BAR_E2 + 2 * g;
+        int2* seg_s = reinterpret_cast<int2*>(smem_u + OFF_SEG) + g * SEG;
+        unsigned* mask_s = smem_u + OFF_MASK + 8 * g;
+        int* nseg_s = reinterpret_cast<int*>(mask_s + 4);
+        int* cut_s = nseg_s + 1;
+        int* cut_first_s = nseg_s + 2;
+        int* cut_last_s = nseg_s + 3;
         long long pt[3] = {0, 0, 0}, tl = 0;
         if (PROFILE) tl = clock64();
         const bool norm2 = a.s2 != nullptr;
@@ -253,9 +280,9 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             t_first = (lane == 0 && v && e > 0) ? __ldg(a.tgt + e - 1) : -2;          // target of the edge before this warp's rows
             t_last = (row == TM - 1 && v && e + 1 < a.n_edges) ? __ldg(a.tgt + e + 1) : -3;
         };
-        load_idx(0);
-        for (int j = 0; j < my_tiles; ++j) {
-            const int b = j & 1;
+        load_idx(g);
+        for (int j = g; j < my_tiles; j += 2) {
+            const int b = g;
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             const int tile = (int)blockIdx.x + j * G;
             const int nvalid = min(TM, a.n_edges - tile * TM);
@@ -270,7 +297,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 if (row == 0) cut_first_s[0] = (t_first == t) ? 1 : 0;
                 if (row == nvalid - 1) cut_last_s[0] = (row == TM - 1 && t_last == t) ? 2 : 0;
             }
-            group_sync(BAR_E2, 128);           // also: the previous tile's segmented sum is complete (stage / table reusable)
+            group_sync(bar_e2, 128);           // also: this group's previous segmented sum is complete (its table is reusable)
             {
                 const unsigned m = mask_s[w4];
                 int base = 0;
@@ -283,57 +310,69 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                     cut_s[0] = cut_first_s[0] | cut_last_s[0];
                 }
             }
-            load_idx(j + 1);
+            load_idx(j + 2);
             // ---- D2[b] -> registers ----
             tc::mbar_wait(&bars[B_D2_FULL + b], ph);
             tc::tc_fence_after();
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
-            float2 va[16], vb[16];
+            if (w4 == 0 && lane == 0) MPF_EV(10);
+            // two sweeps over D2[b] in 32-column chunks (a TMEM read costs ~65 cycles; holding all 64 columns would not fit the
+            // register budget of two E2 groups): statistics, then normalise / activate / store.  Chunk 1 is still in registers
+            // when the second sweep starts, so only chunk 0 is read (and biased) twice.
             const uint32_t d2 = t_row + COL_D2 + (uint32_t)b * CN;
-            tc::tmem_ld16(d2, va);
-            tc::tmem_ld16(d2 + 16, va + 8);
-            tc::tmem_ld16(d2 + 32, vb);
-            tc::tmem_ld16(d2 + 48, vb + 8);
-            tc::tmem_wait_ld();
-            tc::tc_fence_before();
-            warp_arrive(&bars[B_D2_FREE + b], lane);          // GEMM2 of tile j + 2 may overwrite D2[b]
             const float2 us = make_float2(f16::D_UNSCALE, f16::D_UNSCALE);
+            float2 v[16];
+            auto load_chunk = [&](int h) {
+                tc::tmem_ld16(d2 + 32 * h, v);
+                tc::tmem_ld16(d2 + 32 * h + 16, v + 8);
+                tc::tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                va[c] = __ffma2_rn(va[c], us, *reinterpret_cast<const float2*>(bias_s + 2 * c));
-                vb[c] = __ffma2_rn(vb[c], us, *reinterpret_cast<const float2*>(bias_s + 32 + 2 * c));
-            }
+                for (int c = 0; c < 16; ++c) v[c] = __ffma2_rn(v[c], us, *reinterpret_cast<const float2*>(bias_s + 32 * h + 2 * c));
+            };
             float k = 1.f, sh = 0.f, mean = 0.f;
             if (norm2) {
                 RowStats st;
                 st.init();
-                st.add_chunk(va);
-                st.add_chunk(vb);
+                load_chunk(0);
+                st.add_chunk(v);
+                load_chunk(1);
+                st.add_chunk(v);
                 k = s2v * __frcp_rn(st.sigma(CN) + NORM_EPS);
                 sh = m2sv;
                 mean = st.mean;
+            } else {
+                load_chunk(1);
             }
             const float2 k2 = make_float2(k, k), sh2 = make_float2(sh, sh), sl = make_float2(LEAKY, LEAKY), nm = make_float2(-mean, -mean);
             const bool act = a.act2 != 0;
+            auto finish = [&]() {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                va[c] = __ffma2_rn(__fadd2_rn(va[c], nm), k2, sh2);
-                vb[c] = __ffma2_rn(__fadd2_rn(vb[c], nm), k2, sh2);
-                if (act) {
-                    const float2 ta = __fmul2_rn(va[c], sl), tb = __fmul2_rn(vb[c], sl);
-                    va[c].x = fmaxf(va[c].x, ta.x); va[c].y = fmaxf(va[c].y, ta.y);
-                    vb[c].x = fmaxf(vb[c].x, tb.x); vb[c].y = fmaxf(vb[c].y, tb.y);
+                for (int c = 0; c < 16; ++c) {
+                    v[c] = __ffma2_rn(__fadd2_rn(v[c], nm), k2, sh2);
+                    if (act) {
+                        const float2 t2 = __fmul2_rn(v[c], sl);
+                        v[c].x = fmaxf(v[c].x, t2.x); v[c].y = fmaxf(v[c].y, t2.y);
+                    }
                 }
-            }
+            };
+            auto put = [&](int h) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                *reinterpret_cast<float4*>(stage + row * CN + ((c4 ^ (row & 7)) << 2)) =
-                    make_float4(va[2 * c4].x, va[2 * c4].y, va[2 * c4 + 1].x, va[2 * c4 + 1].y);
-                *reinterpret_cast<float4*>(stage + row * CN + (((c4 + 8) ^ (row & 7)) << 2)) =
-                    make_float4(vb[2 * c4].x, vb[2 * c4].y, vb[2 * c4 + 1].x, vb[2 * c4 + 1].y);
-            }
+                for (int c4 = 0; c4 < 8; ++c4)
+                    *reinterpret_cast<float4*>(stage + row * CN + (((c4 + 8 * h) ^ (row & 7)) << 2)) =
+                        make_float4(v[2 * c4].x, v[2 * c4].y, v[2 * c4 + 1].x, v[2 * c4 + 1].y);
+            };
+            finish();
+            if (j > 0) tc::mbar_wait(&bars[B_STAGE], (uint32_t)(j - 1) & 1u);      // the other group has summed tile j - 1
+            if (w4 == 0 && lane == 0) MPF_EV(11);
+            put(1);
+            load_chunk(0);
+            tc::tc_fence_before();
+            warp_arrive(&bars[B_D2_FREE + b], lane);          // GEMM2 of tile j + 2 may overwrite D2[b]
+            finish();
+            put(0);
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
-            group_sync(BAR_E2, 128);           // message tile and segment table complete
+            if (w4 == 0 && lane == 0) MPF_EV(12);
+            group_sync(bar_e2, 128);           // message tile and segment table complete
             // ---- segmented sum over equal consecutive targets: 16 threads (one float4 of columns each) per segment.  Interior
             // segments are whole CSR rows (edges are target-major): plain stores in source-ascending order like the reference's
             // index_add_; only the first / last segment of a tile can be cut by its boundary and uses atomicAdd (<= 2 partials
@@ -367,22 +406,65 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                     }
                 }
             }
+            warp_arrive(&bars[B_STAGE], lane);
+            if (w4 == 0 && lane == 0) MPF_EV(13);
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[2] += n - tl; tl = n; }
         }
         if (PROFILE && lane == 0 && a.prof != nullptr)
-            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 20 + warp) * 4 + i] = pt[i];
+            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 28 + warp) * 4 + i] = pt[i];
     } else if (wg == WG_F) {
         // =========================== F: A operand and accumulator pre-load ===========================
         // This role waits most of the time for a TMEM buffer to come back (GEMM2 of tile j - 2), so everything it needs from
         // global memory for tile j is requested BEFORE that wait and sits in registers across it: three of the four
         // 32-column chunks of P_t[target] and the hi half of the emb row (the L2 round trip of a chunk is ~1 000 cycles here).
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_F));
+        // This role is the one every tile passes through serially, so nothing it needs may cost a memory round trip inside the
+        // tile: the emb row (hi | lo, 64 registers) of tile j + 1 is requested while tile j's accumulator pre-load runs, and the
+        // P_t[target] row of tile j + 1 is brought to L1 one tile ahead (consecutive rows share their target: ~12 rows of 512 B
+        // per tile; the streaming emb loads do not allocate in L1), so the pre-load reads it in 16-column pieces with L1 latency.
         long long pt[3] = {0, 0, 0}, tl = 0;
         if (PROFILE) tl = clock64();
-        int t_next = -1;
+        auto tgt_of = [&](int jj) {
+            const int e = ((int)blockIdx.x + jj * G) * TM + row;
+            return (jj < my_tiles && e < a.n_edges) ? __ldg(a.tgt + e) : -1;
+        };
+        auto prefetch_pt = [&](int t) {      // -> L2: the row is read into registers at the end of the previous tile
+            if (t >= 0) {
+                const float* q = a.P + (size_t)t * (2 * H);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32 * i));
+            }
+        };
+        uint32_t eh[32], el[32];
+        // Rows past the end of the edge list (last tile) are not zeroed anywhere in this role: every row of the tile is independent
+        // through both GEMMs and both epilogues, and E2 never sums rows >= nvalid.  The loads stay in bounds: the emb buffer holds
+        // whole tiles, and an invalid row reads P row 0.
+        auto load_emb = [&](int jj) {
+            // (unconditional: past the CTA's last tile the last tile is simply read again; a predicated load would keep the
+            // arrays in local memory)
+            const long long e = ((long long)blockIdx.x + (long long)(jj < my_tiles ? jj : my_tiles - 1) * G) * TM + row;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const uint4 vh = ldg128u_na(a.emb + emb_tile_word(e, 0, c8));
+                eh[4 * c8] = vh.x; eh[4 * c8 + 1] = vh.y; eh[4 * c8 + 2] = vh.z; eh[4 * c8 + 3] = vh.w;
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const uint4 vl = ldg128u_na(a.emb + emb_tile_word(e, 1, c8));
+                el[4 * c8] = vl.x; el[4 * c8 + 1] = vl.y; el[4 * c8 + 2] = vl.z; el[4 * c8 + 3] = vl.w;
+            }
+        };
+        int t_cur = tgt_of(0), t_nx = tgt_of(1);
+        load_emb(0);
+        float2 p0[16], p1[16];
+        auto load_pt = [&](float2 (&v)[16], const float* Pt, int c) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ldg256(Pt + c + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        };
         {
-            const int e = (int)blockIdx.x * TM + row;
-            t_next = (my_tiles > 0 && e < a.n_edges) ? __ldg(a.tgt + e) : -1;
+            const float* Pt0 = a.P + (size_t)(t_cur >= 0 ? t_cur : 0) * (2 * H);
+            load_pt(p0, Pt0, 0);
+            load_pt(p1, Pt0, 32);
         }
         const float2 sc = make_float2(f16::D_SCALE, f16::D_SCALE);
         for (int j = 0; j < my_tiles; ++j) {
@@ -391,27 +473,12 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             const int tile = (int)blockIdx.x + j * G;
             const int e = tile * TM + row;
             const bool valid = e < a.n_edges;
-            const int t = t_next;
-            const bool pv = valid && t >= 0;
-            const float* Pt = a.P + (size_t)(pv ? t : 0) * (2 * H);
-            float2 p0[16], p1[16], p2[16];
-            auto load_pt = [&](float2 (&v)[16], int c) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ldg256(Pt + c + 8 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            };
-            load_pt(p0, 0);
-            load_pt(p1, 32);
-            load_pt(p2, 64);
-            uint32_t ev[32];
-            const long long el = valid ? e : 0;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                const uint4 v = ldg128u(a.emb + emb_tile_word(el, 0, c8));
-                ev[4 * c8] = v.x; ev[4 * c8 + 1] = v.y; ev[4 * c8 + 2] = v.z; ev[4 * c8 + 3] = v.w;
-            }
-            {   // next tile: target index of this thread's row; its emb row two tiles ahead -> L2 (it streams from DRAM)
-                const int en = ((int)blockIdx.x + (j + 1) * G) * TM + row;
-                t_next = (j + 1 < my_tiles && en < a.n_edges) ? __ldg(a.tgt + en) : -1;
+            const int t = t_cur;
+            const float* Pt = a.P + (size_t)(valid && t >= 0 ? t : 0) * (2 * H);
+            t_cur = t_nx;
+            prefetch_pt(t_cur);                 // tile j + 1's P_t row -> L2
+            t_nx = tgt_of(j + 2);
+            {   // the emb rows of tile j + 2 -> L2 (they stream from DRAM); tile j + 1's are requested below
                 const long long e2 = ((long long)blockIdx.x + (long long)(j + 2) * G) * TM + row;
                 if (j + 2 < my_tiles && e2 < a.n_edges) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.emb + e2 * 64));
@@ -423,117 +490,122 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 tc::tc_fence_after();
             }
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
+            if (tid == WG_F * 128) MPF_EV(0);
             const uint32_t c_emb = t_row + COL_EMB + (uint32_t)b * 64;
-            if (!valid) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ev[i] = 0u;
+            f16::tmem_st16u(c_emb, eh);
+            f16::tmem_st16u(c_emb + 16, eh + 16);
+            if (np != 1) {
+                f16::tmem_st16u(c_emb + 32, el);
+                f16::tmem_st16u(c_emb + 48, el + 16);
             }
-            f16::tmem_st16u(c_emb, ev);
-            f16::tmem_st16u(c_emb + 16, ev + 16);
-            if (np != 1) {      // the lo half: requested now, stored after the accumulator pre-load below
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    const uint4 v = ldg128u(a.emb + emb_tile_word(el, 1, c8));
-                    ev[4 * c8] = v.x; ev[4 * c8 + 1] = v.y; ev[4 * c8 + 2] = v.z; ev[4 * c8 + 3] = v.w;
-                }
-            }
+            load_emb(j + 1);
             // accumulator pre-load: 4096 (P_t[target] + P_s[source]); P_s from the staged rows
             const float* Ps = ps + (size_t)b * TM * H + row * H;
             const uint32_t d1 = t_row + COL_D1 + (uint32_t)b * H;
             tc::mbar_wait(&bars[B_PS_FULL + b], ph);
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
+            if (tid == WG_F * 128) MPF_EV(1);
             auto emit = [&](float2 (&v)[16], int c) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 s4 = *reinterpret_cast<const float4*>(Ps + ((((c >> 2) + i) ^ (row & 7)) << 2));
-                    v[2 * i] = pv ? __ffma2_rn(v[2 * i], sc, __fmul2_rn(make_float2(s4.x, s4.y), sc)) : make_float2(0.f, 0.f);
-                    v[2 * i + 1] = pv ? __ffma2_rn(v[2 * i + 1], sc, __fmul2_rn(make_float2(s4.z, s4.w), sc)) : make_float2(0.f, 0.f);
+                    v[2 * i] = __ffma2_rn(v[2 * i], sc, __fmul2_rn(make_float2(s4.x, s4.y), sc));
+                    v[2 * i + 1] = __ffma2_rn(v[2 * i + 1], sc, __fmul2_rn(make_float2(s4.z, s4.w), sc));
                 }
                 tc::tmem_st16(d1 + c, v);
                 tc::tmem_st16(d1 + c + 16, v + 8);
             };
             emit(p0, 0);
-            load_pt(p0, 96);
+            load_pt(p0, Pt, 64);
             emit(p1, 32);
-            emit(p2, 64);
-            emit(p0, 96);
-            if (np != 1) {
-                if (!valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) ev[i] = 0u;
-                }
-                f16::tmem_st16u(c_emb + 32, ev);
-                f16::tmem_st16u(c_emb + 48, ev + 16);
-            }
+            load_pt(p1, Pt, 96);
+            emit(p0, 64);
+            emit(p1, 96);
             tc::tmem_wait_st();
             tc::tc_fence_before();
             warp_arrive(&bars[B_PS_FREE + b], lane);          // staged rows consumed
             warp_arrive(&bars[B_A_FULL + b], lane);           // -> GEMM1 of this tile
+            {   // the first half of tile j + 1's P_t row (L2: prefetched at the top of this tile)
+                const float* Pn = a.P + (size_t)(t_cur >= 0 ? t_cur : 0) * (2 * H);
+                load_pt(p0, Pn, 0);
+                load_pt(p1, Pn, 32);
+            }
+            if (tid == WG_F * 128) MPF_EV(2);
             if (PROFILE && lane == 0) { const long long n = clock64(); pt[2] += n - tl; tl = n; }
         }
         if (PROFILE && lane == 0 && a.prof != nullptr)
-            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 20 + warp) * 4 + i] = pt[i];
+            for (int i = 0; i < 3; ++i) a.prof[(blockIdx.x * 28 + warp) * 4 + i] = pt[i];
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_AUX));
-        if (w4 == 0) {
-            // =========================== MMA issue warp ===========================
+        if (warp == 4 * WG_AUX) {
+            // =========================== MMA issue warp 1: GEMM1 ===========================
+            // Two issue warps, one per GEMM, each BLOCKING on its own barrier sequence (mbarrier.try_wait suspends the warp in
+            // hardware).  One lane polling both sequences executed a third of the kernel's instructions and took its issue slots
+            // from the row-owning warps of scheduler 0, which every role's barriers then waited for.
             if (lane == 0) {
-                constexpr uint32_t IDESC1 = f16::idesc(TM, H), IDESC2 = f16::idesc(TM, CN);
-                constexpr uint32_t LBO_W1 = H * 16, LBO_W2 = CN * 16, SBO = 128;
-                const uint32_t sW1 = tc::smem_u32(wsm), sW2 = tc::smem_u32(wsm + 2 * W1_WORDS);
-                int g1 = 0, g2 = 0;         // next tile of each GEMM
-                long long idle = 0, t0 = 0;
-                while (g2 < my_tiles) {
-                    bool did = false;
-                    if (g1 < my_tiles && g1 < g2 + 2) {
-                        const int b = g1 & 1;
-                        if (f16::mbar_test(&bars[B_A_FULL + b], (uint32_t)(g1 >> 1) & 1u)) {
-                            tc::tc_fence_after();
-                            const uint32_t dcol = tmem + COL_D1 + (uint32_t)b * H;
-                            for (int p = 0; p < np; ++p) {      // small terms first: lo*hi, hi*lo, then hi*hi
-                                const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                                const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                                const uint32_t acol = tmem + COL_EMB + (uint32_t)b * 64 + (pa ? 32u : 0u);
-                                const uint64_t bd0 = tc::smem_desc(sW1 + pb * (W1_WORDS * 4), LBO_W1, SBO);
+                constexpr uint32_t IDESC1 = f16::idesc(TM, H);
+                constexpr uint32_t LBO_W1 = H * 16, SBO = 128;
+                const uint32_t sW1 = tc::smem_u32(wsm);
+                long long idle = 0;
+                for (int j = 0; j < my_tiles; ++j) {
+                    const int b = j & 1;
+                    long long t0 = 0;
+                    if (PROFILE) t0 = clock64();
+                    tc::mbar_wait(&bars[B_A_FULL + b], (uint32_t)(j >> 1) & 1u);      // F waited for GEMM2(j - 2) before it filled D1[b] / emb[b]
+                    if (PROFILE) idle += clock64() - t0;
+                    MPF_EV(3);
+                    tc::tc_fence_after();
+                    const uint32_t dcol = tmem + COL_D1 + (uint32_t)b * H;
+                    for (int p = 0; p < np; ++p) {      // small terms first: lo*hi, hi*lo, then hi*hi
+                        const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                        const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                        const uint32_t acol = tmem + COL_EMB + (uint32_t)b * 64 + (pa ? 32u : 0u);
+                        const uint64_t bd0 = tc::smem_desc(sW1 + pb * (W1_WORDS * 4), LBO_W1, SBO);
 #pragma unroll
-                                for (int ks = 0; ks < CE / 16; ++ks)
-                                    f16::mma_ts(dcol, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, true);
-                            }
-                            tc::mma_commit(&bars[B_D1_FULL + b]);
-                            ++g1;
-                            did = true;
-                        }
+                        for (int ks = 0; ks < CE / 16; ++ks)
+                            f16::mma_ts(dcol, acol + ks * 8, bd0 + (uint64_t)((ks * 2 * LBO_W1) >> 4), IDESC1, true);
                     }
-                    if (g2 < g1) {
-                        const int b = g2 & 1;
-                        const uint32_t ph = (uint32_t)(g2 >> 1) & 1u;
-                        if (f16::mbar_test(&bars[B_Y1_FULL + b], ph) && (g2 < 2 || f16::mbar_test(&bars[B_D2_FREE + b], ph ^ 1u))) {
-                            tc::tc_fence_after();
-                            const uint32_t dcol = tmem + COL_D2 + (uint32_t)b * CN;
-                            bool acc = false;
-                            for (int p = 0; p < np; ++p) {
-                                const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                                const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                                // y1 as E1 leaves it: per 32-column chunk [hi: K steps 2i, 2i+1 | lo: the same]
-                                const uint32_t acol = tmem + COL_D1 + (uint32_t)b * H + (pa ? 16u : 0u);
-                                const uint64_t bd0 = tc::smem_desc(sW2 + pb * (W2_WORDS * 4), LBO_W2, SBO);
-#pragma unroll
-                                for (int ks = 0; ks < H / 16; ++ks) {
-                                    f16::mma_ts(dcol, acol + (ks >> 1) * 32 + (ks & 1) * 8, bd0 + (uint64_t)((ks * 2 * LBO_W2) >> 4), IDESC2, acc);
-                                    acc = true;
-                                }
-                            }
-                            tc::mma_commit(&bars[B_D2_FULL + b]);
-                            ++g2;
-                            did = true;
-                        }
-                    }
-                    if (PROFILE) {
-                        if (!did) { if (t0 == 0) t0 = clock64(); }
-                        else if (t0 != 0) { idle += clock64() - t0; t0 = 0; }
-                    }
+                    tc::mma_commit(&bars[B_D1_FULL + b]);
+                    MPF_EV(4);
                 }
-                if (PROFILE && a.prof != nullptr) a.prof[(blockIdx.x * 20 + warp) * 4] = idle;
+                if (PROFILE && a.prof != nullptr) a.prof[(blockIdx.x * 28 + warp) * 4] = idle;
+            }
+            __syncwarp();
+        } else if (warp == 4 * WG_AUX + 1) {
+            // =========================== MMA issue warp 2: GEMM2 ===========================
+            if (lane == 0) {
+                constexpr uint32_t IDESC2 = f16::idesc(TM, CN);
+                constexpr uint32_t LBO_W2 = CN * 16, SBO = 128;
+                const uint32_t sW2 = tc::smem_u32(wsm + 2 * W1_WORDS);
+                long long idle = 0;
+                for (int j = 0; j < my_tiles; ++j) {
+                    const int b = j & 1;
+                    const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                    long long t0 = 0;
+                    if (PROFILE) t0 = clock64();
+                    if (j >= 2) tc::mbar_wait(&bars[B_D2_FREE + b], ph ^ 1u);          // E2 has read D2[b] of tile j - 2
+                    tc::mbar_wait(&bars[B_Y1_FULL + b], ph);
+                    if (PROFILE) idle += clock64() - t0;
+                    MPF_EV(8);
+                    tc::tc_fence_after();
+                    const uint32_t dcol = tmem + COL_D2 + (uint32_t)b * CN;
+                    bool acc = false;
+                    for (int p = 0; p < np; ++p) {
+                        const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+                        const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+                        // y1 as E1 leaves it: per 32-column chunk [hi: K steps 2i, 2i+1 | lo: the same]
+                        const uint32_t acol = tmem + COL_D1 + (uint32_t)b * H + (pa ? 16u : 0u);
+                        const uint64_t bd0 = tc::smem_desc(sW2 + pb * (W2_WORDS * 4), LBO_W2, SBO);
+#pragma unroll
+                        for (int ks = 0; ks < H / 16; ++ks) {
+                            f16::mma_ts(dcol, acol + (ks >> 1) * 32 + (ks & 1) * 8, bd0 + (uint64_t)((ks * 2 * LBO_W2) >> 4), IDESC2, acc);
+                            acc = true;
+                        }
+                    }
+                    tc::mma_commit(&bars[B_D2_FULL + b]);
+                    MPF_EV(9);
+                }
+                if (PROFILE && a.prof != nullptr) a.prof[(blockIdx.x * 28 + 20) * 4 + 1] = idle;
             }
             __syncwarp();
         } else {
@@ -541,7 +613,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             // warp s copies rows s, s + 3, s + 6, ... of every tile: whole 512-byte rows per warp instruction (cp.async, 16 B per
             // lane; ONE warp needs ~7 300 cycles per tile for the 128 rows, four need ~2 000: tools/micro/bench_tmem.cu).  Row r
             // is stored with its 16-byte chunks XOR-swizzled by (r & 7) so that the row-owning F threads read it conflict free.
-            const int sI = w4 - 1;
+            const int sI = warp - 4 * WG_AUX - 2;
             constexpr int RPS = (TM + NSTAGER - 1) / NSTAGER;       // rows per stager (43)
             int id0 = -1, id1 = -1;
             auto load_ids = [&](int j) {
@@ -551,9 +623,12 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 id1 = (j < my_tiles && r1 < TM && e0 + r1 < a.n_edges) ? __ldg(a.src + e0 + r1) : -1;
             };
             load_ids(0);
+            long long pt[2] = {0, 0}, tl = 0;
+            if (PROFILE) tl = clock64();
             for (int j = 0; j < my_tiles; ++j) {
                 const int b = j & 1;
                 if (j >= 2) tc::mbar_wait(&bars[B_PS_FREE + b], ((uint32_t)(j >> 1) & 1u) ^ 1u);    // F has consumed tile j - 2
+                if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
                 float* dst = ps + (size_t)b * TM * H;
                 const int my0 = id0, my1 = id1;
                 load_ids(j + 1);
@@ -565,8 +640,11 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 }
                 // the barrier completes when the copies of all stager lanes have landed; nobody waits here
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&bars[B_PS_FULL + b])) : "memory");
+                if (PROFILE && lane == 0) { const long long n = clock64(); pt[1] += n - tl; tl = n; }
             }
             cp_async_wait<0>();
+            if (PROFILE && lane == 0 && a.prof != nullptr && sI == 0)
+                for (int i = 0; i < 2; ++i) a.prof[(blockIdx.x * 28 + 22) * 4 + i] = pt[i];
         }
     }
 
@@ -675,7 +753,7 @@ int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& 
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (g_f16_profile) {    // developer aid (rgnn_set_option("debug", 8)): per-role cycle counters; synchronises
         long long* prof = nullptr;
-        const size_t n = (size_t)grid * 20 * 4;
+        const size_t n = (size_t)grid * 28 * 4 + 16 * 16;
         RGNN_CHECK_CUDA(cudaMalloc(&prof, sizeof(long long) * n));
         RGNN_CHECK_CUDA(cudaMemsetAsync(prof, 0, sizeof(long long) * n, stream));
         a.prof = prof;
@@ -683,12 +761,24 @@ int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& 
         RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
         long long* h = new long long[n];
         RGNN_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(long long) * n, cudaMemcpyDeviceToHost));
-        static const char* role[20] = {"E1a", "", "", "", "E1b", "", "", "", "E2", "", "", "", "F", "", "", "", "MMA idle", "E1a sweep2: ld+wait | math | st+wait", "", ""};
-        for (int w = 0; w < 20; w += (w == 16 ? 1 : (w == 17 ? 3 : 4))) {
+        static const char* role[24] = {"E1a", "", "", "", "E1b", "", "", "", "E2a", "", "", "", "E2b", "", "", "", "F", "", "", "", "MMA wait: GEMM1 | GEMM2", "E1a sweep2: ld+wait | math | st+wait", "stager 0: wait | issue", ""};
+        static const int slots[8] = {0, 4, 8, 12, 16, 20, 21, 22};
+        for (int si = 0; si < 8; ++si) {
+            const int w = slots[si];
             double tot[4] = {0, 0, 0, 0};
-            for (int b = 0; b < grid; ++b) for (int i = 0; i < 4; ++i) tot[i] += (double)h[((size_t)b * 20 + w) * 4 + i];
+            for (int b = 0; b < grid; ++b) for (int i = 0; i < 4; ++i) tot[i] += (double)h[((size_t)b * 28 + w) * 4 + i];
             fprintf(stderr, "[mp_edge_f16 profile] %s warp %d cycles per tile: p0=%.0f p1=%.0f p2=%.0f\n", role[w], w, tot[0] / n_tiles,
                     tot[1] / n_tiles, tot[2] / n_tiles);
+        }
+        {
+            const long long* ev = h + (size_t)grid * 28 * 4;
+            const long long t0 = ev[0];
+            fprintf(stderr, "[mp_edge_f16 events] block 0, tiles 16..31 (cycles since F(16) got its buffer): F buf | F ps | F done | G1 see | G1 iss | E1 see | E1 stat | E1 done | G2 see | G2 iss | E2 see | E2 stage | E2 epi | E2 sum\n");
+            for (int t = 0; t < 16; ++t) {
+                fprintf(stderr, "  tile %2d:", 16 + t);
+                for (int k = 0; k < 14; ++k) fprintf(stderr, " %6lld", ev[t * 16 + k] ? ev[t * 16 + k] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
         }
         delete[] h;
         cudaFree(prof);
