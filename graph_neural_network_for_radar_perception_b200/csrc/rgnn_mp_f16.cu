@@ -55,6 +55,7 @@ struct MpF16Args {
     const float* s2;
     const float* m2;
     long long* prof;        // PROFILE builds
+    int nstager;            // staging warps in use (2 .. NSTAGER)
 };
 
 namespace mpf {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
     if (tid < CN) bias_s[tid] = a.b2 != nullptr ? __ldg(a.b2 + tid) : 0.f;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars[B_PS_FULL + i], 32 * NSTAGER);    // every stager lane: cp.async.mbarrier.arrive.noinc when its copies land
+            tc::mbar_init(&bars[B_PS_FULL + i], 32 * a.nstager);    // every stager lane: cp.async.mbarrier.arrive.noinc when its copies land
             tc::mbar_init(&bars[B_PS_FREE + i], 4);
             tc::mbar_init(&bars[B_A_FULL + i], 4);
             tc::mbar_init(&bars[B_D1_FULL + i], 1);
@@ -614,18 +615,20 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
             // lane; ONE warp needs ~7 300 cycles per tile for the 128 rows, four need ~2 000: tools/micro/bench_tmem.cu).  Row r
             // is stored with its 16-byte chunks XOR-swizzled by (r & 7) so that the row-owning F threads read it conflict free.
             const int sI = warp - 4 * WG_AUX - 2;
-            constexpr int RPS = (TM + NSTAGER - 1) / NSTAGER;       // rows per stager (43)
+            const int NS = a.nstager;
+            const int RPS = (TM + NS - 1) / NS;       // rows per stager
             int id0 = -1, id1 = -1;
             auto load_ids = [&](int j) {
                 const int e0 = ((int)blockIdx.x + j * G) * TM;
-                const int r0 = sI + NSTAGER * lane, r1 = sI + NSTAGER * (lane + 32);
+                const int r0 = sI + NS * lane, r1 = sI + NS * (lane + 32);
                 id0 = (j < my_tiles && r0 < TM && e0 + r0 < a.n_edges) ? __ldg(a.src + e0 + r0) : -1;
                 id1 = (j < my_tiles && r1 < TM && e0 + r1 < a.n_edges) ? __ldg(a.src + e0 + r1) : -1;
             };
+            const int n_my = sI < NS ? my_tiles : 0;        // surplus stagers idle
             load_ids(0);
             long long pt[2] = {0, 0}, tl = 0;
             if (PROFILE) tl = clock64();
-            for (int j = 0; j < my_tiles; ++j) {
+            for (int j = 0; j < n_my; ++j) {
                 const int b = j & 1;
                 if (j >= 2) tc::mbar_wait(&bars[B_PS_FREE + b], ((uint32_t)(j >> 1) & 1u) ^ 1u);    // F has consumed tile j - 2
                 if (PROFILE && lane == 0) { const long long n = clock64(); pt[0] += n - tl; tl = n; }
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(mpf::NTHREADS, 1) mp_edge_f16_kernel(const __g
                 load_ids(j + 1);
 #pragma unroll 4
                 for (int i = 0; i < RPS; ++i) {
-                    const int r = sI + NSTAGER * i;
+                    const int r = sI + NS * i;
                     const int sn = __shfl_sync(0xffffffffu, i < 32 ? my0 : my1, i & 31);
                     if (sn >= 0) cp_async16(dst + r * H + ((lane ^ (r & 7)) << 2), a.P + (size_t)sn * (2 * H) + H + 4 * lane);
                 }
@@ -692,6 +695,7 @@ __global__ void pack_split_f16_kernel(const float* __restrict__ W, int off, int 
 static int g_f16_fwd = 1;
 static int g_f16_passes = 3;
 static int g_f16_profile = 0;
+static int g_f16_stagers = mpf::NSTAGER;
 
 bool mp_f16_supported(const ConvDims& d) { return g_f16_fwd && d.cn == 64 && d.ce == 64 && d.h == 128; }
 int mp_f16_passes() { return g_f16_passes; }
@@ -743,6 +747,7 @@ int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& 
     a.s1 = m0.norm_scale; a.m1 = m0.norm_shift;
     a.b2 = m1.bias; a.s2 = m1.norm_scale; a.m2 = m1.norm_shift;
     a.prof = nullptr;
+    a.nstager = g_f16_stagers;
     static PerDeviceOnce once;
     if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_edge_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mpf::SMEM));
@@ -792,6 +797,7 @@ int run_conv_edges_f16(const rgnn_conv& c, const ConvDims& d, const rgnn_graph& 
 int mp_f16_set_option(const char* name, int value) {
     if (strcmp(name, "f16_fwd") == 0 && (value == 0 || value == 1)) { g_f16_fwd = value; return 1; }
     if (strcmp(name, "f16_passes") == 0 && (value == 1 || value == 3)) { g_f16_passes = value; return 1; }
+    if (strcmp(name, "f16_stagers") == 0 && value >= 2 && value <= mpf::NSTAGER) { g_f16_stagers = value; return 1; }
     if (strcmp(name, "debug") == 0) { g_f16_profile = (value & 8) != 0; return 0; }      // shared with the other kernels
     return 0;
 }
