@@ -621,19 +621,6 @@ __global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const 
                 tile_j[i] = i; step[i] = 0; uses[i] = 0;
                 if (i < my_tiles) ++remaining;
             }
-            auto gemm_ts = [&](uint32_t dcol, uint32_t acol, uint32_t sB, int K, int N, uint32_t idesc_) {
-                const uint32_t lbo = (uint32_t)N * 16, img = (uint32_t)K * N * 2;
-                bool acc = false;
-                for (int p = 0; p < np; ++p) {
-                    const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                    const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                    const uint64_t bd0 = tc::smem_desc(sB + pb * img, lbo, 128);
-                    for (int ks = 0; ks < K / 16; ++ks) {
-                        f16::mma_ts(dcol, acol + (ks >> 1) * 32 + (ks & 1) * 8 + (pa ? 16u : 0u), bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc_, acc);
-                        acc = true;
-                    }
-                }
-            };
             while (remaining > 0) {
                 bool did = false;
 #pragma unroll
@@ -642,9 +629,9 @@ __global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const 
                     if (!f16::mbar_test(&a_full[i], uses[i] & 1u)) continue;
                     tc::tc_fence_after();
                     const uint32_t xr = tmem + (uint32_t)i * 256, yr = xr + 128;
-                    if (step[i] == 0) gemm_ts(yr, xr, sWU, 128, 64, ID64);            // update layer: Y = cat(x, agg) W_upd^T
-                    else if (step[i] == 1) gemm_ts(xr, yr, sWPT, 64, 128, ID128);      // target half of the projection
-                    else gemm_ts(xr, yr, sWPS, 64, 128, ID128);                        // source half
+                    if (step[i] == 0) f16::gemm_ts<128, 64>(yr, xr, sWU, ID64, false, np);            // update layer: Y = cat(x, agg) W_upd^T
+                    else if (step[i] == 1) f16::gemm_ts<64, 128>(xr, yr, sWPT, ID128, false, np);      // target half of the projection
+                    else f16::gemm_ts<64, 128>(xr, yr, sWPS, ID128, false, np);                        // source half
                     tc::mma_commit(&d_full[i]);
                     ++uses[i];
                     if (++step[i] == n_mma) {

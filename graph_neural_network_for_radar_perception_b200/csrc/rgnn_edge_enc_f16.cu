@@ -366,20 +366,6 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                 }
                 tc::mma_commit(&bars[B_D0_FULL + 2 * x + (c & 1)]);
             };
-            // generic TS GEMM: D[dcol] (+)= A-format operand at acol (K columns) * image at sB (N rows)
-            auto gemm_ts = [&](uint32_t dcol, uint32_t acol, uint32_t sB, int K, int N, uint32_t idesc_, bool acc0) {
-                const uint32_t lbo = (uint32_t)N * 16, img = (uint32_t)K * N * 2;
-                bool acc = acc0;
-                for (int p = 0; p < np; ++p) {
-                    const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
-                    const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
-                    const uint64_t bd0 = tc::smem_desc(sB + pb * img, lbo, 128);
-                    for (int ks = 0; ks < K / 16; ++ks) {
-                        f16::mma_ts(dcol, acol + (ks >> 1) * 32 + (ks & 1) * 8 + (pa ? 16u : 0u), bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc_, acc);
-                        acc = true;
-                    }
-                }
-            };
             for (int t = 0; t < n_pairs; ++t) {
                 for (int x = 0; x < 2; ++x) {           // first two L0 chunks of both groups
                     wait_a(x);
@@ -392,8 +378,8 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                     ++n_full[sl];
                     for (int x = 0; x < 2; ++x) {
                         wait_a(x);                       // y0 chunk c of group x is in D0[c & 1]
-                        gemm_ts(tmem + (uint32_t)x * 256 + 128, tmem + (uint32_t)x * 256 + (uint32_t)(c & 1) * 64,
-                                sRing + sl * (W1_BLK_WORDS * 4), 64, C1, ID128, c > 0);
+                        f16::gemm_ts<64, C1>(tmem + (uint32_t)x * 256 + 128, tmem + (uint32_t)x * 256 + (uint32_t)(c & 1) * 64,
+                                            sRing + sl * (W1_BLK_WORDS * 4), ID128, c > 0, np);
                         if (c + 2 < 4) g0(x, c + 2);     // the buffer is free again: next chunk of L0
                         if (c == 3) tc::mma_commit(&bars[B_D_FULL + x]);
                     }
@@ -401,12 +387,12 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                 }
                 for (int x = 0; x < 2; ++x) {           // L2: A = y1 (D1 columns), D2 = the two D0 buffers
                     wait_a(x);
-                    gemm_ts(tmem + (uint32_t)x * 256, tmem + (uint32_t)x * 256 + 128, sW2, C1, C2, ID128, false);
+                    f16::gemm_ts<C1, C2>(tmem + (uint32_t)x * 256, tmem + (uint32_t)x * 256 + 128, sW2, ID128, false, np);
                     tc::mma_commit(&bars[B_D_FULL + x]);
                 }
                 for (int x = 0; x < 2; ++x) {           // L3: A = y2, D3 = first 64 columns of D1
                     wait_a(x);
-                    gemm_ts(tmem + (uint32_t)x * 256 + 128, tmem + (uint32_t)x * 256, sW3, C2, C3, ID64, false);
+                    f16::gemm_ts<C2, C3>(tmem + (uint32_t)x * 256 + 128, tmem + (uint32_t)x * 256, sW3, ID64, false, np);
                     tc::mma_commit(&bars[B_D_FULL + x]);
                 }
             }

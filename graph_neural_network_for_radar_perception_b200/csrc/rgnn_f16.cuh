@@ -110,6 +110,30 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 
+// TS GEMM of one layer, issued by ONE lane: D[dcol] (+)= A-format operand at acol (K columns) * image at sB (N rows).  Shapes are template
+// parameters and the loops are unrolled: with runtime K / N the lane spent ~85 cycles of address arithmetic per MMA (64-bit descriptor adds,
+// loop control in one dependent instruction stream) where an MMA takes 34 - 68, and the tensor pipe waited for it (measured with cycle
+// counters in the lane: 18.9 k -> 16.3 k cycles of issue per tile pair of 30 k).
+template <int K, int N>
+__device__ __forceinline__ void gemm_ts(uint32_t dcol, uint32_t acol, uint32_t sB, uint32_t idesc_, bool acc0, int np) {
+    constexpr uint32_t lbo = (uint32_t)N * 16, img = (uint32_t)K * N * 2;
+    bool acc = acc0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (p < np) {
+            const int pa = (np == 1) ? 0 : (p == 0 ? 1 : 0);
+            const int pb = (np == 1) ? 0 : (p == 1 ? 1 : 0);
+            const uint64_t bd0 = tc::smem_desc(sB + pb * img, lbo, 128);
+            const uint32_t a0 = acol + (pa ? 16u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < K / 16; ++ks) {
+                mma_ts(dcol, a0 + (ks >> 1) * 32 + (ks & 1) * 8, bd0 + (uint64_t)((ks * 2 * lbo) >> 4), idesc_, acc);
+                acc = true;
+            }
+        }
+    }
+}
+
 }  // namespace f16
 
 // TILED layout of the pre-split edge rows (what the edge encoder writes and the message kernels read): per tile of 128 edges one
