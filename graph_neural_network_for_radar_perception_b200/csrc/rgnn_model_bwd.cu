@@ -236,6 +236,10 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
     const float* xL = pl.x[L];
     int rc;
+    // Training envelope: the backward of a conv block handles the hoisted projection gradient dP (N, 2 h) as ONE
+    // row of at most 256 channels.  Wider message layers (msg_mlp_hidden_dim > 128, i.e. hidden width 128 / 256 of the sweep) run the
+    // forward but are NOT validated for training -- at hidden 128 the gradients of msg.0 came out wrong against the oracle -- so they fail here
+    RGNN_REQUIRE(2 * d.h <= 256 && d.cn <= 128, "backward: msg_mlp_hidden_dim %d / node width %d are outside the training envelope (<= 128 / <= 128)", d.h, d.cn);
     // ---- heads: accumulate dL/dx_L in pl.dx ----
     // node-sized stack: tensor-core chain backward when the forward saved its activations, else the recompute tile program
     auto node_bwd = [&](int i, const rgnn_stack& s, const float* y_out, const float* g_top, bool accumulate) -> int {

@@ -262,13 +262,14 @@ def test_hidden_width_sweep_forward_matches_oracle(hidden):
         assert_close(g.cpu().numpy(), w, 1e-4, 1e-5 * max(np.abs(w).max(), 1.0), f'hidden {hidden}: {name}')
 
 
-def test_hidden_width_32_training_step_matches_oracle_autograd():
-    """Training at hidden width 32 (every gradient through the recompute tile programs on the CUDA cores; the natural-layout
-    weight operands of their dgrad steps are 32 / 96 columns wide, zero-filled to the 64-column blocks of the tile GEMM),
+@pytest.mark.parametrize('hidden', [32])
+def test_hidden_width_training_step_matches_oracle_autograd(hidden):
+    """Training off the reference plan: hidden width 32 (every gradient through the recompute tile programs on the CUDA cores; the
+    natural-layout weight operands of their dgrad steps are 32 / 96 columns wide, zero-filled to the 64-column blocks of the tile GEMM),
     random-init weights, against the same yardstick as the reference plan."""
     from graph_neural_network_for_radar_perception_b200 import Model_Training
     torch.manual_seed(1234)
-    cfg = _width_config(32)
+    cfg = _width_config(hidden)
     sd0 = {k: v.detach().clone() for k, v in Model_Training(cfg, 'cpu').state_dict().items()}
     frames = synth_batch((150, 90), seed0=760)
     ys = GradientYardstick(sd0, frames, members=5, flip_window=FLIP_WINDOW)
@@ -282,16 +283,18 @@ def test_hidden_width_32_training_step_matches_oracle_autograd():
     sum(loss.values()).backward()
     got = model_grads(m)
     assert set(got) == set(ys.names)
-    ys.check(got, what='hidden width 32, random-init weights')
+    ys.check(got, what=f'hidden width {hidden}, random-init weights')
 
 
-def test_hidden_width_256_training_fails_loudly():
-    """Outside the training envelope: the backward tile programs hold rows of at most 256 channels; a wider
-    plan must raise, not compute something else."""
+@pytest.mark.parametrize('hidden', [128, 256])
+def test_hidden_width_beyond_the_training_envelope_fails_loudly(hidden):
+    """Outside the training envelope: the backward holds the hoisted projection gradient (2 x msg hidden
+    channels) as one row of at most 256 channels; a wider plan must raise, not compute something else (at hidden 128 it used to run
+    and return wrong msg.0 gradients, found with the yardstick of the test above)."""
     from graph_neural_network_for_radar_perception_b200 import Model_Training
     from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
     torch.manual_seed(1234)
-    m = Model_Training(_width_config(256), 'cuda').to('cuda').train()
+    m = Model_Training(_width_config(hidden), 'cuda').to('cuda').train()
     frames = synth_batch((60,), seed0=770)
     loss, _ = m([f['nf'].cuda() for f in frames], [f['ef'].cuda() for f in frames], [f['ei'].cuda() for f in frames],
                 [None], batch_labels(frames, 'cuda'))
