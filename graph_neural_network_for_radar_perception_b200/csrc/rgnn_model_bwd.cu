@@ -107,13 +107,25 @@ static int stack_bwd(const rgnn_stack& s, const float* x, const int* ridx, const
 // dL/dP (N, 2h) -> weight gradient of the projection part of msg.0 and the contribution to dL/dx, added into wcur
 static void proj_bwd(BwdBuilder& b, const rgnn_conv& c, const ConvDims& d, const float* dP, int r_x, int r_tmp) {
     const rgnn_linear& m0 = c.msg.layer[0];
-    b.load_rows(b.wnxt, dP, 2 * d.h, 2 * d.h);
-    // msg.0.weight (h, 2cn+ce): columns [0,cn) act on x_target, [cn,2cn) on x_source (gnn_blocks.py:113)
-    b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, 0, 0, nullptr);
-    b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, d.cn, d.h, nullptr);
     const float* wp_nat = m0.weight_t + conv_msg0_proj_floats(d) + conv_msg0_edge_floats(d);
-    b.gemm(b.wnxt, r_tmp, wp_nat, round_up(d.cn, 64), 2 * d.h, 2 * d.h, d.cn, round_up(d.cn, 64), nullptr);
-    b.add_region(b.wcur, r_tmp, d.cn);
+    const int ldn = round_up(d.cn, 64);
+    // msg.0.weight (h, 2cn+ce): columns [0,cn) act on x_target, [cn,2cn) on x_source (gnn_blocks.py:113)
+    if (2 * d.h <= 256) {       // the whole dP row fits a work region
+        b.load_rows(b.wnxt, dP, 2 * d.h, 2 * d.h);
+        b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, 0, 0, nullptr);
+        b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, d.cn, d.h, nullptr);
+        b.gemm(b.wnxt, r_tmp, wp_nat, ldn, 2 * d.h, 2 * d.h, d.cn, ldn, nullptr);
+        b.add_region(b.wcur, r_tmp, d.cn);
+        return;
+    }
+    // wider message layers (h <= 256): the target and the source half of dP pass through the 256-column work region one after the
+    // other (a 2 h = 512 column row used to overrun it: wrong, run-to-run different msg.0 gradients at hidden width 128)
+    for (int half = 0; half < 2; ++half) {
+        b.load_rows(b.wnxt, dP + (size_t)half * d.h, 2 * d.h, d.h);
+        b.wgrad(b.wnxt, r_x, d.h, d.cn, m0.grad_weight, m0.in_features, half * d.cn, 0, nullptr);
+        b.gemm(b.wnxt, r_tmp, wp_nat + (size_t)half * d.h * ldn, ldn, d.h, d.h, d.cn, ldn, nullptr);
+        b.add_region(b.wcur, r_tmp, d.cn);
+    }
 }
 
 static int conv_nodes_bwd(const rgnn_conv& c, const ConvDims& d, int n_nodes, const float* x, const float* agg,
@@ -236,10 +248,9 @@ static int detector_bwd(const rgnn_detector& net, const rgnn_graph& g, const flo
     const int N = g.n_nodes, E = g.n_edges, L = net.n_conv;
     const float* xL = pl.x[L];
     int rc;
-    // Training envelope: the backward of a conv block handles the hoisted projection gradient dP (N, 2 h) as ONE
-    // row of at most 256 channels.  Wider message layers (msg_mlp_hidden_dim > 128, i.e. hidden width 128 / 256 of the sweep) run the
-    // forward but are NOT validated for training -- at hidden 128 the gradients of msg.0 came out wrong against the oracle -- so they fail here
-    RGNN_REQUIRE(2 * d.h <= 256 && d.cn <= 128, "backward: msg_mlp_hidden_dim %d / node width %d are outside the training envelope (<= 128 / <= 128)", d.h, d.cn);
+    // Training envelope: the backward tile programs hold rows of at most 256 channels (dz1 of msg.0, each half of the
+    // hoisted projection gradient dP); wider plans (hidden width 256 of the sweep: msg_mlp_hidden_dim 512) run the forward only
+    RGNN_REQUIRE(d.h <= 256 && d.cn <= 128, "backward: msg_mlp_hidden_dim %d / node width %d are outside the training envelope (<= 256 / <= 128)", d.h, d.cn);
     // ---- heads: accumulate dL/dx_L in pl.dx ----
     // node-sized stack: tensor-core chain backward when the forward saved its activations, else the recompute tile program
     auto node_bwd = [&](int i, const rgnn_stack& s, const float* y_out, const float* g_top, bool accumulate) -> int {

@@ -262,7 +262,7 @@ def test_hidden_width_sweep_forward_matches_oracle(hidden):
         assert_close(g.cpu().numpy(), w, 1e-4, 1e-5 * max(np.abs(w).max(), 1.0), f'hidden {hidden}: {name}')
 
 
-@pytest.mark.parametrize('hidden', [32])
+@pytest.mark.parametrize('hidden', [32, 128])
 def test_hidden_width_training_step_matches_oracle_autograd(hidden):
     """Training off the reference plan: hidden width 32 (every gradient through the recompute tile programs on the CUDA cores; the
     natural-layout weight operands of their dgrad steps are 32 / 96 columns wide, zero-filled to the 64-column blocks of the tile GEMM),
@@ -286,7 +286,7 @@ def test_hidden_width_training_step_matches_oracle_autograd(hidden):
     ys.check(got, what=f'hidden width {hidden}, random-init weights')
 
 
-@pytest.mark.parametrize('hidden', [128, 256])
+@pytest.mark.parametrize('hidden', [256])
 def test_hidden_width_beyond_the_training_envelope_fails_loudly(hidden):
     """Outside the training envelope: the backward holds the hoisted projection gradient (2 x msg hidden
     channels) as one row of at most 256 channels; a wider plan must raise, not compute something else (at hidden 128 it used to run
