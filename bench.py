@@ -507,6 +507,13 @@ def measure_c1(det, model, dev):
     with torch.no_grad():
         out['inference_1_frame_1000_points_ms'] = lat(lambda: det(bf.node_features, bf.edge_features, ei, None, cl))
         out['graph_build_1_frame_1000_points_ms'] = lat(lambda: gf.build_graph_batch(pts, fp, EPS2, KNN, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH))
+        # the reference's inference call proper (inference/output.py:88-94: no cluster lists; offsets -> centres -> connected components of
+        # the predicted links on the device -> class head on the found clusters), member lists returned as the reference returns them
+        other = torch.from_numpy(np.stack([d['meas_px'], d['meas_py'], d['meas_vx'], d['meas_vy']], axis=1).astype(np.float32)).to(dev)
+        had = getattr(det, 'extract_proposals', False)
+        det.set_param_for_proposal_extraction(1.4, True)
+        out['inference_with_proposal_extraction_1_frame_1000_points_ms'] = lat(lambda: det(bf.node_features, bf.edge_features, ei, None, None, other))
+        det.extract_proposals = had
     # 8 frames x 100 points through Model_Training.forward with per-frame lists (forward + losses; eval mode, no backward)
     nf_l, ef_l, ei_l = [], [], []
     labels = {k: [] for k in ('cluster_node_idx', 'cluster_labels', 'edge_class', 'node_class', 'node_offsets')}

@@ -448,6 +448,43 @@ class DetectorFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(views)
 
 
+def run_detector_then_cluster(model, gb: GraphBatch, node_features, edge_features, cluster_fn):
+    """Inference with proposal extraction in ONE pass over the graph (no gradient): the detector forward with no clusters, then
+    `cluster_fn(node_off, link_cls)` sets gb.cl_ptr / cl_members / n_clusters, then ONLY the per-cluster class head runs on the
+    per-node stem output that is still in the forward's workspace (rgnn_detector_obj_head).  The reference evaluates the encoders
+    and the heads once and the class head afterwards as well (gnn_detector.py:164-187)."""
+    _require_cuda(node_features, edge_features)
+    nf, ef = _f32c(node_features), _f32c(edge_features)
+    table = detector_table(model)
+    table.refill(None)
+    s = stream_ptr()
+    table.ensure_packed(s)
+    g = gb.c_struct()
+    nbytes = lib().rgnn_detector_workspace_bytes(C.byref(table.det), C.byref(g), 0)
+    if nbytes == 0:
+        raise _cabi.RgnnError('rgnn_detector_workspace_bytes: ' + lib().rgnn_last_error().decode())
+    dev = nf.device
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    det = table.det
+    n_cls = det.head_node.layer[det.head_node.n - 1].out_features
+    n_off = det.head_offset.layer[det.head_offset.n - 1].out_features
+    n_lnk = det.head_link.layer[det.head_link.n - 1].out_features
+    n_obj = det.head_class.layer[det.head_class.n - 1].out_features
+    node_cls = torch.empty((gb.n_nodes, n_cls), dtype=torch.float32, device=dev)
+    node_off = torch.empty((gb.n_nodes, n_off), dtype=torch.float32, device=dev)
+    link_cls = torch.empty((gb.n_und, n_lnk), dtype=torch.float32, device=dev)
+    none = torch.empty((max(gb.n_clusters, 0), n_obj), dtype=torch.float32, device=dev)
+    check(lib().rgnn_detector_fwd(C.byref(det), C.byref(g), ptr(nf), ptr(ef), ptr(node_cls), ptr(node_off), ptr(link_cls),
+                                  ptr(none), ptr(ws), nbytes, 0, s), 'rgnn_detector_fwd')
+    cluster_fn(node_off, link_cls)              # fills the cluster fields of gb
+    g2 = gb.c_struct()
+    if lib().rgnn_detector_workspace_bytes(C.byref(det), C.byref(g2), 0) > nbytes:
+        raise _cabi.RgnnError('detector workspace grew with the clusters')      # the plan does not depend on them
+    obj_cls = torch.empty((gb.n_clusters, n_obj), dtype=torch.float32, device=dev)
+    check(lib().rgnn_detector_obj_head(C.byref(det), C.byref(g2), ptr(obj_cls), ptr(ws), nbytes, 0, s), 'rgnn_detector_obj_head')
+    return node_cls, node_off, link_cls, obj_cls
+
+
 def run_detector(model, gb: GraphBatch, node_features, edge_features, training: Optional[bool] = None):
     params = detector_table(model).tab.tensors      # ParamTable order == order of the returned gradients
     if training is None:

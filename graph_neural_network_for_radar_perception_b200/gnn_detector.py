@@ -18,7 +18,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from ._engine import GraphBatch, run_detector
+from ._engine import GraphBatch, run_detector, run_detector_then_cluster
 from .clustering import Simple_DBSCAN
 from .compute_offsets import normalize_gt_offsets, unnormalize_gt_offsets
 from .gnn_blocks import (graph_convolution, graph_feature_encoding, link_predictions, node_offset_predictions,
@@ -104,15 +104,28 @@ class Model_Inference(nn.Module):
                 raise AttributeError("call set_param_for_proposal_extraction(eps, ...) before forward without "
                                      "cluster_node_idx (the reference fails here too: gnn_detector.py:170)")
             gb.set_clusters([[]], [0], node_features.device)
-            with torch.no_grad():
-                _, off0, link0, _ = run_detector(self, gb, node_features, edge_features, training=False)
-            reg = unnormalize_gt_offsets(off0.clone(), self.reg_mu, self.reg_sigma)
-            centres = other_features[:, :2].to(torch.float32) + reg
-            res = self.clustering_obj.cluster_nodes_device(centres, gb, link0)
-            cluster_members_list = res.member_lists()
-            gb.cl_ptr, gb.cl_members, gb.n_clusters = res.cl_ptr, res.cl_members, res.n_clusters
-            gb.frame_cluster_ptr = [0, res.n_clusters]
-            node_cls, node_off, link_cls, obj_cls = run_detector(self, gb, node_features, edge_features)
+            found = {}
+
+            def cluster(off0, link0):
+                reg = unnormalize_gt_offsets(off0.clone(), self.reg_mu, self.reg_sigma)
+                centres = other_features[:, :2].to(torch.float32) + reg
+                res = self.clustering_obj.cluster_nodes_device(centres, gb, link0)
+                found['members'] = res.member_lists()
+                gb.cl_ptr, gb.cl_members, gb.n_clusters = res.cl_ptr, res.cl_members, res.n_clusters
+                gb.frame_cluster_ptr = [0, res.n_clusters]
+
+            needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            if not needs_grad:
+                # inference: ONE pass; the class head alone runs after the clustering (on the stem output kept in the workspace)
+                node_cls, node_off, link_cls, obj_cls = run_detector_then_cluster(self, gb, node_features, edge_features, cluster)
+            else:
+                # fine-tuning of the class head (Model_Object_Classifier_Finetuning): a first pass without gradient finds the
+                # clusters, the second one is the differentiable forward
+                with torch.no_grad():
+                    _, off0, link0, _ = run_detector(self, gb, node_features, edge_features, training=False)
+                cluster(off0, link0)
+                node_cls, node_off, link_cls, obj_cls = run_detector(self, gb, node_features, edge_features)
+            cluster_members_list = found['members']
         if self.extract_proposals:
             return node_cls, node_off, link_cls, obj_cls, cluster_members_list
         return node_cls, node_off, link_cls, obj_cls
