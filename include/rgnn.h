@@ -41,6 +41,11 @@ const char* rgnn_last_error(void);
  *                  1           = single TF32 pass (faster, ~1e-3 relative error per layer; never the default)
  *   "tensor_cores" 1 (default) = tcgen05 kernels where the channel plan allows; 0 = FFMA tile programs only.
  *   "tensor_cores_bwd" 1 (default) = tcgen05 backward of the message function; 0 = FFMA backward tile programs.
+ *   "f16_fwd" / "f16_bwd" / "f16_node_bwd" / "f16_edge_enc"  1 (default) = the fixed-shape fp16-split kernels of round 2; 0 = the round-1 kernels
+ *   "f16_passes"   3 (default) = hi/lo split products, fp32-equivalent; 1 = plain fp16 operands, fp32 accumulate (reduced precision:
+ *                  5e-3 of each output's largest magnitude, tests/test_model_gpu.py; never the default)
+ *   "f16_stagers"  2 .. 6 (default 6) staging warps of the forward message kernel (developer aid: profiles/README.md)
+ *   "debug"        bit mask of developer aids: 8 = per-role cycle counters / event timeline of the message kernels (synchronises)
  * rgnn_get_option returns -1 for an unknown name. */
 int rgnn_set_option(const char* name, int value);
 int rgnn_get_option(const char* name);
