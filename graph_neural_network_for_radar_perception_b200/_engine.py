@@ -14,10 +14,20 @@ from ._cabi import check, lib, ptr, stream_ptr
 
 
 def _require_cuda(*tensors):
+    """No CPU path, and the C library launches on the CURRENT device with the current stream of that device: tensors on another
+    GPU would be read by kernels of the wrong device, so that fails here (one process per GPU, or torch.cuda.device(i))."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _cabi.RgnnError('this implementation has no CPU path: tensors must live on a CUDA device '
                                   f'(got {t.device})')
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _cabi.RgnnError(f'tensor on {t.device} but the current CUDA device is cuda:{cur}: call inside '
+                                  f'`with torch.cuda.device({t.device.index}):` (kernels run on the current device and stream)')
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:

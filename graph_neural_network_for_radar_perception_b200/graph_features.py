@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ._cabi import check, lib, ptr, stream_ptr
-from ._engine import GraphBatch
+from ._engine import GraphBatch, _require_cuda
 
 _KEYS = ('meas_px', 'meas_py', 'meas_vx', 'meas_vy', 'meas_vr', 'meas_rcs', 'meas_timestamp')
 
@@ -48,6 +48,7 @@ def build_graph_batch(points: Dict[str, torch.Tensor], frame_ptr: Sequence[int],
     """points: device tensors meas_px, meas_py (f32) [+ meas_vx, meas_vy, meas_vr, meas_rcs (f32),
     meas_timestamp (int64) when with_features], all frames concatenated; frame_ptr: host offsets (F+1)."""
     px, py = points['meas_px'].contiguous(), points['meas_py'].contiguous()
+    _require_cuda(px, py)
     dev = px.device
     n, nf = int(px.shape[0]), len(frame_ptr) - 1
     fp_host = np.ascontiguousarray(np.asarray(frame_ptr, dtype=np.int32))

@@ -80,3 +80,28 @@ def test_two_rank_step_equals_single_process_step(tmp_path):
     # per-rank partial sums + all-reduce vs one sum; lr = 0.005 scales any gradient noise down)
     d = (r0['params'] - single_params).abs()
     assert float(d.max()) <= 1e-6 + 1e-5 * float(single_params.abs().max()), float(d.max())
+
+
+def test_tensors_on_a_non_current_device_fail_loudly(ckpt_state_dict):
+    """The C library launches on the current device and its current stream: a model on cuda:1 called while cuda:0 is current must
+    raise, and work inside torch.cuda.device(1)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from gpu_util import load_model, synth_batch
+    from graph_neural_network_for_radar_perception_b200._cabi import RgnnError
+    f = synth_batch((120,), seed0=31)[0]
+    d1 = torch.device('cuda', 1)
+    m = load_model(ckpt_state_dict, d1).pred.eval()
+    args = (f['nf'].to(d1), f['ef'].to(d1), f['ei'].to(d1), None, [c.to(d1) for c in f['clusters']] if 'clusters' in f else [torch.arange(4, device=d1)])
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        with pytest.raises(RgnnError):
+            m(*args)
+        with torch.cuda.device(1):
+            out = m(*args)
+        m0 = load_model(ckpt_state_dict, 'cuda:0').pred.eval()
+        ref = m0(*[a.to('cuda:0') if isinstance(a, torch.Tensor) else ([c.to('cuda:0') for c in a] if a is not None else None) for a in args])
+    for a, b in zip(out, ref):
+        assert torch.equal(a.cpu(), b.cpu())
+
