@@ -324,6 +324,22 @@ def run_gpu(args):
                    'max_abs_err_over_max_abs_vs_fp32_path': dict(zip(('node_cls', 'node_off', 'link_cls', 'obj_cls'), rel)),
                    'stated_tolerance': '5e-3 of each output tensor\'s largest magnitude (tests/test_model_gpu.py::test_reduced_precision_mode)',
                    'scope': 'edge encoder, 7 message kernels, stems / heads run single-pass; node encoder, node update and the per-cluster head stay 3xTF32'}
+    # SURVEY 8(d) C2, second graph: the radius-union adjacency of compute_adjacency_information_v2 (graph_features.py:87-114) on the
+    # same frames -- about twice the edges; graph build + forward like the headline step (rank 0, its own GPU)
+    union = None
+    if rank == 0:
+        def union_step():
+            bfu = gf.build_graph_batch(pts_dev, fp, EPS2, KNN, union_radius=True, max_range=GRID_MAX_R, max_azimuth=GRID_MAX_TH)
+            bfu.gb.cl_ptr, bfu.gb.cl_members, bfu.gb.n_clusters = cl_ptr, cl_members, n_clusters
+            with torch.no_grad():
+                det.forward_batch(bfu.gb, bfu.node_features, bfu.edge_features, training=False)
+            return bfu.gb.n_edges
+        e_union = union_step()
+        ms_union = timed_local(union_step, max(2, min(args.steps, 3)))
+        union = {'workload': 'the same 256 frames with the radius-union graph (kNN k=10 OR d^2 <= 25: compute_adjacency_information_v2)',
+                 'directed_edges_per_gpu': e_union, 'ms_per_step': ms_union / max(2, min(args.steps, 3)),
+                 'value': args.frames / (ms_union / max(2, min(args.steps, 3)) / 1e3), 'unit': 'frames/s (this GPU)',
+                 'edges_per_s': e_union / (ms_union / max(2, min(args.steps, 3)) / 1e3)}
     c1 = measure_c1(det, model, dev) if rank == 0 else None
     parity = parity_check(det, bf0, frames, fp, cl_lists, ref_out) if rank == 0 else None
     train = measure_train(dev, args, timed, rank, world) if not args.no_train else None
@@ -356,6 +372,7 @@ def run_gpu(args):
     line.update({k: dict(v, peak_source=which) for k, v in roof_extra.items()})
     line['reduced_precision'] = reduced
     line['c1_latency'] = c1
+    line['radius_union_graph'] = union
     line['parity_max_err'] = parity[0]
     line['parity'] = {'what': 'frame 0 of the bench batch, four outputs vs the float32 oracle; ratio to (1e-4 |want| + 1e-5 max|want|), <= 1 passes',
                       'max_abs_err': parity[1]}
