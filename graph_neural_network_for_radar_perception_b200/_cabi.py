@@ -85,6 +85,8 @@ SIGNATURES = {
     'rgnn_ffn_stack_bwd_workspace_bytes': (_SZ, [C.POINTER(rgnn_stack)]),
     'rgnn_ffn_stack_bwd': (_I, [C.POINTER(rgnn_stack), _V, _V, _I, _V, _V, _SZ, _V]),
     'rgnn_conv_block_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V]),
+    'rgnn_conv_block_bwd_workspace_bytes': (_SZ, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph)]),
+    'rgnn_conv_block_bwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_conv_edges_fwd': (_I, [C.POINTER(rgnn_conv), C.POINTER(rgnn_graph), _V, _V, _V, _V]),
     'rgnn_split_edge_embedding_words': (_SZ, [_I]),
     'rgnn_split_edge_embedding': (_I, [_V, _I, _V, _V]),

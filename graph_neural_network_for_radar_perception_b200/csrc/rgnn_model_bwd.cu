@@ -396,3 +396,51 @@ extern "C" int rgnn_detector_bwd(const rgnn_detector* net, const rgnn_graph* g, 
     return detector_bwd(*net, *g, node_features, edge_features, grad_node_cls, grad_node_off, grad_link_cls,
                         grad_obj_cls, pl, static_cast<cudaStream_t>(stream));
 }
+
+// ---------------------------------------------------------------------------------------------
+// Backward of ONE stand-alone residual_graph_conv_block (gnn_blocks.py:45-113 under torch autograd): the block-level modules of
+// the boundary are differentiable on their own (Model_Inference_v1-style compositions, unit tests of a single block).  Generic tile
+// programs on the CUDA cores for every channel plan of the training envelope; a training run goes through rgnn_detector_bwd, which
+// owns the fused tensor-core kernels.
+//   x (N, cn), e (E, ce) target-major, agg (N, cn) and proj (N, 2h) as rgnn_conv_block_fwd left them, d_out (N, cn)
+//   -> dx (N, cn), de (E, ce) target-major; parameter gradients are ACCUMULATED into blk's grad_* pointers
+// workspace: dagg (N, cn) | dP (N, 2h)
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t rgnn_conv_block_bwd_workspace_bytes(const rgnn_conv* blk, const rgnn_graph* g) {
+    using namespace rgnn;
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return 0;
+    return align256((size_t)g->n_nodes * d.cn * sizeof(float)) + align256((size_t)g->n_nodes * 2 * d.h * sizeof(float));
+}
+
+extern "C" int rgnn_conv_block_bwd(const rgnn_conv* blk, const rgnn_graph* g, const float* x, const float* e, const float* agg,
+                                   const float* proj, const float* d_out, float* dx, float* de, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+    using namespace rgnn;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ConvDims d;
+    if (!conv_dims(*blk, &d)) return RGNN_ERR_INVALID;
+    RGNN_REQUIRE(d.h <= 256 && d.cn <= 128, "conv_block_bwd: msg_mlp_hidden_dim %d / node width %d are outside the training envelope", d.h, d.cn);
+    RGNN_REQUIRE(workspace_bytes >= rgnn_conv_block_bwd_workspace_bytes(blk, g), "conv_block_bwd: workspace too small");
+    const int N = g->n_nodes;
+    float* dagg = static_cast<float*>(workspace);
+    float* dP = reinterpret_cast<float*>(static_cast<char*>(workspace) + align256((size_t)N * d.cn * sizeof(float)));
+    int rc;
+    // node update: dx <- d_out (identity residual) + upd backward w.r.t. x; dagg
+    RGNN_CHECK_CUDA(cudaMemcpyAsync(dx, d_out, (size_t)N * d.cn * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if ((rc = conv_nodes_bwd(*blk, d, N, x, agg, nullptr, nullptr, nullptr, dx, dagg, stream))) return rc;
+    // message function: dP (hoisted node half), de, weight gradients of msg.0's edge part / bias and of msg.1
+    if ((rc = conv_edges_bwd(*blk, d, *g, e, proj, dagg, dP, de, true, stream))) return rc;
+    // hoisted projection: dx += dP W_proj, dW_msg0[:, 0:2cn] += dP^T x
+    BwdBuilder b(N);
+    const int r_x = b.region(d.cn);
+    b.load_rows(r_x, x, d.cn, d.cn, 0, round_up(d.cn, 8));
+    const int r_tmp = b.region(round_up(d.cn, 64));
+    b.work_regions();
+    b.load_rows(b.wcur, dx, d.cn, d.cn, 0, round_up(d.cn, 8));
+    proj_bwd(b, *blk, d, dP, r_x, r_tmp);
+    b.store_rows(b.wcur, dx, d.cn, d.cn, 0, false, 0);
+    if (!b.ok) return RGNN_ERR_INVALID;
+    return launch_program(b.p, stream);
+}
+

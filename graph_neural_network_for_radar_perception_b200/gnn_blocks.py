@@ -15,7 +15,7 @@ from torch import nn
 
 from . import _cabi
 from ._cabi import check, lib, ptr, stream_ptr
-from ._engine import GraphBatch, ParamTable, apply_stack, stack_refs, _check_params, _f32c, _require_cuda
+from ._engine import GraphBatch, ParamTable, apply_stack, flat_grads, stack_refs, _check_params, _f32c, _require_cuda
 from .common import ffn_block
 from .constants import (_CLS_BIAS_INIT_, _HEAD_WEIGHT_MEAN_INIT_, _HEAD_WEIGHT_STD_INIT_, _REG_BIAS_INIT_)
 
@@ -45,41 +45,76 @@ class graph_feature_encoding(nn.Module):
         return apply_stack(x, list(self.encoder))
 
 
+def _build_conv(blk, device, grads=None):
+    """rgnn_conv struct of one block: parameter pointers, freshly packed weight images, optional gradient views."""
+    tab = ParamTable()
+    msg, upd = stack_refs(blk.msg), stack_refs(blk.upd)
+    cn = upd[-1].out_features
+    dims = (cn, msg[0].in_features - 2 * cn, msg[0].out_features)
+    conv = _cabi.rgnn_conv()
+    conv.msg.n, conv.upd.n = len(msg), len(upd)
+    slots_m = [tab.add(r, dims if i == 0 else None) for i, r in enumerate(msg)]
+    slots_u = [tab.add(r) for r in upd]
+    _check_params(tab.tensors)
+    packed = torch.empty(tab.packed_floats(), dtype=torch.float32, device=device)
+    off = 0
+    for i, s in enumerate(slots_m):
+        off += tab.fill(s, conv.msg.layer[i], packed, off, grads)
+    for i, s in enumerate(slots_u):
+        off += tab.fill(s, conv.upd.layer[i], packed, off, grads)
+    check(lib().rgnn_pack_conv(C.byref(conv), stream_ptr()), 'rgnn_pack_conv')
+    return tab, conv, packed, dims
+
+
 class _ConvBlockFn(torch.autograd.Function):
-    """Stand-alone residual_graph_conv_block forward (inference use).  Training goes through the
-    detector-level Function, which owns the backward."""
+    """Stand-alone residual_graph_conv_block: forward on the fused kernels, backward through rgnn_conv_block_bwd (generic tile
+    programs; a training run of the whole detector goes through the detector-level Function and its fused backward kernels).
+    `params` are the block's parameters in ParamTable order (msg stack, then upd stack: weight, bias, mu, std per layer)."""
 
     @staticmethod
     def forward(ctx, blk, gb: GraphBatch, x, e_tm, *params):
-        tab = ParamTable()
-        msg, upd = stack_refs(blk.msg), stack_refs(blk.upd)
-        cn = upd[-1].out_features
-        dims = (cn, msg[0].in_features - 2 * cn, msg[0].out_features)
-        conv = _cabi.rgnn_conv()
-        conv.msg.n, conv.upd.n = len(msg), len(upd)
-        slots_m = [tab.add(r, dims if i == 0 else None) for i, r in enumerate(msg)]
-        slots_u = [tab.add(r) for r in upd]
-        _check_params(tab.tensors)
-        packed = torch.empty(tab.packed_floats(), dtype=torch.float32, device=x.device)
-        off = 0
-        for i, s in enumerate(slots_m):
-            off += tab.fill(s, conv.msg.layer[i], packed, off, None)
-        for i, s in enumerate(slots_u):
-            off += tab.fill(s, conv.upd.layer[i], packed, off, None)
+        tab, conv, packed, dims = _build_conv(blk, x.device)
         st = stream_ptr()
-        check(lib().rgnn_pack_conv(C.byref(conv), st), 'rgnn_pack_conv')
         out = torch.empty_like(x)
         agg = torch.empty_like(x)
         proj = torch.empty((x.shape[0], 2 * dims[2]), dtype=torch.float32, device=x.device)
         g = gb.c_struct()
         check(lib().rgnn_conv_block_fwd(C.byref(conv), C.byref(g), ptr(x), ptr(e_tm), ptr(out), ptr(agg), ptr(proj), st),
               'rgnn_conv_block_fwd')
+        ctx.blk, ctx.gb = blk, gb
+        ctx.save_for_backward(x, e_tm, agg, proj, *params)
         return out
 
     @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError('stand-alone residual_graph_conv_block has no backward; train through '
-                                  'Model_Training / Model_Inference (detector-level backward)')
+    def backward(ctx, g_out):
+        x, e_tm, agg, proj = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
+        needs = list(ctx.needs_input_grad[4:])
+        flat, views = flat_grads(params, needs)
+        tab, conv, packed, dims = _build_conv(ctx.blk, x.device, views)
+        if [t.data_ptr() for t in tab.tensors] != [p.data_ptr() for p in params]:
+            raise _cabi.RgnnError('residual_graph_conv_block: parameters moved between forward and backward')
+        g = ctx.gb.c_struct()
+        dx = torch.empty_like(x)
+        de = torch.empty_like(e_tm)
+        nbytes = lib().rgnn_conv_block_bwd_workspace_bytes(C.byref(conv), C.byref(g))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+        check(lib().rgnn_conv_block_bwd(C.byref(conv), C.byref(g), ptr(x), ptr(e_tm), ptr(agg), ptr(proj), ptr(_f32c(g_out)),
+                                        ptr(dx), ptr(de), ptr(ws), nbytes, stream_ptr()), 'rgnn_conv_block_bwd')
+        return (None, None, dx, de) + tuple(views)
+
+
+def _conv_params(blk):
+    """The block's parameters in ParamTable order (what _build_conv registers), so that the gradient views line up."""
+    tab = ParamTable()
+    msg, upd = stack_refs(blk.msg), stack_refs(blk.upd)
+    cn = upd[-1].out_features
+    dims = (cn, msg[0].in_features - 2 * cn, msg[0].out_features)
+    for i, r in enumerate(msg):
+        tab.add(r, dims if i == 0 else None)
+    for r in upd:
+        tab.add(r)
+    return list(tab.tensors)
 
 
 class residual_graph_conv_block(nn.Module):
@@ -112,7 +147,7 @@ class residual_graph_conv_block(nn.Module):
         _require_cuda(node_features, edge_features, edge_index)
         gb = GraphBatch.from_edge_index(edge_index, node_features.shape[0])
         e_tm = _f32c(edge_features).index_select(0, gb.perm[:gb.n_edges].long()) if gb.n_edges else _f32c(edge_features)
-        params = [p for p in self.parameters()]
+        params = _conv_params(self)
         return _ConvBlockFn.apply(self, gb, _f32c(node_features), e_tm, *params)
 
 

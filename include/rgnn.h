@@ -196,6 +196,14 @@ size_t rgnn_ffn_stack_bwd_workspace_bytes(const rgnn_stack* stack);
 int rgnn_conv_block_fwd(const rgnn_conv* blk, const rgnn_graph* g, const float* x, const float* e,
                         float* out, float* agg, float* proj, void* stream);
 
+/* Backward of ONE stand-alone block (torch autograd over gnn_blocks.py:45-113): x, e (target-major), and agg / proj exactly as
+ * rgnn_conv_block_fwd left them; d_out (n_nodes, cn) -> dx (n_nodes, cn), de (n_edges, ce, target-major); parameter gradients are
+ * ACCUMULATED into blk's grad_* pointers.  Generic tile programs (every channel plan of the training envelope); a training run of the
+ * detector goes through rgnn_detector_bwd, which owns the fused tensor-core kernels. */
+size_t rgnn_conv_block_bwd_workspace_bytes(const rgnn_conv* blk, const rgnn_graph* g);
+int rgnn_conv_block_bwd(const rgnn_conv* blk, const rgnn_graph* g, const float* x, const float* e, const float* agg, const float* proj,
+                        const float* d_out, float* dx, float* de, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The message + aggregation half of the block alone (MessagePassing.propagate, gnn_blocks.py:106-113):
  * agg[t] = sum over edges s->t of msg(x_t, x_s, e); proj = the hoisted node projections written by
  * rgnn_conv_block_fwd (or by the previous block).  This is the dominant kernel of the forward; bench.py times it. */

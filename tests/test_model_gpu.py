@@ -60,6 +60,38 @@ def test_blocks_standalone_match_oracle(ckpt_state_dict):
         assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), 'conv block')
 
 
+def test_standalone_conv_block_backward_matches_oracle_autograd(ckpt_state_dict):
+    """residual_graph_conv_block used on its own under torch autograd (rgnn_conv_block_bwd): gradients w.r.t. x, the edge features
+    (caller's edge order) and every parameter of the block against float64 autograd of the oracle, on a random unsorted edge list."""
+    from oracle import model_torch as mt
+    torch.manual_seed(11)
+    m = load_model(ckpt_state_dict).pred.train()
+    blk = m.pass_messages.conv_blk[2]
+    stem = 'pred.pass_messages.conv_blk.2'
+    n, ne = 700, 6000
+    x, e = torch.randn(n, 64), torch.randn(ne, 64)
+    ei = torch.randint(0, n, (2, ne))
+    w = torch.randn(n, 64) / 8          # loss = sum(out * w)
+    xg, eg = x.cuda().requires_grad_(True), e.cuda().requires_grad_(True)
+    for p_ in blk.parameters():
+        p_.grad = None
+    out = blk(xg, eg, ei.cuda())
+    (out * w.cuda()).sum().backward()
+    sd64 = {k: v.double().requires_grad_(k.startswith(stem)) for k, v in ckpt_state_dict.items()}
+    x64, e64 = x.double().requires_grad_(True), e.double().requires_grad_(True)
+    (mt.conv_block(sd64, stem, x64, e64, ei) * w.double()).sum().backward()
+
+    def close(got, want, what):
+        want = want.numpy()
+        assert_close(got.detach().cpu().numpy(), want, 2e-4, 2e-5 * max(np.abs(want).max(), 1e-12), what)
+    close(xg.grad, x64.grad, 'dL/dx')
+    close(eg.grad, e64.grad, 'dL/de')
+    names = dict(blk.named_parameters())
+    assert len(names) == 12
+    for k, p_ in names.items():
+        close(p_.grad, sd64[f'{stem}.{k}'].grad, k)
+
+
 @pytest.mark.parametrize('n,e,layer', [(5000, 100_000, 0), (1500, 151_555, 3), (40_000, 420_000, 6)])
 def test_conv_block_many_tiles_per_cta_matches_oracle(ckpt_state_dict, n, e, layer):
     """The persistent message kernel in its steady state: 780 - 3 280 tiles of 128 edges over 148 CTAs (5 - 22 tiles per CTA,
