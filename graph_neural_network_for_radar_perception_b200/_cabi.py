@@ -104,6 +104,8 @@ SIGNATURES = {
     'rgnn_cluster_proposals': (_I, [_V, _V, _V, _I, _V, _V, _I, _V, _V, _V, _V, _V, _V]),
     'rgnn_accumulate_workspace_bytes': (_SZ, [_I]),
     'rgnn_accumulate_windows': (_I, [_V] * 13 + [_I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float] + [_V] * 11 + [_V, _SZ, _V]),
+    'rgnn_segment_max_fwd': (_I, [_V, _I, _V, _V, _I, _V, _V, _V]),
+    'rgnn_segment_max_bwd': (_I, [_V, _V, _I, _I, _I, _V, _V]),
     'rgnn_detector_obj_head': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _SZ, _I, _V]),
     'rgnn_detector_bwd': (_I, [C.POINTER(rgnn_detector), C.POINTER(rgnn_graph), _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     'rgnn_wgrad': (_I, [_V, _I, _I, _V, _I, _I, C.c_longlong, _V, _V, _V, _V]),

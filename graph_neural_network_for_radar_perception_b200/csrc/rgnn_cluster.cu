@@ -252,3 +252,63 @@ extern "C" int rgnn_cluster_proposals(const float* px, const float* py, const fl
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Per-cluster max over member rows (object_classification used on its own, gnn_blocks.py:384-386: torch.max(x[idx], dim=0) per cluster):
+// one warp per cluster, lane = channel (mod 32); the row that supplied each maximum (first in member order on ties) is kept for the
+// backward, which routes d pooled to exactly that row like autograd of torch.max(dim).  The detector-level forward fuses this
+// reduction into the class-head kernel; this is the block-level API path.
+// ---------------------------------------------------------------------------------------------
+namespace rgnn {
+__global__ void segment_max_kernel(const float* __restrict__ x, int W, const int* __restrict__ cl_ptr, const int* __restrict__ members,
+                                   int n_clusters, float* __restrict__ pooled, int* __restrict__ argrow) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n_clusters; c += gridDim.x * wpb) {
+        const int m0 = __ldg(cl_ptr + c), m1 = __ldg(cl_ptr + c + 1);
+        for (int col = lane; col < W; col += 32) {
+            float best = -INFINITY;
+            int arg = -1;
+            for (int m = m0; m < m1; ++m) {
+                const int r = __ldg(members + m);
+                const float v = __ldg(x + (size_t)r * W + col);
+                if (v > best || arg < 0) { best = v; arg = r; }       // first maximum in member order; NaN-free inputs
+            }
+            pooled[(size_t)c * W + col] = best;
+            if (argrow != nullptr) argrow[(size_t)c * W + col] = arg;
+        }
+    }
+}
+__global__ void segment_max_bwd_kernel(const float* __restrict__ d_pooled, const int* __restrict__ argrow, long long total, int W,
+                                       float* __restrict__ dx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(argrow + i);
+        if (r >= 0) atomicAdd(dx + (size_t)r * W + (int)(i % W), __ldg(d_pooled + i));      // clusters may share nodes: accumulate
+    }
+}
+}  // namespace rgnn
+
+extern "C" int rgnn_segment_max_fwd(const float* x, int width, const int32_t* cl_ptr, const int32_t* cl_members, int n_clusters,
+                                    float* pooled, int32_t* argrow, void* stream_) {
+    using namespace rgnn;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_clusters <= 0) return RGNN_OK;
+    RGNN_REQUIRE(width >= 1, "segment_max: width %d", width);
+    const int wpb = 8;
+    const int blocks = (n_clusters + wpb - 1) / wpb;
+    segment_max_kernel<<<blocks > 8 * 148 ? 8 * 148 : blocks, 32 * wpb, 0, stream>>>(x, width, cl_ptr, cl_members, n_clusters, pooled, argrow);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}
+
+extern "C" int rgnn_segment_max_bwd(const float* d_pooled, const int32_t* argrow, int n_clusters, int width, int n_rows, float* dx,
+                                    void* stream_) {
+    using namespace rgnn;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RGNN_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_rows * width * sizeof(float), stream));
+    const long long total = (long long)n_clusters * width;
+    if (total <= 0) return RGNN_OK;
+    const long long blocks = (total + 255) / 256;
+    segment_max_bwd_kernel<<<(unsigned)(blocks > 8 * 148 ? 8 * 148 : blocks), 256, 0, stream>>>(d_pooled, argrow, total, width, dx);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
+}

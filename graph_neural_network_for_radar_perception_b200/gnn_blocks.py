@@ -265,6 +265,30 @@ class link_predictions(nn.Module):
         return apply_stack(u, list(self.stem) + list(self.pred_cls.head))
 
 
+class _SegMaxFn(torch.autograd.Function):
+    """pooled[c] = max over the member rows of cluster c (rgnn_segment_max_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, g, cl_ptr, cl_members, n_clusters):
+        _require_cuda(g)
+        g = _f32c(g)
+        pooled = torch.empty((n_clusters, g.shape[1]), dtype=torch.float32, device=g.device)
+        arg = torch.empty((max(n_clusters, 1), g.shape[1]), dtype=torch.int32, device=g.device)
+        check(lib().rgnn_segment_max_fwd(ptr(g), g.shape[1], ptr(cl_ptr), ptr(cl_members), n_clusters, ptr(pooled), ptr(arg),
+                                         stream_ptr()), 'rgnn_segment_max_fwd')
+        ctx.save_for_backward(arg)
+        ctx.shape = (g.shape[0], g.shape[1], n_clusters)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        (arg,) = ctx.saved_tensors
+        n, w, c = ctx.shape
+        dx = torch.empty((n, w), dtype=torch.float32, device=d_pooled.device)
+        check(lib().rgnn_segment_max_bwd(ptr(_f32c(d_pooled)), ptr(arg), c, w, n, ptr(dx), stream_ptr()), 'rgnn_segment_max_bwd')
+        return dx, None, None, None
+
+
 class object_classification(nn.Module):
     """Per-cluster class logits: stem on nodes, max-pool over cluster members, head (reference :347-389)."""
 
@@ -277,12 +301,9 @@ class object_classification(nn.Module):
     def forward(self, x: torch.Tensor, cluster_node_idx: List[torch.Tensor]):
         g = apply_stack(x, list(self.stem))
         # stand-alone API path (the detector-level forward fuses the segment-max into the head kernel)
-        lens = [int(c.shape[0]) for c in cluster_node_idx]
-        members = torch.cat([c.to(g.device) for c in cluster_node_idx])
-        seg = torch.repeat_interleave(torch.arange(len(lens), device=g.device),
-                                      torch.tensor(lens, device=g.device))
-        pooled = torch.full((len(lens), g.shape[1]), float('-inf'), device=g.device, dtype=g.dtype)
-        pooled = pooled.index_reduce(0, seg, g.index_select(0, members), 'amax', include_self=True)
+        gb = GraphBatch()
+        gb.set_clusters([list(cluster_node_idx)], [0], g.device)
+        pooled = _SegMaxFn.apply(g, gb.cl_ptr, gb.cl_members, gb.n_clusters)
         return apply_stack(pooled, list(self.pred_cls.head))
 
 

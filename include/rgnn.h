@@ -304,6 +304,14 @@ int rgnn_accumulate_windows(const float* x_cc, const float* y_cc, const float* v
                             float* class_labels, int32_t* src_index, uint8_t* stationary_flag, int32_t* out_ptr_dev,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-cluster max over member rows for object_classification used on its own (gnn_blocks.py:384-386: torch.max(x[idx], dim=0) per
+ * cluster).  x (n_rows, width); pooled (n_clusters, width); argrow (n_clusters, width) receives the row that supplied each maximum
+ * (first in member order on ties; nullable).  The backward zero-fills dx (n_rows, width) and routes d_pooled to those rows, like
+ * autograd of torch.max(dim).  The detector-level forward fuses this reduction into the class-head kernel. */
+int rgnn_segment_max_fwd(const float* x, int width, const int32_t* cl_ptr, const int32_t* cl_members, int n_clusters,
+                         float* pooled, int32_t* argrow, void* stream);
+int rgnn_segment_max_bwd(const float* d_pooled, const int32_t* argrow, int n_clusters, int width, int n_rows, float* dx, void* stream);
+
 /* predict_class on clusters found after the forward pass: the per-node stem output of predict_class is still in the
  * workspace of the preceding rgnn_detector_fwd call on the same graph (same `training` flag); g carries the new
  * cl_ptr / cl_members / n_clusters.  obj_cls (n_clusters, n_classes). */

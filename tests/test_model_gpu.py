@@ -60,6 +60,31 @@ def test_blocks_standalone_match_oracle(ckpt_state_dict):
         assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), 'conv block')
 
 
+def test_standalone_object_head_segment_max_matches_torch(ckpt_state_dict):
+    """object_classification used on its own (gnn_blocks.py:347-389): the per-cluster max (rgnn_segment_max_fwd / _bwd) against
+    torch.max(x[idx], dim=0) per cluster as the reference writes it, values and the gradient routed to the arg-max rows."""
+    torch.manual_seed(3)
+    m = load_model(ckpt_state_dict).pred.train()
+    head = m.predict_class
+    n = 500
+    x = torch.randn(n, 64)
+    perm = torch.randperm(n)
+    cuts = [0, 1, 2, 40, 41, 300, 500]
+    clusters = [perm[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    xg = x.cuda().requires_grad_(True)
+    out = head(xg, [c.cuda() for c in clusters])
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    from graph_neural_network_for_radar_perception_b200._engine import apply_stack
+    xr = x.cuda().requires_grad_(True)
+    g = apply_stack(xr, list(head.stem))
+    pooled = torch.stack([torch.max(g[c.cuda()], dim=0)[0] for c in clusters])
+    ref = apply_stack(pooled, list(head.pred_cls.head))
+    (ref * w).sum().backward()
+    assert torch.equal(out, ref)
+    assert_close(xg.grad.cpu().numpy(), xr.grad.cpu().numpy(), 1e-5, 1e-7, 'dL/dx through the segment max')
+
+
 def test_standalone_conv_block_backward_matches_oracle_autograd(ckpt_state_dict):
     """residual_graph_conv_block used on its own under torch autograd (rgnn_conv_block_bwd): gradients w.r.t. x, the edge features
     (caller's edge order) and every parameter of the block against float64 autograd of the oracle, on a random unsorted edge list."""
