@@ -453,7 +453,19 @@ class DetectorFn(torch.autograd.Function):
         params = ctx.saved_tensors[2:]
         needs = list(ctx.needs_input_grad[5:])
         table = detector_table(ctx.model)
-        flat, views = flat_grads(params, needs)
+        # DataParallelTrainer installs a gradient sink: views of its flat gradient buffer, keyed by parameter storage.  The kernels
+        # accumulate straight into them and autograd gets no per-parameter gradients to add (184 tiny kernels per step otherwise).
+        sink = getattr(ctx.model, '_rgnn_grad_sink', None)
+        # only while every needed parameter's .grad still IS its view of that buffer (a zero_grad(set_to_none=True) or a foreign
+        # optimizer in between falls back to ordinary autograd accumulation)
+        live = table.tab.tensors
+        direct = sink is not None and len(live) == len(params) and all(
+            (not n) or (p.data_ptr() in sink and q.grad is not None and q.grad.data_ptr() == sink[p.data_ptr()].data_ptr())
+            for p, q, n in zip(params, live, needs))
+        if direct:
+            views = [sink[p.data_ptr()] if n else None for p, n in zip(params, needs)]
+        else:
+            flat, views = flat_grads(params, needs)
         table.refill(views)
         s = stream_ptr()
         g = ctx.gb.c_struct()
@@ -473,6 +485,8 @@ class DetectorFn(torch.autograd.Function):
                                       ptr(g_link), ptr(g_obj), ptr(ctx.ws), ctx.nbytes, s), 'rgnn_detector_bwd')
         table.refill(None)
         ctx.ws = None
+        if direct:
+            return (None, None, None, None, None) + (None,) * len(params)
         return (None, None, None, None, None) + tuple(views)
 
 
