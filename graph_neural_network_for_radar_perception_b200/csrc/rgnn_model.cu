@@ -1,5 +1,6 @@
 // Host side of the model entry points: weight packing and the forward tile programs of the detector.
 #include "rgnn_model.h"
+#include "rgnn_pack.cuh"
 
 namespace rgnn {
 
@@ -457,8 +458,11 @@ extern "C" int rgnn_pack_conv(const rgnn_conv* c, void* stream) {
 
 extern "C" int rgnn_pack_detector(const rgnn_detector* net, void* stream) {
     Packer pk(static_cast<cudaStream_t>(stream));
+    if (g_pack_batch) packq_begin(static_cast<cudaStream_t>(stream));        // ~214 per-image launches -> a handful (rgnn_pack.cuh)
     pk.stack(net->node_enc);
     pk.stack(net->edge_enc);
+    // edge_enc_f16_pack REWRITES layer 1's fp16 image in four K blocks: what the generic packer queued for it must be launched first
+    if (pk.rc == RGNN_OK) pk.rc = packq_flush();
     if (pk.rc == RGNN_OK) pk.rc = edge_enc_f16_pack(net->edge_enc, static_cast<cudaStream_t>(stream));
     for (int l = 0; l < net->n_conv; ++l) pk.conv(net->conv[l]);
     pk.stack(net->head_node);
@@ -468,6 +472,10 @@ extern "C" int rgnn_pack_detector(const rgnn_detector* net, void* stream) {
     pk.stack(net->class_node);
     pk.stack(net->head_class);
     pk.flush();
+    {
+        const int rq = packq_end();
+        if (pk.rc == RGNN_OK) pk.rc = rq;
+    }
     return pk.rc;
 }
 

@@ -34,6 +34,7 @@
 // stagers, blocking MMA lanes) only paid once the F role stopped waiting for its own loads.
 #include "rgnn_f16.cuh"
 #include "rgnn_model.h"
+#include "rgnn_pack.cuh"
 #include "rgnn_tc_rows.cuh"
 #include "rgnn_tile.cuh"
 
@@ -677,19 +678,14 @@ __global__ void emb_split_f16_kernel(const float* __restrict__ emb, uint32_t* __
     }
 }
 
-// weights: element (n, k) = W[off + n * sn + k * sk], x 256 -> fp16 hi / lo chunk-major images [K/8][N][8]
-__global__ void pack_split_f16_kernel(const float* __restrict__ W, int off, int sn, int sk, int K, int N, int n_valid, int k_valid,
-                                      __half* __restrict__ hi, __half* __restrict__ lo) {
-    const int tot = K * N;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
-        const int q = i & 7, n = (i >> 3) % N, kc = (i >> 3) / N;
-        const float w = (n < n_valid && 8 * kc + q < k_valid) ? W[(size_t)off + (size_t)n * sn + (size_t)(8 * kc + q) * sk] * f16::W_SCALE : 0.f;
-        const uint32_t h2 = f16::pack_sat(w, 0.f);
-        const float hf = f16::unpack(h2).x;
-        const uint32_t l2 = f16::pack_sat(w - hf, 0.f);
-        hi[i] = __ushort_as_half((unsigned short)(h2 & 0xFFFFu));
-        lo[i] = __ushort_as_half((unsigned short)(l2 & 0xFFFFu));
-    }
+// weights: element (n, k) = W[off + n * sn + k * sk], x 256 -> fp16 hi / lo chunk-major images [K/8][N][8] (rgnn_pack.cuh)
+__global__ void pack_split_f16_kernel(const PackF16Args a) { pack_f16_body(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
+static int launch_pack_f16(const PackF16Args& a, int blocks, cudaStream_t stream) {
+    if (packq_push(a)) return RGNN_OK;          // inside rgnn_pack_detector: batched
+    pack_split_f16_kernel<<<blocks, 256, 0, stream>>>(a);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
 }
 
 static int g_f16_fwd = 1;
@@ -708,19 +704,16 @@ int mp_f16_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t 
     const rgnn_linear& m1 = c.msg.layer[1];
     __half* w = reinterpret_cast<__half*>(dst);
     const int W1 = d.ce * d.h, W2 = d.h * d.cn;
-    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, m0.in_features, 1, d.ce, d.h, d.h, d.ce, w, w + W1);
-    pack_split_f16_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, m1.in_features, 1, d.h, d.cn, d.cn, d.h, w + 2 * W1, w + 2 * W1 + W2);
-    RGNN_CHECK_CUDA(cudaGetLastError());
-    return RGNN_OK;
+    int rc = launch_pack_f16({m0.weight, w, w + W1, 2 * d.cn, m0.in_features, 1, d.ce, d.h, d.h, d.ce}, 16, stream);
+    if (rc) return rc;
+    return launch_pack_f16({m1.weight, w + 2 * W1, w + 2 * W1 + W2, 0, m1.in_features, 1, d.h, d.cn, d.cn, d.h}, 16, stream);
 }
 
 // (K x N) image pair of one Linear for the f16 kernels: element (n, k) = W[n * ldw + k] (n < n_valid, k < k_valid, else 0)
 int pack_f16_image(const float* W, int ldw, int K, int N, int n_valid, int k_valid, uint32_t* dst, cudaStream_t stream) {
     __half* w = reinterpret_cast<__half*>(dst);
     const int blocks = (K * N + 255) / 256;
-    pack_split_f16_kernel<<<blocks > 32 ? 32 : blocks, 256, 0, stream>>>(W, 0, ldw, 1, K, N, n_valid, k_valid, w, w + (size_t)K * N);
-    RGNN_CHECK_CUDA(cudaGetLastError());
-    return RGNN_OK;
+    return launch_pack_f16({W, w, w + (size_t)K * N, 0, ldw, 1, K, N, n_valid, k_valid}, blocks > 32 ? 32 : blocks, stream);
 }
 
 int mp_f16_split_emb(const float* emb, int n_edges, uint32_t* out, cudaStream_t stream) {

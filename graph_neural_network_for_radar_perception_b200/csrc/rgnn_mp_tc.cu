@@ -16,6 +16,7 @@
 // is accumulated in fp32 by the tensor core (relative error ~2^-21 per product); `passes = 1` keeps only the
 // hi*hi term (plain TF32, documented tolerance).
 #include "rgnn_model.h"
+#include "rgnn_pack.cuh"
 #include "rgnn_tc.cuh"
 #include "rgnn_tile.cuh"
 #include "rgnn_tc_rows.cuh"
@@ -591,17 +592,13 @@ teardown:
 // ---------------------------------------------------------------------------------------------
 // weight packing: element (n, k) = W[off + n * sn + k * sk] -> hi/lo chunk-major operands [K/4][N][4]
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_split_kernel(const float* __restrict__ W, int off, int sn, int sk, int K, int N, float* __restrict__ hi,
-                                  float* __restrict__ lo) {
-    const int tot = K * N;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
-        const int q = i & 3, n = (i >> 2) % N, kc = (i >> 2) / N;
-        const float w = W[(size_t)off + (size_t)n * sn + (size_t)(4 * kc + q) * sk];
-        float h, l;
-        tc::split_tf32(w, h, l);
-        hi[i] = h;
-        lo[i] = l;
-    }
+__global__ void pack_split_kernel(const PackSplitArgs a) { pack_split_body(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
+static int launch_pack_split(const PackSplitArgs& a, cudaStream_t stream) {
+    if (packq_push(a)) return RGNN_OK;          // inside rgnn_pack_detector: batched (rgnn_pack.cuh)
+    pack_split_kernel<<<16, 256, 0, stream>>>(a);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    return RGNN_OK;
 }
 
 int g_use_tensor_cores_flag() { return g_use_tensor_cores; }
@@ -623,10 +620,11 @@ int mp_tc_pack(const rgnn_conv& c, const ConvDims& d, float* dst, cudaStream_t s
     float* w2 = w1 + 2 * W1;         // (n = i, k = h)  = msg.1.weight[i][h]
     float* w2t = w2 + 2 * W2;        // (n = h, k = i)  = msg.1.weight[i][h]         (d y1 = dz2 W_2)
     float* w1t = w2t + 2 * W2;       // (n = c, k = h)  = msg.0.weight[h][2cn + c]   (d emb = dz1 W_e)
-    pack_split_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, m0.in_features, 1, d.ce, d.h, w1, w1 + W1);
-    pack_split_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, m1.in_features, 1, d.h, d.cn, w2, w2 + W2);
-    pack_split_kernel<<<16, 256, 0, stream>>>(m1.weight, 0, 1, m1.in_features, d.cn, d.h, w2t, w2t + W2);
-    pack_split_kernel<<<16, 256, 0, stream>>>(m0.weight, 2 * d.cn, 1, m0.in_features, d.h, d.ce, w1t, w1t + W1);
+    int rcp = launch_pack_split({m0.weight, w1, w1 + W1, 2 * d.cn, m0.in_features, 1, d.ce, d.h}, stream);
+    if (rcp == RGNN_OK) rcp = launch_pack_split({m1.weight, w2, w2 + W2, 0, m1.in_features, 1, d.h, d.cn}, stream);
+    if (rcp == RGNN_OK) rcp = launch_pack_split({m1.weight, w2t, w2t + W2, 0, 1, m1.in_features, d.cn, d.h}, stream);
+    if (rcp == RGNN_OK) rcp = launch_pack_split({m0.weight, w1t, w1t + W1, 2 * d.cn, 1, m0.in_features, d.h, d.ce}, stream);
+    if (rcp) return rcp;
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }
@@ -693,6 +691,7 @@ extern "C" int rgnn_set_option(const char* name, int value) {
     if (name != nullptr && strcmp(name, "tensor_cores") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0 && (value == 0 || value == 1)) { g_use_tensor_cores_bwd = value; return RGNN_OK; }
     if (name != nullptr && strcmp(name, "wgrad_tma") == 0 && (value == 0 || value == 1)) { g_wgrad_tma = value; return RGNN_OK; }
+    if (name != nullptr && strcmp(name, "pack_batch") == 0 && (value == 0 || value == 1)) { g_pack_batch = value; return RGNN_OK; }
     if (name != nullptr && mp_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && mp_bwd_f16_set_option(name, value)) return RGNN_OK;
     if (name != nullptr && graph_set_option(name, value)) return RGNN_OK;
@@ -710,6 +709,7 @@ extern "C" int rgnn_get_option(const char* name) {
     if (name != nullptr && strcmp(name, "tensor_cores") == 0) return g_use_tensor_cores;
     if (name != nullptr && strcmp(name, "tensor_cores_bwd") == 0) return g_use_tensor_cores_bwd;
     if (name != nullptr && strcmp(name, "wgrad_tma") == 0) return g_wgrad_tma;
+    if (name != nullptr && strcmp(name, "pack_batch") == 0) return g_pack_batch;
     if (name != nullptr && mp_f16_get_option(name) != -2) return mp_f16_get_option(name);
     if (name != nullptr && mp_bwd_f16_get_option(name) != -2) return mp_bwd_f16_get_option(name);
     if (name != nullptr && graph_get_option(name) != -2) return graph_get_option(name);

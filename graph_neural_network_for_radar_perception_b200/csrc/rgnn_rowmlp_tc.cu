@@ -8,6 +8,7 @@
 // arrive when the next A operand is in TMEM.
 #include <type_traits>
 
+#include "rgnn_pack.cuh"
 #include "rgnn_rowmlp_tc.cuh"
 #include "rgnn_tc_rows.cuh"
 #include "rgnn_tile.cuh"
@@ -800,29 +801,16 @@ int launch_rowmlp_tc(const TcProgram& pg, cudaStream_t stream) {
 // weight packing for the chunk stream: rows [n0, n0+Nt) x columns [k0 + c*kc, ...) of W (row stride ldW) ->
 // per K chunk:  hi (kc/4, Np, 4)  |  lo (kc/4, Np, 4),   zero padded to Np rows / Kp columns
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_tc_kernel(const float* __restrict__ W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp,
-                               int kc, int n_loop, float* __restrict__ dst, int transpose) {
-    const int tot = Kp * n_loop;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
-        const int k = i / n_loop, n = i - k * n_loop;
-        float w = 0.f;
-        if (k < Kt && n < Nt) w = transpose ? W[(size_t)(k0 + k) * ldW + n0 + n] : W[(size_t)(n0 + n) * ldW + k0 + k];
-        float h, l;
-        tc::split_tf32(w, h, l);
-        const int chunk = k / kc, kk = k - chunk * kc;
-        float* base = dst + (size_t)chunk * (2 * kc * Np);
-        const int off = ((kk >> 2) * Np + nd0 + n) * 4 + (kk & 3);
-        base[off] = h;
-        base[kc * Np + off] = l;
-    }
-}
+__global__ void pack_tc_kernel(const PackTcArgs a) { pack_tc_body(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
 // transpose: the packed layer is W^T (element (n, k) = W[k0 + k][n0 + n])
 int pack_tc(const float* W, int ldW, int n0, int Nt, int nd0, int Np, int k0, int Kt, int Kp, int kc, bool pad_rows, float* dst,
             cudaStream_t stream, bool transpose) {
     const int n_loop = pad_rows ? Np - nd0 : Nt;
     const int blocks = (Kp * n_loop + 255) / 256;
-    pack_tc_kernel<<<blocks > 64 ? 64 : blocks, 256, 0, stream>>>(W, ldW, n0, Nt, nd0, Np, k0, Kt, Kp, kc, n_loop, dst, transpose ? 1 : 0);
+    const PackTcArgs a{W, dst, ldW, n0, Nt, nd0, Np, k0, Kt, Kp, kc, n_loop, transpose ? 1 : 0};
+    if (packq_push(a)) return RGNN_OK;          // inside rgnn_pack_detector: one table-driven launch for many images (rgnn_pack.cuh)
+    pack_tc_kernel<<<blocks > 64 ? 64 : blocks, 256, 0, stream>>>(a);
     RGNN_CHECK_CUDA(cudaGetLastError());
     return RGNN_OK;
 }

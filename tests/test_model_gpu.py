@@ -60,6 +60,30 @@ def test_blocks_standalone_match_oracle(ckpt_state_dict):
         assert_close(a.numpy(), b.numpy(), RTOL, scaled_atol(b, 2e-5), 'conv block')
 
 
+def test_batched_packing_is_bit_identical(ckpt_state_dict):
+    """rgnn_pack_detector with the batched pack queue (one table-driven launch per kind and 48 images, csrc/rgnn_pack.cuh) writes the
+    same bytes as one launch per image: entries of a batch run concurrently, so this also guards the one image that is written
+    twice (layer 1 of the edge encoder, re-packed in K blocks)."""
+    from graph_neural_network_for_radar_perception_b200._cabi import check, lib, stream_ptr
+    from graph_neural_network_for_radar_perception_b200._engine import detector_table
+    m = load_model(ckpt_state_dict).pred.eval()
+    table = detector_table(m)
+    images = []
+    try:
+        for batched in (0, 1, 1, 0):
+            check(lib().rgnn_set_option(b'pack_batch', batched), 'opt')
+            table.packed.fill_(123.0)
+            table.invalidate_packed()
+            table.ensure_packed(stream_ptr())
+            torch.cuda.synchronize()
+            images.append(table.packed.view(torch.int32).clone())
+    finally:
+        check(lib().rgnn_set_option(b'pack_batch', 1), 'opt')
+    assert (images[0] != 123.0).any()
+    for im in images[1:]:
+        assert torch.equal(im, images[0])
+
+
 def test_standalone_object_head_segment_max_matches_torch(ckpt_state_dict):
     """object_classification used on its own (gnn_blocks.py:347-389): the per-cluster max (rgnn_segment_max_fwd / _bwd) against
     torch.max(x[idx], dim=0) per cluster as the reference writes it, values and the gradient routed to the arg-max rows."""
