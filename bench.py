@@ -546,6 +546,26 @@ def measure_c1(det, model, dev):
             labels[k].append(torch.from_numpy(lab[k]).to(dev))
     with torch.no_grad():
         out['training_forward_8_frames_100_points_ms'] = lat(lambda: model(nf_l, ef_l, ei_l, [None] * 8, labels))
+    # the same 8 small frames through a whole optimisation step (pack_batch + DataParallelTrainer.step: forward, losses, backward,
+    # SGD; a fresh copy of the model, its parameters are re-homed in the trainer's flat buffers); steps are issued back to back
+    from graph_neural_network_for_radar_perception_b200 import config as _config, Model_Training as _MT
+    from graph_neural_network_for_radar_perception_b200.training import DataParallelTrainer
+    m2 = _MT(_config(), dev)
+    m2.load_state_dict(model.state_dict())
+    m2 = m2.to(dev).train()
+    trainer = DataParallelTrainer(m2, lr=1e-5)
+
+    def train_step():
+        gb, x, e = m2.pack_batch(nf_l, ef_l, ei_l, labels['cluster_node_idx'])
+        trainer.step(gb, x, e, labels)
+    for _ in range(5):
+        train_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        train_step()
+    torch.cuda.synchronize()
+    out['training_step_8_frames_100_points_ms'] = 1e3 * (time.perf_counter() - t0) / 50
     return out
 
 
