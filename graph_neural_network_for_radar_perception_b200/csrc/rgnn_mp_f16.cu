@@ -63,7 +63,7 @@ namespace mpf {
 constexpr int CE = 64, H = 128, CN = 64, TM = 128;
 // warp groups (4 warps each): E1 x 2 (each owns half of the columns of every tile), E2 x 2 (+ segmented sum), F, aux x 2 (2 MMA issue warps + 6 stagers)
 constexpr int NTHREADS = 896;
-constexpr int WG_E1 = 0, WG_E2 = 2, WG_F = 4, WG_AUX = 5;      // E2 group g (warpgroup WG_E2 + g) owns the tiles of parity g
+constexpr int WG_E2 = 2, WG_F = 4, WG_AUX = 5;         // warpgroups 0, 1: E1;      // E2 group g (warpgroup WG_E2 + g) owns the tiles of parity g
 constexpr int NSTAGER = 6;
 constexpr int W1_WORDS = CE * H / 2, W2_WORDS = H * CN / 2;         // 32-bit words per (hi or lo) image
 constexpr int OFF_W = 0;                                            // words: W_e hi | lo | W_2 hi | lo
