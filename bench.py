@@ -405,6 +405,18 @@ def _traffic_from_profile(n_edges, n_nodes):
     return t['dram_bytes'] * alg_here / alg_there
 
 
+def _traffic_entry(key, n_edges, n_nodes, per_edge, per_node):
+    """Same for the other captured kernels (`edge_enc`: the inference edge encoder; `bwd`: mp_edge_bwd_f16_kernel + dproj_gather_kernel of one
+    conv block), scaled by the algorithmic bytes per_edge * E + per_node * N."""
+    path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path)).get(key)
+    if not t:
+        return None
+    return t['dram_bytes'] * (per_edge * n_edges + per_node * n_nodes) / (per_edge * t['n_edges'] + per_node * t.get('n_nodes', 0))
+
+
 def measure_roofline(det, bf, dev, steps, hbm, tf):
     """Roofline entries with SURVEY.md section 8(d)'s ALGORITHMIC figures (fp32 storage, int32 indices, weights counted once):
       per conv layer forward   B_f = 512 N + 260 E bytes,  F_f = 65 536 E + 16 384 N FLOP   (message path alone: 65 536 E)
@@ -485,12 +497,14 @@ def measure_roofline(det, bf, dev, steps, hbm, tf):
                              'ms_per_launch': ms_edge_1p, 'layer_ms': ms_layer_1p, 'layer_frac': gbs(B_f, ms_layer_1p) / hbm, 'traffic': None},
         'roofline_rowmlp': {'kernel': 'edge_enc_f16_kernel (graph_feature_encoding of the edges, 7-256-128-128-64)', 'bound': 'tensor',
                             'achieved': tfs(2 * 59136.0 * E, ms_enc), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * 59136.0 * E, ms_enc) / tf,
-                            'ms_per_launch': ms_enc, 'algorithmic_bytes': 284.0 * E, 'traffic': None},
+                            'ms_per_launch': ms_enc, 'algorithmic_bytes': 284.0 * E, 'traffic': _traffic_entry('edge_enc', E, N, 284.0, 0.0)},
         'roofline_bwd': {'kernel': 'message backward of one conv block: absmax_kernel + mp_edge_bwd_f16_kernel (recompute + dgrad + both weight gradients fused, '
                                    'fp16-split x 3 passes) + dproj_gather_kernel',
                          'bound': 'tensor', 'achieved': tfs(2 * F_msg, ms_bwd), 'peak': tf, 'unit': 'TFLOP/s', 'frac': tfs(2 * F_msg, ms_bwd) / tf,
                          'ms': ms_bwd, 'hbm_view': {'algorithmic_bytes': B_b, 'GBps': gbs(B_b, ms_bwd), 'frac_of_hbm': gbs(B_b, ms_bwd) / hbm},
-                         'traffic': None},
+                         'traffic': _traffic_entry('bwd', E, N, 772.0, 768.0),
+                         'traffic_note': 'the 512 B / edge of dz1 written by the fused kernel and read twice by dproj_gather_kernel put the traffic '
+                                         'at ~2.3 x the algorithmic bytes'},
     }
     return main, extra
 

@@ -44,6 +44,7 @@ struct Chain64Args {
     float* save_y[C64_MAX_LAYERS];
     float* save_sd[C64_MAX_LAYERS];
     int passes;
+    int prefetch;               // input rows of the next tile are requested into L2 one tile ahead (pair mode: indices two tiles ahead)
 };
 
 namespace c64 {
@@ -110,6 +111,17 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
         // =========================== epilogue groups ===========================
         const uint32_t t_base = tmem + ((uint32_t)w4 << 21) + (uint32_t)g * 128;    // this group's 128 columns, this warp's lanes
         uint32_t uses = 0;          // completed phases of this group's barriers (one per MMA group)
+        const bool pf = a.prefetch != 0;
+        auto idx_of = [&](const int* ix, int jj) -> int {
+            const long long rq = ((long long)blockIdx.x + (long long)jj * G) * TM + row;
+            return (jj < my_tiles && rq < a.n_rows) ? __ldg(ix + rq) : -1;
+        };
+        auto prefetch_row = [&](const float* q) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
+        };
+        int a1 = -1, b1 = -1, a2 = -1, b2 = -1;     // pair mode: indices of this group's next tile / the one after
+        if (pf && a.in_mode == 1) { a1 = idx_of(a.ia, g); b1 = idx_of(a.ib, g); a2 = idx_of(a.ia, g + NGROUPS); b2 = idx_of(a.ib, g + NGROUPS); }
         for (int j = g; j < my_tiles; j += NGROUPS) {
             const int tile = (int)blockIdx.x + j * G;
             const int r = tile * TM + row;
@@ -119,11 +131,23 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
                 const float* pa = a.x;
                 const float* pb = nullptr;
                 if (a.in_mode == 1) {
-                    const int na = valid ? __ldg(a.ia + r) : 0, nb = valid ? __ldg(a.ib + r) : 0;
+                    int na, nb;
+                    if (pf) {
+                        na = valid ? a1 : 0; nb = valid ? b1 : 0;
+                        a1 = a2; b1 = b2;
+                        if (a1 >= 0) { prefetch_row(a.x + (size_t)a1 * a.ldx); prefetch_row(a.x + (size_t)b1 * a.ldx); }
+                        a2 = idx_of(a.ia, j + 2 * NGROUPS); b2 = idx_of(a.ib, j + 2 * NGROUPS);
+                    } else {
+                        na = valid ? __ldg(a.ia + r) : 0; nb = valid ? __ldg(a.ib + r) : 0;
+                    }
                     pa = a.x + (size_t)na * a.ldx;
                     pb = a.x + (size_t)nb * a.ldx;
                 } else {
                     pa = a.x + (size_t)(valid ? r : 0) * a.ldx;
+                    if (pf) {
+                        const long long rn = (long long)r + (long long)NGROUPS * G * TM;
+                        if (rn < a.n_rows) prefetch_row(a.x + (size_t)rn * a.ldx);
+                    }
                 }
                 const float2 s16 = make_float2(f16::A_SCALE, f16::A_SCALE);
 #pragma unroll 1
@@ -314,11 +338,17 @@ __global__ void __launch_bounds__(c64::NTHREADS, 1) chain64_f16_kernel(const __g
 // host side
 // ---------------------------------------------------------------------------------------------
 static int g_chain_f16 = 1;
+static int g_rows_prefetch = 1;     // row-owning kernels request their next tile's rows into L2 one tile ahead (prefetch.global.L2)
 int chain_f16_set_option(const char* name, int value) {
     if (strcmp(name, "f16_chain") == 0 && (value == 0 || value == 1)) { g_chain_f16 = value; return 1; }
+    if (strcmp(name, "rows_prefetch") == 0 && (value == 0 || value == 1)) { g_rows_prefetch = value; return 1; }
     return 0;
 }
-int chain_f16_get_option(const char* name) { return strcmp(name, "f16_chain") == 0 ? g_chain_f16 : -2; }
+int chain_f16_get_option(const char* name) {
+    if (strcmp(name, "f16_chain") == 0) return g_chain_f16;
+    if (strcmp(name, "rows_prefetch") == 0) return g_rows_prefetch;
+    return -2;
+}
 
 // floats appended to a Linear's packed buffer for its fp16 image pair (0: the layer has none)
 size_t f16_image_floats(int in_features, int out_features) {
@@ -378,6 +408,7 @@ int run_chain64(const rgnn_stack& s, const float* x, int ldx, const int* ia, con
         for (int l = 0; l < a.n_hidden; ++l) { a.save_y[l] = (l + 1 < s.n) ? save->y[l] : nullptr; a.save_sd[l] = save->sd[l]; }
     }
     a.passes = mp_f16_passes();
+    a.prefetch = g_rows_prefetch;
     static PerDeviceOnce once;
     if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(chain64_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c64::SMEM));
@@ -418,6 +449,7 @@ struct ConvNodesArgs {
     float* u_save;              // training: the update's output before the residual (N, 64) and its sigma (N), or nullptr
     float* sd_save;
     int passes;
+    int prefetch;
 };
 
 namespace cnn {
@@ -488,6 +520,17 @@ __global__ void __launch_bounds__(cnn::NTHREADS, 1) conv_nodes_f16_kernel(const 
             const int r = tile * TM + row;
             const bool valid = r < a.n_rows;
             const size_t rr = valid ? (size_t)r : 0;
+            if (a.prefetch) {       // this group's next tile: its x / agg rows start their way from HBM to L2 one tile ahead
+                const long long rn = (long long)r + (long long)NGROUPS * G * TM;
+                if (rn < a.n_rows) {
+                    const float* px = a.x + (size_t)rn * 64;
+                    const float* pa = a.agg + (size_t)rn * 64;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 32));
+                }
+            }
             // ---- cat(x, agg) -> A operand (x 16, hi | lo per 32 columns) ----
 #pragma unroll 1
             for (int c = 0; c < 128; c += 32) {
@@ -688,6 +731,7 @@ int run_conv_nodes_f16(const rgnn_conv& c, const ConvDims& d, int n_nodes, const
     }
     a.u_save = u_save; a.sd_save = sd_save;
     a.passes = mp_f16_passes();
+    a.prefetch = g_rows_prefetch;
     static PerDeviceOnce once;
     if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(conv_nodes_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn::SMEM));

@@ -36,6 +36,7 @@ struct EdgeEncArgs {
     float* save_y1; float* save_y2;                         // training: outputs of layers 1 / 2 (E, 128) and the three sigmas (E), nullable
     float* save_sd1; float* save_sd2; float* save_sd3;
     int passes;
+    int prefetch;               // feature rows of the next tile are requested into L2 one tile ahead (their perm entry two tiles ahead)
 };
 
 namespace een {
@@ -196,6 +197,16 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
         uint32_t* a0 = smem_u + OFF_A0 + g * A0_WORDS;          // [hi: 2 chunks x 128 rows x 16 B | lo: same]
         uint32_t n_d0[2] = {0, 0}, n_d = 0, n_arr = 0;         // completed phases of this group's barriers / operands handed over
         const bool n1 = a.s1 != nullptr, n2 = a.s2 != nullptr, n3 = a.s3 != nullptr;
+        // The feature row of an edge is reached through perm: two dependent trips to HBM at the head of every tile of this group's
+        // serial chain.  With `prefetch` the perm entries run two tiles ahead in registers and the feature row of the next tile is
+        // requested into L2 while this tile is evaluated, so the head of a tile costs one L2 round trip.
+        const bool pf = a.prefetch != 0 && a.perm != nullptr;
+        auto perm_of = [&](int jj) -> int {
+            const long long rq = ((long long)blockIdx.x + (long long)jj * G) * TM + row;
+            return (jj < my_tiles && rq < a.n_rows) ? __ldg(a.perm + rq) : -1;
+        };
+        int p1 = -1, p2 = -1;               // perm entries of this group's next tile / the one after
+        if (pf) { p1 = perm_of(g); p2 = perm_of(2 + g); }
         for (int t = 0; t < n_pairs; ++t) {
             const int j = 2 * t + g;
             const int tile = (int)blockIdx.x + j * G;
@@ -206,8 +217,18 @@ __global__ void __launch_bounds__(een::NTHREADS, 1) edge_enc_f16_kernel(const __
                 float f[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = 0.f;
+                const int p0 = p1;
+                if (pf) {
+                    p1 = p2;
+                    if (p1 >= 0) {
+                        const float* q = a.feat + (size_t)p1 * a.n_feat;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + a.n_feat - 1));      // a 28-byte row can straddle two lines
+                    }
+                    p2 = perm_of(j + 4);
+                }
                 if (valid) {
-                    const size_t fr = a.perm != nullptr ? (size_t)__ldg(a.perm + r) : (size_t)r;
+                    const size_t fr = pf ? (size_t)p0 : (a.perm != nullptr ? (size_t)__ldg(a.perm + r) : (size_t)r);
 #pragma unroll
                     for (int k = 0; k < 7; ++k)
                         if (k < a.n_feat) f[k] = __ldg(a.feat + fr * a.n_feat + k) * f16::A_SCALE;
@@ -484,6 +505,7 @@ int run_edge_enc_f16(const rgnn_stack& s, const float* feat, const int* perm, in
         a.save_sd1 = save->sd[1]; a.save_sd2 = save->sd[2]; a.save_sd3 = save->sd[3];
     }
     a.passes = mp_f16_passes();
+    a.prefetch = chain_f16_get_option("rows_prefetch");
     static PerDeviceOnce once;
     if (once.needed()) {
         RGNN_CHECK_CUDA(cudaFuncSetAttribute(edge_enc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)een::SMEM));

@@ -44,6 +44,9 @@ const char* rgnn_last_error(void);
  *   "f16_fwd" / "f16_bwd" / "f16_node_bwd" / "f16_edge_enc"  1 (default) = the fixed-shape fp16-split kernels of round 2; 0 = the round-1 kernels
  *   "f16_passes"   3 (default) = hi/lo split products, fp32-equivalent; 1 = plain fp16 operands, fp32 accumulate (reduced precision:
  *                  5e-3 of each output's largest magnitude, tests/test_model_gpu.py; never the default)
+ *   "f16_chain"    1 (default) = fixed-shape fp16-split kernels for the 64-wide stems / heads / node update; 0 = the row-MLP interpreter
+ *   "rows_prefetch" 1 (default) = row-owning kernels (node update, 64-wide chains, edge encoder) request the next tile's input rows into
+ *                  L2 one tile ahead (prefetch.global.L2; results unchanged); 0 = off (A/B aid)
  *   "f16_stagers"  2 .. 6 (default 6) staging warps of the forward message kernel (developer aid: profiles/README.md)
  *   "debug"        bit mask of developer aids: 8 = per-role cycle counters / event timeline of the message kernels (synchronises)
  * rgnn_get_option returns -1 for an unknown name. */

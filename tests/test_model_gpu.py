@@ -237,6 +237,34 @@ def test_reduced_precision_mode_stated_tolerance(ckpt_state_dict):
     assert lib().rgnn_get_option(b'f16_passes') == 3
 
 
+def test_rows_prefetch_is_bit_identical(ckpt_state_dict):
+    """rgnn_set_option("rows_prefetch", 0 / 1): the next-tile L2 prefetch of the row-owning kernels (node update, 64-wide chains, edge
+    encoder) is a hint, the four outputs must not change in a single bit.  32 x 3000 points = 96 k nodes / 1.17 M edges: every CTA of
+    the node kernels runs several tiles per group (the prefetch and the two-tiles-ahead index registers are live), and the last tiles are
+    ragged."""
+    from graph_neural_network_for_radar_perception_b200 import graph_features as gf, synth
+    from graph_neural_network_for_radar_perception_b200._cabi import check, lib
+    m = load_model(ckpt_state_dict).pred.eval()
+    base = [synth.make_frame(700 + i, 3000 - 7 * i, knn=10)[0] for i in range(4)]
+    frames = [base[i % 4] for i in range(32)]
+    pts, fp = gf.frames_to_device(frames)
+    R = np.float64(np.sqrt(100.0 ** 2 + 50.0 ** 2))
+    bf = gf.build_graph_batch(pts, fp, 25, 10, max_range=R, max_azimuth=np.pi * 0.5)
+    bf.gb.set_clusters([[torch.arange(i, min(i + 5, n)) for i in range(0, n, 5)] for n in np.diff(fp)], fp[:-1], 'cuda')
+    outs = {}
+    try:
+        for v in (0, 1):
+            check(lib().rgnn_set_option(b'rows_prefetch', v), 'opt')
+            with torch.no_grad():
+                outs[v] = [o.clone() for o in m.forward_batch(bf.gb, bf.node_features, bf.edge_features)]
+    finally:
+        check(lib().rgnn_set_option(b'rows_prefetch', 1), 'opt')
+    assert lib().rgnn_get_option(b'rows_prefetch') == 1
+    for a, b in zip(outs[0], outs[1]):
+        assert a.shape == b.shape and a.numel() > 0 and torch.isfinite(a).all()
+        assert torch.equal(a, b)
+
+
 def test_conv_layer_entry_points_match_oracle(ckpt_state_dict):
     """The layer-level C-ABI entries bench.py times (rgnn_split_edge_embedding, rgnn_conv_layer_f16_fwd): one residual conv
     block on a random symmetric-free edge list == oracle conv_block, plus the next block's hoisted projection."""
