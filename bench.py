@@ -340,7 +340,7 @@ def run_gpu(args):
                  'directed_edges_per_gpu': e_union, 'ms_per_step': ms_union / max(2, min(args.steps, 3)),
                  'value': args.frames / (ms_union / max(2, min(args.steps, 3)) / 1e3), 'unit': 'frames/s (this GPU)',
                  'edges_per_s': e_union / (ms_union / max(2, min(args.steps, 3)) / 1e3)}
-    c1 = measure_c1(det, model, dev) if rank == 0 else None
+    c1 = measure_c1(det, model, dev, train_step=(world == 1)) if rank == 0 else None
     parity = parity_check(det, bf0, frames, fp, cl_lists, ref_out) if rank == 0 else None
     train = measure_train(dev, args, timed, rank, world) if not args.no_train else None
     clocks = sampler.stop() if rank == 0 else None
@@ -509,7 +509,7 @@ def measure_roofline(det, bf, dev, steps, hbm, tf):
     return main, extra
 
 
-def measure_c1(det, model, dev):
+def measure_c1(det, model, dev, train_step=True):
     """The reference's own calling convention (one frame at a time, modules/inference/output.py:88-94; lists of small frames
     in Model_Training.forward): host + device latency in ms, median of 20 calls, everything a caller pays included
     (int64 edge_index -> CSR, cluster lists, weight images cached).  C1 = BASELINE.json configs[0]'s frame shape."""
@@ -560,6 +560,8 @@ def measure_c1(det, model, dev):
             labels[k].append(torch.from_numpy(lab[k]).to(dev))
     with torch.no_grad():
         out['training_forward_8_frames_100_points_ms'] = lat(lambda: model(nf_l, ef_l, ei_l, [None] * 8, labels))
+    if not train_step:      # rank 0 alone is here: under torchrun the trainer's all-reduce would wait for ranks that never come (1-GPU figure only)
+        return out
     # the same 8 small frames through a whole optimisation step (pack_batch + DataParallelTrainer.step: forward, losses, backward,
     # SGD; a fresh copy of the model, its parameters are re-homed in the trainer's flat buffers); steps are issued back to back
     from graph_neural_network_for_radar_perception_b200 import config as _config, Model_Training as _MT
