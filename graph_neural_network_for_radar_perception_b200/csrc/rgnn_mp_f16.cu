@@ -797,6 +797,7 @@ int mp_f16_set_option(const char* name, int value) {
 int mp_f16_get_option(const char* name) {
     if (strcmp(name, "f16_fwd") == 0) return g_f16_fwd;
     if (strcmp(name, "f16_passes") == 0) return g_f16_passes;
+    if (strcmp(name, "f16_stagers") == 0) return g_f16_stagers;
     return -2;
 }
 

@@ -78,3 +78,26 @@ def test_unsupported_configurations_raise():
         ffn_block(8, 8, 'relu')
     with pytest.raises(NotImplementedError):
         ffn_block(8, 8, 'leakyrelu', norm_layer='layer_normalization')
+
+
+def test_options_are_host_state_with_loud_rejection():
+    """rgnn_set_option / rgnn_get_option (include/rgnn.h) are pure host state: every documented name reads back its default, a
+    value outside the documented set and an unknown name are rejected with an error message, and nothing changes."""
+    from graph_neural_network_for_radar_perception_b200._cabi import lib
+    L = lib()
+    defaults = {b'tf32_passes': 3, b'tensor_cores': 1, b'tensor_cores_bwd': 1, b'f16_fwd': 1, b'f16_bwd': 1, b'f16_node_bwd': 1,
+                b'f16_edge_enc': 1, b'f16_passes': 3, b'f16_chain': 1, b'rows_prefetch': 1, b'f16_stagers': 6, b'pack_batch': 1}
+    for name, want in defaults.items():
+        assert L.rgnn_get_option(name) == want, name
+    assert L.rgnn_get_option(b'no_such_option') == -1
+    assert L.rgnn_set_option(b'no_such_option', 1) != 0
+    assert b'no_such_option' in L.rgnn_last_error()
+    for name, bad in ((b'f16_passes', 2), (b'rows_prefetch', 2), (b'f16_stagers', 1), (b'tf32_passes', 0)):
+        assert L.rgnn_set_option(name, bad) != 0, name
+        assert L.rgnn_get_option(name) == defaults[name], name
+    try:
+        assert L.rgnn_set_option(b'rows_prefetch', 0) == 0 and L.rgnn_get_option(b'rows_prefetch') == 0
+        assert L.rgnn_set_option(b'f16_stagers', 4) == 0 and L.rgnn_get_option(b'f16_stagers') == 4
+    finally:
+        assert L.rgnn_set_option(b'rows_prefetch', 1) == 0
+        assert L.rgnn_set_option(b'f16_stagers', 6) == 0
